@@ -1,0 +1,126 @@
+// Shared device/host helpers for the dcfa_b200 kernel library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dcfa_b200.h"
+
+namespace dcfa {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (api.cu owns the storage)
+// ---------------------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+#define DCFA_CHECK_LAUNCH(name)                                                         \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return dcfa::fail(DCFA_E_CUDA, "%s launch failed: %s", name, \
+                                              cudaGetErrorString(e__));                 \
+    dcfa::count_launch();                                                               \
+  } while (0)
+
+#define DCFA_REQUIRE(cond, ...)                                        \
+  do {                                                                 \
+    if (!(cond)) return dcfa::fail(DCFA_E_INVALID, __VA_ARGS__);       \
+  } while (0)
+
+// A resolved activation view (device pointer + strides in elements).
+template <typename T>
+struct View {
+  T* p;
+  int64_t img_stride;
+  int64_t gstride;
+  int ld;
+  int gi;
+  __host__ __device__ __forceinline__ int64_t img_off(int n) const {
+    if (gi <= 0) return (int64_t)n * img_stride;
+    int g = n / gi;
+    return (int64_t)(n - g * gi) * img_stride + (int64_t)g * gstride;
+  }
+};
+
+template <typename T>
+static inline View<T> resolve(const dcfa_view& v, void* const* bufs) {
+  View<T> r;
+  r.p = (v.buf < 0) ? nullptr : reinterpret_cast<T*>(static_cast<char*>(bufs[v.buf]) + v.off);
+  r.img_stride = v.img_stride;
+  r.gstride = v.gstride;
+  r.ld = v.ld;
+  r.gi = v.gi;
+  return r;
+}
+
+template <typename T>
+static inline T* resolve_ptr(const dcfa_view& v, void* const* bufs) {
+  return (v.buf < 0) ? nullptr : reinterpret_cast<T*>(static_cast<char*>(bufs[v.buf]) + v.off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == DCFA_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == DCFA_ACT_SILU) return v * sigmoid_fast(v);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+
+// 8 bf16 <-> 8 floats through one 128-bit word
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg128(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// launchers implemented in the individual .cu files (host side; bufs already resolved by the caller)
+int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_cbam_pool(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_cbam_mlp(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_cbam_stats(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_cbam_apply(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_maxpool5(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_upsample(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_dfl(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+
+}  // namespace dcfa

@@ -1,0 +1,311 @@
+// dcfa_nms: DecodeBox.non_max_suppression (utils/utils_bbox.py:87-168) without its per-image Python loop
+// and its three host synchronisations, bit-exact in the kept indices.
+//
+//   nms_prepare  xywh -> xyxy in place (:92-97), class max with "first max wins" (:106), conf >= thr (:111),
+//                one 64-bit sort key per anchor:  class(8) | ~orderable(conf)(32) | anchor(24)
+//                (non-candidates get the all-ones sentinel).
+//   nms_sort     one CTA per image, bitonic sort of the keys (shared memory up to 16384 keys, global above):
+//                ascending key order == classes ascending (:130,:136), scores descending, ties by lower
+//                anchor index -- exactly torch's stable descending sort that torchvision.ops.nms uses.
+//   nms_greedy   one CTA per image.  Sorted candidates are processed in chunks of 64: the chunk's 64x64
+//                suppression bits are computed in parallel, resolved serially by one thread, and only the
+//                KEPT boxes of the chunk are then tested against all later candidates.  This equals the
+//                greedy scan of torchvision (only kept boxes ever suppress) at O(kept * n) instead of O(n^2).
+//
+// IoU arithmetic follows torchvision.ops.nms, the un-vendored dependency the reference calls at :145:
+//   DCFA_IOU_TV_CPU   areas rounded separately, (double)iou > thr          (torchvision/csrc/ops/cpu/nms_kernel.cpp)
+//   DCFA_IOU_TV_CUDA  Sa + Sb evaluated as fma(wb, hb, Sa), iou > (float)thr (SASS of torchvision 0.26.0+cu128
+//                     nms_kernel_impl<float> for sm_100: FMUL, FFMA, FADD, IEEE divide, FSETP.GT on F2F.F32.F64(thr))
+// All box arithmetic uses _rn intrinsics so nvcc cannot contract anything else.
+#include "common.cuh"
+
+namespace dcfa {
+namespace {
+
+constexpr uint64_t kSentinel = ~0ull;
+constexpr int kNmsThreads = 1024;
+constexpr int kChunk = 64;
+constexpr int kSmemSortMax = 16384;
+
+__device__ __forceinline__ uint32_t orderable(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct PrepArgs {
+  float* pred;
+  uint64_t* keys;
+  int B, A, Apad, nc;
+  float conf_thres;
+};
+
+__global__ void __launch_bounds__(256) nms_prepare_kernel(const PrepArgs p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)p.B * p.Apad) return;
+  const int b = (int)(i / p.Apad);
+  const int a = (int)(i - (int64_t)b * p.Apad);
+  uint64_t key = kSentinel;
+  if (a < p.A) {
+    float* row = p.pred + ((int64_t)b * p.A + a) * (4 + p.nc);
+    const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    row[0] = __fsub_rn(cx, hw);
+    row[1] = __fsub_rn(cy, hh);
+    row[2] = __fadd_rn(cx, hw);
+    row[3] = __fadd_rn(cy, hh);
+    float best = row[4];
+    int bi = 0;
+    for (int c = 1; c < p.nc; ++c) {
+      const float v = row[4 + c];
+      if (best != best) break;                    // torch.max propagates NaN
+      if (v > best || v != v) { best = v; bi = c; }
+    }
+    if (best >= p.conf_thres) {                   // false for NaN
+      const float conf = best + 0.0f;             // -0.0 -> +0.0 (equal under torch.sort)
+      key = ((uint64_t)bi << 56) | ((uint64_t)(~orderable(conf)) << 24) | (uint64_t)a;
+    }
+  }
+  p.keys[i] = key;
+}
+
+struct SortArgs {
+  uint64_t* keys;  // [B][Apad]
+  int Apad;
+  int use_smem;
+};
+
+__global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p) {
+  extern __shared__ uint64_t s_keys[];
+  uint64_t* g = p.keys + (int64_t)blockIdx.x * p.Apad;
+  uint64_t* k = p.use_smem ? s_keys : g;
+  const int N = p.Apad;
+  if (p.use_smem) {
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) s_keys[i] = g[i];
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= N; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = k[i], b = k[ixj];
+          const bool asc = (i & kk) == 0;
+          if ((a > b) == asc) { k[i] = b; k[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (p.use_smem) {
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) g[i] = s_keys[i];
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool suppresses(const float4& a, const float4& b, float thr_f, double thr_d) {
+  // a = earlier (higher score) box, b = later box; both (x1, y1, x2, y2)
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.0f), h = fmaxf(__fsub_rn(bottom, top), 0.0f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float wb = __fsub_rn(b.z, b.x), hb = __fsub_rn(b.w, b.y);
+  if (MODE == DCFA_IOU_TV_CUDA) {
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fmaf_rn(wb, hb, sa), inter));
+    return iou > thr_f;
+  } else {
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, __fmul_rn(wb, hb)), inter));
+    return (double)iou > thr_d;
+  }
+}
+
+struct GreedyArgs {
+  const float* pred;     // xyxy already
+  const uint64_t* keys;  // sorted
+  float4* sbox;          // [B][A] scratch: boxes in sorted order
+  float* out_det;
+  int32_t* out_idx;
+  int32_t* out_cnt;
+  int32_t* out_cand;
+  int B, A, Apad, nc;
+  float thr_f;
+  double thr_d;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArgs p) {
+  extern __shared__ uint8_t s_removed[];  // [A]
+  __shared__ float4 c_box[kChunk];
+  __shared__ int c_cls[kChunk];
+  __shared__ unsigned long long c_mask[kChunk];
+  __shared__ float4 k_box[kChunk];
+  __shared__ int k_cls[kChunk];
+  __shared__ int s_kc, s_total, s_n;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint64_t* keys = p.keys + (int64_t)b * p.Apad;
+  const float* pred = p.pred + (int64_t)b * p.A * (4 + p.nc);
+  float4* sbox = p.sbox + (int64_t)b * p.A;
+
+  // number of candidates = keys below the sentinel (they are sorted first)
+  int cnt = 0;
+  for (int i = tid; i < p.A; i += kNmsThreads) cnt += (keys[i] != kSentinel) ? 1 : 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (tid == 0) { s_n = 0; s_total = 0; }
+  __syncthreads();
+  if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
+  __syncthreads();
+  const int n = s_n;
+  for (int j = tid; j < n; j += kNmsThreads) {
+    const int a = (int)(keys[j] & 0xFFFFFFull);
+    const float* row = pred + (int64_t)a * (4 + p.nc);
+    sbox[j] = make_float4(row[0], row[1], row[2], row[3]);
+    s_removed[j] = 0;
+  }
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += kChunk) {
+    const int cn = min(kChunk, n - c0);
+    // (1) stage the chunk
+    int alive = 0;
+    if (tid < kChunk) {
+      c_mask[tid] = 0ull;
+      if (tid < cn) {
+        c_box[tid] = sbox[c0 + tid];
+        c_cls[tid] = (int)(keys[c0 + tid] >> 56);
+        alive = s_removed[c0 + tid] ? 0 : 1;
+      }
+    }
+    const int any_alive = __syncthreads_or(alive);
+    if (!any_alive) continue;  // uniform: every box of the chunk is already suppressed
+    // (2) 64x64 suppression bits, 4 pairs per thread: bit i of c_mask[j] <=> box i (earlier) suppresses box j
+    {
+      const int j = tid >> 4;           // 0..63
+      const int i0 = (tid & 15) << 2;   // 0,4,..,60
+      if (j < cn) {
+        unsigned long long bits = 0ull;
+        const float4 bj = c_box[j];
+        const int cj = c_cls[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+          if (i < j && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d)) bits |= 1ull << i;
+        }
+        if (bits) atomicOr(&c_mask[j], bits);
+      }
+    }
+    __syncthreads();
+    // (3) serial resolution of the chunk by one thread
+    if (tid == 0) {
+      unsigned long long keep = 0ull;
+      int kc = 0;
+      const int base = s_total;
+      for (int j = 0; j < cn; ++j) {
+        if (s_removed[c0 + j]) continue;
+        if (c_mask[j] & keep) { s_removed[c0 + j] = 1; continue; }
+        keep |= 1ull << j;
+        k_box[kc] = c_box[j];
+        k_cls[kc] = c_cls[j];
+        const uint64_t key = keys[c0 + j];
+        const int a = (int)(key & 0xFFFFFFull);
+        const int pos = base + kc;
+        float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
+        const float4 bx = c_box[j];
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[j]];
+        o[5] = (float)c_cls[j];
+        p.out_idx[(int64_t)b * p.A + pos] = a;
+        ++kc;
+      }
+      s_kc = kc;
+      s_total = base + kc;
+    }
+    __syncthreads();
+    // (4) kept boxes of this chunk suppress later candidates
+    const int kc = s_kc;
+    if (kc > 0) {
+      for (int j = c0 + kChunk + tid; j < n; j += kNmsThreads) {
+        if (s_removed[j]) continue;
+        const float4 bj = sbox[j];
+        const int cj = (int)(keys[j] >> 56);
+        for (int k = 0; k < kc; ++k) {
+          if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { s_removed[j] = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.out_cnt[b] = s_total;
+    if (p.out_cand) p.out_cand[b] = n;
+  }
+}
+
+int next_pow2(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+}  // namespace
+}  // namespace dcfa
+
+extern "C" int64_t dcfa_nms_workspace_bytes(int B, int A) {
+  if (B <= 0 || A <= 0) return 0;
+  const int64_t apad = dcfa::next_pow2(A);
+  return (int64_t)B * apad * 8 + (int64_t)B * A * 16 + 256;
+}
+
+extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, double nms_thres, int iou_mode,
+                        float* out_det, int32_t* out_idx, int32_t* out_cnt, int32_t* out_cand, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  using namespace dcfa;
+  cudaStream_t st = (cudaStream_t)stream;
+  DCFA_REQUIRE(pred && out_det && out_idx && out_cnt && workspace, "nms: null pointer");
+  DCFA_REQUIRE(B > 0 && A > 0 && nc > 0, "nms: bad sizes B=%d A=%d nc=%d", B, A, nc);
+  DCFA_REQUIRE(nc <= 256, "nms: nc %d > 256 unsupported", nc);
+  DCFA_REQUIRE(A <= 65536, "nms: A %d > 65536 unsupported", A);
+  DCFA_REQUIRE(iou_mode == DCFA_IOU_TV_CPU || iou_mode == DCFA_IOU_TV_CUDA, "nms: bad iou_mode %d", iou_mode);
+  DCFA_REQUIRE(workspace_bytes >= dcfa_nms_workspace_bytes(B, A), "nms: workspace too small");
+  DCFA_REQUIRE(((uintptr_t)workspace % 16) == 0, "nms: workspace must be 16-byte aligned");
+  const int Apad = next_pow2(A);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(workspace);
+  float4* sbox = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + (int64_t)B * Apad * 8);
+
+  PrepArgs pa{pred, keys, B, A, Apad, nc, conf_thres};
+  const int64_t tot = (int64_t)B * Apad;
+  nms_prepare_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pa);
+  DCFA_CHECK_LAUNCH("nms_prepare_kernel");
+
+  SortArgs sa{keys, Apad, Apad <= kSmemSortMax ? 1 : 0};
+  const size_t sort_smem = sa.use_smem ? (size_t)Apad * 8 : 0;
+  static bool attr_sort = false, attr_g0 = false, attr_g1 = false;
+  if (!attr_sort) {
+    cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSortMax * 8);
+    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(sort): %s", cudaGetErrorString(e));
+    attr_sort = true;
+  }
+  nms_sort_kernel<<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa);
+  DCFA_CHECK_LAUNCH("nms_sort_kernel");
+
+  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, B, A, Apad, nc, (float)nms_thres, nms_thres};
+  const size_t g_smem = (size_t)((A + 15) / 16) * 16;
+  if (iou_mode == DCFA_IOU_TV_CUDA) {
+    if (!attr_g1) {
+      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16);
+      if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
+      attr_g1 = true;
+    }
+    nms_greedy_kernel<DCFA_IOU_TV_CUDA><<<(unsigned)B, kNmsThreads, g_smem, st>>>(ga);
+  } else {
+    if (!attr_g0) {
+      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16);
+      if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
+      attr_g0 = true;
+    }
+    nms_greedy_kernel<DCFA_IOU_TV_CPU><<<(unsigned)B, kNmsThreads, g_smem, st>>>(ga);
+  }
+  DCFA_CHECK_LAUNCH("nms_greedy_kernel");
+  return DCFA_OK;
+}

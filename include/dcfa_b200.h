@@ -1,0 +1,197 @@
+/*
+ * dcfa_b200 -- C ABI of the B200 (sm_100a) kernel library behind the DCFA-YOLO
+ * dual-channel inference hot path.
+ *
+ * The reference (heitieya/DCFA-YOLO) has no FFI: its boundary is the Python
+ * class API of three modules.  Each entry point / op kind below names the
+ * reference code it replaces (file:line under the reference root):
+ *
+ *   DCFA_OP_STEM        nets/yolo_mul.py:104-115   Conv_maxpool (conv3x3+BN+ReLU+maxpool3/2)
+ *   DCFA_OP_CONV        nets/yolo_mul.py:190-204   Conv (conv+BN+SiLU); nets/repghost.py:291-305;
+ *                       nets/yolo_mul.py:138-151   ShuffleNetV2 1x1 convs (+BN+ReLU);
+ *                       nets/repghost.py:80-84     RepGhostModule.primary_conv;
+ *                       nets/yolo_mul.py:388-391   head cv2/cv3 (incl. final biased 1x1, fp32 NCHW out)
+ *   DCFA_OP_DWCONV      nets/yolo_mul.py:144-146   ShuffleNetV2 depthwise 3x3 (+bias)+BN;
+ *                       nets/repghost.py:98-115    RepGhost cheap_operation + fusion_bn (+SiLU) (+residual :279)
+ *   DCFA_OP_CBAM_POOL   nets/yolo_mul.py:59-60,70-71   avg/max pool over HW (partials)
+ *   DCFA_OP_CBAM_MLP    nets/yolo_mul.py:63-73     fc1-relu-fc2 on avg and max, add, sigmoid
+ *   DCFA_OP_CBAM_STATS  nets/yolo_mul.py:100,86-88 x*gate, mean/max over channels
+ *   DCFA_OP_CBAM_APPLY  nets/yolo_mul.py:89-90,101 conv7x7 on the 2-plane map, sigmoid, scale
+ *   DCFA_OP_MAXPOOL5    nets/yolo_mul.py:17,26-30  MaxPool2d(5,1,2) inside SPPF_CBAM
+ *   DCFA_OP_UPSAMPLE    nets/yolo_mul.py:421,426,433  feat3_rgb+feat3_nir, bilinear(align_corners=True)
+ *   DCFA_OP_DFL         nets/yolo_mul.py:312-322,459-461  view/split + DFL softmax expectation
+ *   dcfa_decode_box     utils/utils_bbox.py:30-40,49-58   dist2bbox(xywh) * strides, sigmoid, normalise
+ *   dcfa_nms            utils/utils_bbox.py:87-168 + torchvision.ops.nms (un-vendored dependency)
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  Every pointer is a DEVICE
+ *     pointer unless stated otherwise.  The caller owns all memory.
+ *   - Every function returns 0 on success, a negative DCFA_E_* code otherwise;
+ *     dcfa_last_error() returns a thread-local message.  Nothing throws or
+ *     aborts across the ABI.
+ *   - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*).  No host synchronisation, no allocation: every call is CUDA-graph
+ *     capturable.
+ *   - Activations are bf16 NHWC inside the path; fp32 at the reference-facing
+ *     surface (inputs NCHW fp32, head maps NCHW fp32, dbox/cls/decoded fp32).
+ */
+#ifndef DCFA_B200_H_
+#define DCFA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCFA_ABI_VERSION 1
+
+enum {
+  DCFA_OK = 0,
+  DCFA_E_INVALID = -1,   /* bad argument / unsupported shape */
+  DCFA_E_CUDA = -2,      /* a CUDA runtime call failed */
+  DCFA_E_ARCH = -3       /* device is not sm_100 */
+};
+
+/* op kinds executed by dcfa_run_ops */
+enum {
+  DCFA_OP_STEM = 1,
+  DCFA_OP_CONV = 2,
+  DCFA_OP_DWCONV = 3,
+  DCFA_OP_CBAM_POOL = 4,
+  DCFA_OP_CBAM_MLP = 5,
+  DCFA_OP_CBAM_STATS = 6,
+  DCFA_OP_CBAM_APPLY = 7,
+  DCFA_OP_MAXPOOL5 = 8,
+  DCFA_OP_UPSAMPLE = 9,
+  DCFA_OP_DFL = 10
+};
+
+/* activation applied in conv / depthwise epilogues */
+enum { DCFA_ACT_NONE = 0, DCFA_ACT_RELU = 1, DCFA_ACT_SILU = 2 };
+
+/* DCFA_OP_CONV output modes */
+enum { DCFA_OUT_BF16_NHWC = 0, DCFA_OUT_F32_NCHW = 1 };
+
+/*
+ * A strided view of an activation tensor (or a flat parameter array).
+ *   address(n, y, x, c) = bufs[buf] + off
+ *                         + elem_size * ( (n % gi) * img_stride + (n / gi) * gstride
+ *                                         + (y * W + x) * ld + c )
+ * `gi` (images per group) and `gstride` let one launch cover both modalities:
+ * either as a [2B,...] tensor (gstride = gi*img_stride) or as two channel slots
+ * of one concat buffer (gstride = slot width).  gi == 0 means "no grouping".
+ * For parameter arrays only buf/off are used.
+ */
+typedef struct dcfa_view {
+  int32_t buf;        /* index into the bufs[] array given to dcfa_run_ops; -1 = absent */
+  int32_t ld;         /* elements between consecutive pixels (NHWC) */
+  int64_t off;        /* byte offset inside the buffer */
+  int64_t img_stride; /* elements between consecutive images of one group */
+  int64_t gstride;    /* elements between groups */
+  int32_t gi;         /* images per group (0: single group) */
+  int32_t pad_;
+} dcfa_view;
+
+/*
+ * One op of the flat execution plan.  Field use per kind:
+ *
+ * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = fp32 [G][27][Cout]
+ *        (BN scale folded, k = (ky*3+kx)*3+ci); bias = fp32 [G][Cout]; y = bf16 NHWC [n_img,Ho,Wo,Cout],
+ *        Ho = Hi/2, Wo = Wi/2.
+ * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed
+ *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
+ *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added
+ *        after the activation; y = output (out_mode).  f0 = post-activation scale (1.0 = none).
+ * DWCONV x -> y depthwise 3x3 s1 p1, w = fp32 [G][9][Cin] (BN folded), bias = fp32 [G][Cin], act,
+ *        x2 = optional residual (added after activation).
+ * CBAM_POOL   x -> a0 = fp32 [n_img][parts][Cin] sums, a1 = same shape maxima; parts pixel chunks.
+ * CBAM_MLP    a0,a1 partials -> a2 = fp32 gate [n_img][Cin]; w = fp32 fc1 [G][hidden][Cin],
+ *             scale = fp32 fc2 [G][Cin][hidden]; Hi*Wi is the pooling divisor.
+ * CBAM_STATS  x, a2 gate -> a0 = fp32 [n_img][Hi][Wi][2] (mean_c, max_c of x*gate).
+ * CBAM_APPLY  x, a2 gate, a0 stats, w = fp32 [G][2][7][7] -> y = x*gate*sigmoid(conv7x7(stats)).
+ * MAXPOOL5    x -> y, 5x5 s1 p2, -inf padding.
+ * UPSAMPLE    x (+ x2 if present, summed first) [n_img,Hi,Wi,Cin] -> y [n_img,Ho,Wo,Cin] bilinear,
+ *             align_corners=True.
+ * DFL    x = fp32 NCHW head maps of the 3 levels at a0.off/a1.off/a2.off inside buffers a0/a1/a2.buf
+ *        ([n_img, 64+nc, H_l, W_l], H_l = Hi>>l, W_l = Wi>>l for l = 0,1,2 taken from Hi,Wi of level 0);
+ *        y = fp32 dbox [n_img,4,A]; x2 = fp32 cls logits out [n_img,nc,A].
+ */
+typedef struct dcfa_op {
+  int32_t kind;
+  int32_t act;
+  int32_t out_mode;
+  int32_t flags;
+  dcfa_view x, x2, y, w, scale, bias, a0, a1, a2;
+  int32_t n_img, group_imgs;
+  int32_t Hi, Wi, Cin;
+  int32_t Ho, Wo, Cout;
+  int32_t ksize, stride;
+  int32_t BN, n_tiles, k_blocks, K_real;
+  int32_t hidden, parts, nc, A;
+  int32_t out_ctot;   /* CONV F32_NCHW: total channels of the destination tensor */
+  int32_t out_coff;   /* CONV F32_NCHW: first destination channel */
+  int64_t w_gstride;  /* elements between the weight sets of two groups */
+  int64_t sb_gstride; /* elements between the scale/bias (or fc2) sets of two groups */
+  float f0, f1, f2, f3;
+} dcfa_op;
+
+/* ABI self-description (the Python loader checks these against its ctypes mirror). */
+int dcfa_abi_version(void);
+int dcfa_sizeof_view(void);
+int dcfa_sizeof_op(void);
+
+/* Thread-local description of the last failure. */
+const char* dcfa_last_error(void);
+
+/* 0 when device `dev` can run the library (compute capability 10.x), else DCFA_E_ARCH/CUDA. */
+int dcfa_device_check(int dev);
+
+/* Number of kernels launched by this process through the library so far. */
+int64_t dcfa_launch_count(void);
+
+/*
+ * Execute `n_ops` ops in order on `stream`.  `ops` is HOST memory (read during
+ * the call only).  `bufs[nbufs]` are the device base pointers the views index.
+ */
+int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, void* stream);
+
+/*
+ * DecodeBox.decode_box (utils/utils_bbox.py:49-58).
+ *   dbox [B,4,A] fp32 (l,t,r,b distances), cls [B,nc,A] fp32 logits (batch stride cls_bstride
+ *   elements, row stride A), anchors [2,A] fp32 with element (k,a) at anchors[k*anc_s0 + a*anc_s1],
+ *   strides [A] fp32 -> out [B,A,4+nc] fp32 contiguous: (cx,cy,w,h)/(W,H,W,H), sigmoid(cls).
+ */
+int dcfa_decode_box(const float* dbox, const float* cls, int64_t cls_bstride,
+                    const float* anchors, int64_t anc_s0, int64_t anc_s1, const float* strides,
+                    int B, int A, int nc, float img_w, float img_h, float* out, void* stream);
+
+/* IoU arithmetic of the un-vendored torchvision.ops.nms the reference calls (utils/utils_bbox.py:145). */
+enum {
+  DCFA_IOU_TV_CPU = 0,  /* areas rounded separately, fp32 IoU compared with the double threshold   */
+  DCFA_IOU_TV_CUDA = 1  /* Sa + fma(wj,hj) fused as torchvision's CUDA kernel, float threshold     */
+};
+
+/* Bytes of scratch dcfa_nms needs for (B, A). */
+int64_t dcfa_nms_workspace_bytes(int B, int A);
+
+/*
+ * DecodeBox.non_max_suppression up to (not including) the host-side un-letterbox
+ * (utils/utils_bbox.py:92-168).
+ *   pred [B,A,4+nc] fp32: columns 0..3 are rewritten IN PLACE from (cx,cy,w,h) to (x1,y1,x2,y2), as
+ *   the reference does (:92-97).  Per image: class max (first max wins), keep rows with
+ *   conf >= conf_thres, per class (ascending) greedy NMS in stable descending-score order.
+ *   out_det  [B,A,6] fp32: kept rows (x1,y1,x2,y2,conf,cls) in the reference's output order.
+ *   out_idx  [B,A] int32: anchor index of every kept row (same order).
+ *   out_cnt  [B]   int32: kept rows per image;  out_cand [B] int32 (may be NULL): candidates after
+ *   the confidence filter.
+ *   Limits: nc <= 256, A < 2^24.
+ */
+int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, double nms_thres, int iou_mode,
+             float* out_det, int32_t* out_idx, int32_t* out_cnt, int32_t* out_cand,
+             void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCFA_B200_H_ */

@@ -1,0 +1,280 @@
+"""Op-level parity of every CUDA kernel against a plain PyTorch fp32 reference of the same op
+(inputs/weights rounded to bf16 first, so only accumulation order and the final bf16 store differ)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import bf16_round, conv_op, flat_view, nhwc_view, ptrs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ops, bufs):
+    from dcfa_b200 import _lib
+    _lib.run_ops(ops, ptrs(bufs), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+def _act(v, act):
+    from dcfa_b200 import abi
+    if act == abi.ACT_RELU:
+        return F.relu(v)
+    if act == abi.ACT_SILU:
+        return v * torch.sigmoid(v)
+    return v
+
+
+def _bf16_close(got, ref, what):
+    got, ref = got.float(), ref.float()
+    tol = 1e-2 * ref.abs() + 2e-2 * max(ref.abs().max().item(), 1e-6) / 4
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), "%s: %d mismatches, max abs err %.4g (ref max %.4g)" % (
+        what, int(bad.sum()), (got - ref).abs().max().item(), ref.abs().max().item())
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, s, act, groups
+    (2, 8, 8, 64, 64, 1, 1, 2, 1),      # one tile, one k-block
+    (1, 16, 16, 32, 32, 1, 1, 1, 1),    # Cin < 64: K padding
+    (2, 20, 20, 128, 64, 1, 1, 2, 1),   # M tail (800 rows), 2 k-blocks
+    (2, 16, 16, 64, 128, 3, 1, 2, 1),   # 3x3, padding
+    (2, 16, 16, 32, 64, 3, 2, 2, 1),    # 3x3 stride 2, taps straddling 64-wide k-blocks
+    (1, 12, 20, 16, 16, 3, 2, 0, 1),    # tiny channels (phi=n), N=16
+    (2, 10, 10, 256, 512, 1, 1, 2, 1),  # two N tiles of 256
+    (4, 12, 12, 64, 192, 3, 1, 2, 2),   # two weight groups (modalities), N=192
+    (3, 40, 40, 128, 128, 3, 1, 2, 1),  # many tiles > pipeline depth, persistent loop
+    (2, 9, 7, 48, 80, 3, 1, 1, 1),      # odd sizes, Cin not a multiple of 64
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,act,groups", CONV_CASES)
+def test_conv_bf16_nhwc(cuda, n, h, w, cin, cout, k, s, act, groups):
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(1234 + cin + cout + k + s)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    ws = [bf16_round(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5) for _ in range(groups)]
+    scs = [torch.rand(cout, generator=g) + 0.5 for _ in range(groups)]
+    bis = [torch.randn(cout, generator=g) * 0.1 for _ in range(groups)]
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    y = torch.full((n, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=cuda)
+    gi = n // groups
+    op, bufs = conv_op(x_nhwc, ws, scs, bis, y, ksize=k, stride=s, act=act, cin=cin, group_imgs=gi)
+    _run([op], bufs)
+    refs = []
+    for gg in range(groups):
+        r = F.conv2d(x[gg * gi:(gg + 1) * gi].to(cuda), ws[gg].to(cuda), None, s, pad)
+        r = r * scs[gg].to(cuda)[None, :, None, None] + bis[gg].to(cuda)[None, :, None, None]
+        refs.append(_act(r, act))
+    ref = torch.cat(refs).permute(0, 2, 3, 1)
+    _bf16_close(y, ref, "conv")
+
+
+def test_conv_views_residual_postscale(cuda):
+    """channel-offset input view, channel-offset output slot, residual add and post-activation scale."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(7)
+    n, h, w, ctot, c_off, cin, cout = 2, 14, 14, 96, 32, 64, 32
+    x = bf16_round(torch.randn(n, h, w, ctot, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / 8)
+    sc, bi = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    res = bf16_round(torch.randn(n, h, w, 48, generator=g))
+    y = torch.full((n, h, w, 80), 3.0, dtype=torch.bfloat16, device=cuda)
+    op, bufs = conv_op(x.to(torch.bfloat16).to(cuda), [wt], [sc], [bi], y, ksize=1, stride=1, act=abi.ACT_SILU, cin=cin,
+                       c_off_in=c_off, c_off_out=40, res=res.to(torch.bfloat16).to(cuda), c_off_res=16, post_scale=0.5)
+    _run([op], bufs)
+    xin = x[..., c_off:c_off + cin].permute(0, 3, 1, 2)
+    r = F.conv2d(xin, wt) * sc[None, :, None, None] + bi[None, :, None, None]
+    r = (r * torch.sigmoid(r)) * 0.5 + res[..., 16:16 + cout].permute(0, 3, 1, 2)
+    _bf16_close(y[..., 40:72].cpu(), r.permute(0, 2, 3, 1), "conv view")
+    assert (y[..., :40] == 3.0).all() and (y[..., 72:] == 3.0).all(), "conv wrote outside its channel slot"
+
+
+def test_conv_f32_nchw_out(cuda):
+    """head-style output: fp32 NCHW at a channel offset, Cout not a multiple of 16 (nc = 1 and 64)."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(11)
+    n, h, w, cin = 2, 10, 10, 64
+    x = bf16_round(torch.randn(n, h, w, cin, generator=g))
+    out = torch.zeros(n, 65, h, w, dtype=torch.float32, device=cuda)
+    xg = x.to(torch.bfloat16).to(cuda)
+    for cout, coff in ((64, 0), (1, 64)):
+        wt = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / 8)
+        bi = torch.randn(cout, generator=g)
+        op, bufs = conv_op(xg, [wt], [torch.ones(cout)], [bi], out, ksize=1, stride=1, act=abi.ACT_NONE, cin=cin,
+                           out_mode=abi.OUT_F32_NCHW, out_ctot=65, out_coff=coff)
+        _run([op], bufs)
+        r = F.conv2d(x.permute(0, 3, 1, 2), wt, bi)
+        got = out[:, coff:coff + cout].cpu()
+        assert torch.allclose(got, r, atol=2e-4, rtol=1e-4), (got - r).abs().max()
+
+
+@pytest.mark.parametrize("b,h,w,c0,groups", [(1, 32, 64, 16, 1), (2, 40, 72, 32, 2), (1, 70, 130, 32, 1)])
+def test_stem(cuda, b, h, w, c0, groups):
+    """fused conv3x3+BN+ReLU+maxpool3/2 vs F.conv2d + F.max_pool2d (nets/yolo_mul.py:104-115)."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.rand(b, 3, h, w, generator=g) for _ in range(groups)]
+    ws = [torch.randn(c0, 3, 3, 3, generator=g) * 0.3 for _ in range(groups)]
+    bs = [torch.randn(c0, generator=g) * 0.2 for _ in range(groups)]
+    wk = torch.stack([wt.permute(2, 3, 1, 0).reshape(27, c0) for wt in ws]).contiguous().to(cuda)  # (ky,kx,ci) x co
+    bk = torch.stack(bs).to(cuda)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.zeros(groups * b, ho, wo, c0, dtype=torch.bfloat16, device=cuda)
+    xg = [t.to(cuda) for t in xs]
+    bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y]
+    op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
+                    bias=flat_view(3), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w, Ho=ho, Wo=wo, Cout=c0)
+    _run([op], bufs)
+    ref = torch.cat([F.max_pool2d(F.relu(F.conv2d(xs[i], ws[i], bs[i], 1, 1)), 3, 2, 1) for i in range(groups)])
+    _bf16_close(y.cpu(), ref.permute(0, 2, 3, 1), "stem")
+
+
+@pytest.mark.parametrize("n,h,w,c,act,groups,use_res", [(2, 9, 11, 16, 0, 1, False), (4, 20, 20, 64, 2, 2, True),
+                                                      (2, 13, 6, 128, 2, 1, True)])
+def test_dwconv(cuda, n, h, w, c, act, groups, use_res):
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(9)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    ws = [torch.randn(c, 1, 3, 3, generator=g) * 0.3 for _ in range(groups)]
+    bs = [torch.randn(c, generator=g) * 0.2 for _ in range(groups)]
+    res = bf16_round(torch.randn(n, c, h, w, generator=g))
+    wk = torch.stack([wt.reshape(c, 9).t().contiguous() for wt in ws]).to(cuda)  # [G][9][C]
+    bk = torch.stack(bs).to(cuda)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    rg = res.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    y = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+    bufs = [xg, rg, wk, bk, y]
+    op = abi.new_op(abi.OP_DWCONV, act=act, x=nhwc_view(xg, 0), x2=nhwc_view(rg, 1) if use_res else abi.no_view(),
+                    w=flat_view(2), bias=flat_view(3), y=nhwc_view(y, 4), n_img=n, group_imgs=n // groups, Hi=h, Wi=w, Cin=c)
+    _run([op], bufs)
+    gi = n // groups
+    ref = torch.cat([F.conv2d(x[i * gi:(i + 1) * gi], ws[i], bs[i], 1, 1, groups=c) for i in range(groups)])
+    ref = _act(ref, act)
+    if use_res:
+        ref = ref + res
+    _bf16_close(y.cpu(), ref.permute(0, 2, 3, 1), "dwconv")
+
+
+def _cbam_ref(x, fc1, fc2, w7):
+    """CBAM restated with plain torch ops (nets/yolo_mul.py:56-102); x NCHW fp32."""
+    avg, mx = x.mean((2, 3), keepdim=True), x.amax((2, 3), keepdim=True)
+    mlp = lambda v: F.conv2d(F.relu(F.conv2d(v, fc1)), fc2)
+    t = x * torch.sigmoid(mlp(avg) + mlp(mx))
+    p = torch.cat([t.mean(1, keepdim=True), t.amax(1, keepdim=True)], 1)
+    return t * torch.sigmoid(F.conv2d(p, w7, padding=3))
+
+
+@pytest.mark.parametrize("b,h,w,c,hidden,groups", [(2, 20, 20, 128, 1, 2), (1, 80, 80, 64, 8, 2), (2, 12, 28, 256, 32, 1)])
+def test_cbam_chain(cuda, b, h, w, c, hidden, groups):
+    """pool -> mlp -> stats -> apply, two modalities writing adjacent channel slots of one concat buffer."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(21)
+    n = b * groups
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    fc1 = [torch.randn(hidden, c, 1, 1, generator=g) * 0.2 for _ in range(groups)]
+    fc2 = [torch.randn(c, hidden, 1, 1, generator=g) * 0.5 for _ in range(groups)]
+    w7 = [torch.randn(1, 2, 7, 7, generator=g) * 0.2 for _ in range(groups)]
+    xg = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    parts = 4
+    psum = torch.zeros(n, parts, c, device=cuda)
+    pmax = torch.zeros(n, parts, c, device=cuda)
+    gate = torch.zeros(n, c, device=cuda)
+    stats = torch.zeros(n, h, w, 2, device=cuda)
+    f1 = torch.stack([t.reshape(hidden, c) for t in fc1]).to(cuda)
+    f2 = torch.stack([t.reshape(c, hidden) for t in fc2]).to(cuda)
+    k7 = torch.stack([t.reshape(98) for t in w7]).to(cuda)
+    slot0 = 16
+    ctot = slot0 + groups * c
+    y = torch.full((b, h, w, ctot), 5.0, dtype=torch.bfloat16, device=cuda)
+    bufs = [xg, psum, pmax, gate, stats, f1, f2, k7, y]
+    common = dict(n_img=n, group_imgs=b, Hi=h, Wi=w, Cin=c, hidden=hidden, parts=parts)
+    ops = [
+        abi.new_op(abi.OP_CBAM_POOL, x=nhwc_view(xg, 0), a0=flat_view(1), a1=flat_view(2), **common),
+        abi.new_op(abi.OP_CBAM_MLP, a0=flat_view(1), a1=flat_view(2), a2=flat_view(3), w=flat_view(5), scale=flat_view(6),
+                   w_gstride=hidden * c, sb_gstride=hidden * c, **common),
+        abi.new_op(abi.OP_CBAM_STATS, x=nhwc_view(xg, 0), a2=flat_view(3), a0=flat_view(4), **common),
+        abi.new_op(abi.OP_CBAM_APPLY, x=nhwc_view(xg, 0), a2=flat_view(3), a0=flat_view(4), w=flat_view(7),
+                   y=nhwc_view(y, 8, slot0, gi=b, gstride=c), **common),
+    ]
+    _run(ops, bufs)
+    for gg in range(groups):
+        ref = _cbam_ref(x[gg * b:(gg + 1) * b], fc1[gg], fc2[gg], w7[gg]).permute(0, 2, 3, 1)
+        _bf16_close(y[..., slot0 + gg * c: slot0 + (gg + 1) * c].cpu(), ref, "cbam group %d" % gg)
+    assert (y[..., :slot0] == 5.0).all()
+
+
+def test_maxpool5_and_upsample(cuda):
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(3)
+    n, h, w, c = 3, 20, 20, 64
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    x2 = bf16_round(torch.randn(n, c, h, w, generator=g))
+    xg = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    x2g = x2.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    y = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+    up = torch.zeros(n, 40, 40, c + 8, dtype=torch.bfloat16, device=cuda)
+    ops = [abi.new_op(abi.OP_MAXPOOL5, x=nhwc_view(xg, 0), y=nhwc_view(y, 2), n_img=n, Hi=h, Wi=w, Cin=c),
+           abi.new_op(abi.OP_UPSAMPLE, x=nhwc_view(xg, 0), x2=nhwc_view(x2g, 1), y=nhwc_view(up, 3, 8), n_img=n, Hi=h, Wi=w,
+                      Ho=40, Wo=40, Cin=c)]
+    _run(ops, [xg, x2g, y, up])
+    assert torch.equal(y.float().cpu(), F.max_pool2d(x, 5, 1, 2).permute(0, 2, 3, 1))
+    ref = F.interpolate(x + x2, size=(40, 40), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    _bf16_close(up[..., 8:].cpu(), ref, "upsample")
+
+
+def _dfl_ref(maps, nc):
+    b = maps[0].shape[0]
+    cat = torch.cat([m.reshape(b, 64 + nc, -1) for m in maps], 2)
+    box, cls = cat.split((64, nc), 1)
+    a = box.shape[-1]
+    d = (box.view(b, 4, 16, a).transpose(2, 1).softmax(1) * torch.arange(16.0).view(1, 16, 1, 1)).sum(1)
+    return d, cls
+
+
+@pytest.mark.parametrize("nc", [1, 3])
+def test_dfl_and_decode(cuda, nc):
+    """DFL (+ level gather) and decode_box against torch restatements; adversarial logits included."""
+    import ctypes as C
+    from dcfa_b200 import _lib, abi
+    g = torch.Generator().manual_seed(17)
+    b, h0, w0 = 2, 12, 20
+    sizes = [(h0, w0), (h0 // 2, w0 // 2), (h0 // 4, w0 // 4)]
+    maps = [torch.randn(b, 64 + nc, hh, ww, generator=g) * 3 for hh, ww in sizes]
+    maps[0][0, :16, 0, 0] = 30.0          # uniform large
+    maps[0][0, 16:32, 0, 0] = torch.tensor([-30.0] * 15 + [30.0])  # one-hot at the last bin
+    maps[1][1, 32:48, 1, 1] = 0.0
+    a_tot = sum(hh * ww for hh, ww in sizes)
+    mg = [m.to(cuda) for m in maps]
+    dbox = torch.zeros(b, 4, a_tot, device=cuda)
+    cls = torch.zeros(b, nc, a_tot, device=cuda)
+    op = abi.new_op(abi.OP_DFL, a0=flat_view(0), a1=flat_view(1), a2=flat_view(2), y=flat_view(3), x2=flat_view(4), n_img=b,
+                    Hi=h0, Wi=w0, nc=nc, A=a_tot)
+    _run([op], mg + [dbox, cls])
+    d_ref, c_ref = _dfl_ref(maps, nc)
+    assert torch.allclose(dbox.cpu(), d_ref, atol=1e-5, rtol=0), (dbox.cpu() - d_ref).abs().max()
+    assert torch.equal(cls.cpu(), c_ref)
+
+    # decode_box (utils/utils_bbox.py:49-58)
+    anchors, strides = [], []
+    for (hh, ww), s in zip(sizes, (8.0, 16.0, 32.0)):
+        sy, sx = torch.meshgrid(torch.arange(hh) + 0.5, torch.arange(ww) + 0.5, indexing="ij")
+        anchors.append(torch.stack((sx, sy), -1).view(-1, 2))
+        strides.append(torch.full((hh * ww, 1), s))
+    anc = torch.cat(anchors).t().contiguous()   # (2, A)
+    strd = torch.cat(strides).t().contiguous()  # (1, A)
+    img_w, img_h = w0 * 8.0, h0 * 8.0
+    out = torch.zeros(b, a_tot, 4 + nc, device=cuda)
+    ancg, strg = anc.to(cuda), strd.to(cuda)
+    _lib.check(_lib.lib.dcfa_decode_box(dbox.data_ptr(), cls.data_ptr(), nc * a_tot, ancg.data_ptr(), a_tot, 1,
+                                        strg.data_ptr(), b, a_tot, nc, img_w, img_h, out.data_ptr(),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    d = dbox.cpu()
+    lt, rb = d.split(2, 1)
+    x1y1, x2y2 = anc[None] - lt, anc[None] + rb
+    ref = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * strd
+    ref = torch.cat((ref, cls.cpu().sigmoid()), 1).permute(0, 2, 1).clone()
+    ref[:, :, :4] = ref[:, :, :4] / torch.tensor([img_w, img_h, img_w, img_h])
+    assert torch.allclose(out.cpu(), ref, atol=1e-6, rtol=1e-6), (out.cpu() - ref).abs().max()
