@@ -254,7 +254,8 @@ int next_pow2(int v) {
 extern "C" int64_t dcfa_nms_workspace_bytes(int B, int A) {
   if (B <= 0 || A <= 0) return 0;
   const int64_t apad = dcfa::next_pow2(A);
-  return (int64_t)B * apad * 8 + (int64_t)B * A * 16 + 256;
+  const int64_t key_bytes = ((int64_t)B * apad * 8 + 255) / 256 * 256;
+  return key_bytes + (int64_t)B * A * 16 + 256;
 }
 
 extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, double nms_thres, int iou_mode,
@@ -271,7 +272,8 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
   DCFA_REQUIRE(((uintptr_t)workspace % 16) == 0, "nms: workspace must be 16-byte aligned");
   const int Apad = next_pow2(A);
   uint64_t* keys = reinterpret_cast<uint64_t*>(workspace);
-  float4* sbox = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + (int64_t)B * Apad * 8);
+  const int64_t key_bytes = ((int64_t)B * Apad * 8 + 255) / 256 * 256;
+  float4* sbox = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + key_bytes);
 
   PrepArgs pa{pred, keys, B, A, Apad, nc, conf_thres};
   const int64_t tot = (int64_t)B * Apad;
