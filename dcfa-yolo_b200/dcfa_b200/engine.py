@@ -1,0 +1,111 @@
+"""Runtime of the B200 hot path: owns the packed parameter blob and the activation arena on one device and
+enqueues a compiled Plan (dcfa_run_ops) on the caller's CUDA stream.  PyTorch is used for device memory and
+streams only; every kernel launched here comes from lib/libdcfa_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib, abi
+from . import plan as P
+
+
+class Engine:
+    """One (batch, H, W) instance of the forward pass on one device."""
+
+    def __init__(self, state_dict, phi, num_classes, batch, height, width, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dcfa_b200 has no CPU path: the engine needs a CUDA (sm_100a) device")
+        _lib.check(_lib.lib.dcfa_device_check(self.device.index if self.device.index is not None else torch.cuda.current_device()))
+        self.plan = P.Plan(state_dict, phi, num_classes, batch, height, width)
+        self.B, self.H, self.W, self.nc, self.no, self.A = batch, height, width, self.plan.nc, self.plan.no, self.plan.A
+        self.level_shapes = list(self.plan.level_shapes)
+        self.blob = self.plan.blob_tensor.to(self.device)
+        self.arena = torch.empty(self.plan.arena_bytes + 256, dtype=torch.uint8, device=self.device)
+        self.n_ops = len(self.plan.ops)
+        self._bufs = (C.c_void_p * P.NUM_BUFS)()
+        self._bufs[P.BUF_BLOB] = self.blob.data_ptr()
+        self._bufs[P.BUF_ARENA] = self.arena.data_ptr()
+        self.anchors, self.strides = self._make_anchors()
+
+    def _make_anchors(self):
+        """make_anchors (reference utils/utils_bbox.py:16-28), always fp32; returned as (2,A) and (1,A)."""
+        pts, st = [], []
+        for (h, w), s in zip(self.level_shapes, (8.0, 16.0, 32.0)):
+            sx = torch.arange(w, dtype=torch.float32, device=self.device) + 0.5
+            sy = torch.arange(h, dtype=torch.float32, device=self.device) + 0.5
+            sy, sx = torch.meshgrid(sy, sx, indexing="ij")
+            pts.append(torch.stack((sx, sy), -1).view(-1, 2))
+            st.append(torch.full((h * w, 1), s, dtype=torch.float32, device=self.device))
+        return torch.cat(pts).t().contiguous(), torch.cat(st).t().contiguous()
+
+    def new_outputs(self):
+        dev, b = self.device, self.B
+        x = [torch.empty(b, self.no, h, w, dtype=torch.float32, device=dev) for (h, w) in self.level_shapes]
+        dbox = torch.empty(b, 4, self.A, dtype=torch.float32, device=dev)
+        cls = torch.empty(b, self.nc, self.A, dtype=torch.float32, device=dev)
+        return dbox, cls, x
+
+    def run(self, rgb, nir, outputs=None, stream=None):
+        """rgb, nir: contiguous float32 CUDA tensors [B,3,H,W].  Enqueues the whole forward; returns (dbox, cls, x)."""
+        shp = (self.B, 3, self.H, self.W)
+        for t in (rgb, nir):
+            if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("engine.run: expected contiguous float32 %s on %s, got %s %s on %s" % (
+                    shp, self.device, tuple(t.shape), t.dtype, t.device))
+        dbox, cls, x = outputs if outputs is not None else self.new_outputs()
+        b = self._bufs
+        b[P.BUF_RGB], b[P.BUF_NIR] = rgb.data_ptr(), nir.data_ptr()
+        b[P.BUF_X0], b[P.BUF_X1], b[P.BUF_X2] = x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr()
+        b[P.BUF_DBOX], b[P.BUF_CLS] = dbox.data_ptr(), cls.data_ptr()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib.dcfa_run_ops(self.plan.op_array, self.n_ops, b, P.NUM_BUFS, C.c_void_p(st)))
+        return dbox, cls, x
+
+
+def decode_box(dbox, cls, anchors, strides, input_shape):
+    """dcfa_decode_box on CUDA tensors -> [B, A, 4+nc] float32 (contiguous)."""
+    if not dbox.is_cuda:
+        raise RuntimeError("dcfa_b200 has no CPU path: decode_box needs CUDA tensors")
+    b, _, a = dbox.shape
+    nc = cls.shape[1]
+    dbox = dbox.float().contiguous()
+    if cls.dtype != torch.float32 or cls.stride(2) != 1 or cls.stride(1) != a:
+        cls = cls.float().contiguous()
+    anchors = anchors.float().to(dbox.device)
+    strides = strides.float().to(dbox.device).reshape(-1).contiguous()
+    out = torch.empty(b, a, 4 + nc, dtype=torch.float32, device=dbox.device)
+    st = torch.cuda.current_stream(dbox.device).cuda_stream
+    _lib.check(_lib.lib.dcfa_decode_box(dbox.data_ptr(), cls.data_ptr(), cls.stride(0), anchors.data_ptr(),
+                                        anchors.stride(0), anchors.stride(1), strides.data_ptr(), b, a, nc,
+                                        float(input_shape[1]), float(input_shape[0]), out.data_ptr(), C.c_void_p(st)))
+    return out
+
+
+class NmsWorkspace:
+    """Device scratch + outputs for dcfa_nms at a fixed (B, A)."""
+
+    def __init__(self, b, a, device):
+        self.b, self.a = b, a
+        self.bytes = int(_lib.lib.dcfa_nms_workspace_bytes(b, a))
+        self.ws = torch.empty(self.bytes, dtype=torch.uint8, device=device)
+        self.det = torch.empty(b, a, 6, dtype=torch.float32, device=device)
+        self.idx = torch.empty(b, a, dtype=torch.int32, device=device)
+        self.cnt = torch.zeros(b, dtype=torch.int32, device=device)
+        self.cand = torch.zeros(b, dtype=torch.int32, device=device)
+
+
+def nms(pred, conf_thres, nms_thres, iou_mode=abi.IOU_TV_CPU, workspace=None):
+    """dcfa_nms on a contiguous float32 CUDA tensor [B,A,4+nc] (boxes rewritten in place to xyxy).
+    Returns the NmsWorkspace holding det/idx/cnt/cand (device tensors, stream-ordered)."""
+    if not pred.is_cuda:
+        raise RuntimeError("dcfa_b200 has no CPU path: nms needs a CUDA tensor")
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    b, a, row = pred.shape
+    ws = workspace if workspace is not None else NmsWorkspace(b, a, pred.device)
+    assert ws.b == b and ws.a == a
+    st = torch.cuda.current_stream(pred.device).cuda_stream
+    _lib.check(_lib.lib.dcfa_nms(pred.data_ptr(), b, a, row - 4, float(conf_thres), float(nms_thres), int(iou_mode),
+                                 ws.det.data_ptr(), ws.idx.data_ptr(), ws.cnt.data_ptr(), ws.cand.data_ptr(),
+                                 ws.ws.data_ptr(), ws.bytes, C.c_void_p(st)))
+    return ws

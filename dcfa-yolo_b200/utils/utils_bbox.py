@@ -1,0 +1,101 @@
+"""Drop-in for the reference's utils/utils_bbox.py: same names and signatures
+(make_anchors :16-28, dist2bbox :30-40, DecodeBox.decode_box :49-58, .yolo_correct_boxes :60-85,
+.non_max_suppression :87-174), with decode and NMS executed by lib/libdcfa_b200.so on the GPU.
+"""
+import numpy as np
+import torch
+
+from dcfa_b200 import abi
+from dcfa_b200 import engine as _engine
+
+
+def make_anchors(feats, strides, grid_cell_offset=0.5):
+    """Anchor centres (A,2) and per-anchor stride (A,1) for a list of feature maps.  Always fp32: under bf16
+    features the reference's dtype-following version (:20) cannot represent 159.5."""
+    assert feats is not None
+    device = feats[0].device
+    pts, st = [], []
+    for f, s in zip(feats, strides):
+        h, w = f.shape[-2:]
+        gy, gx = torch.meshgrid(torch.arange(h, device=device, dtype=torch.float32) + grid_cell_offset,
+                                torch.arange(w, device=device, dtype=torch.float32) + grid_cell_offset, indexing='ij')
+        pts.append(torch.stack((gx, gy), -1).view(-1, 2))
+        st.append(torch.full((h * w, 1), float(s), dtype=torch.float32, device=device))
+    return torch.cat(pts), torch.cat(st)
+
+
+def dist2bbox(distance, anchor_points, xywh=True, dim=-1):
+    """(l,t,r,b) distances -> boxes; used by the training loss of the reference (kept for import parity)."""
+    lt, rb = torch.split(distance, 2, dim)
+    x1y1, x2y2 = anchor_points - lt, anchor_points + rb
+    if xywh:
+        return torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), dim)
+    return torch.cat((x1y1, x2y2), dim)
+
+
+class DecodeBox():
+    #: IoU arithmetic of torchvision.ops.nms to reproduce: 'cpu' (the reference's CPU-runnable path, pinned by
+    #: the golden vectors) or 'cuda' (torchvision's CUDA kernel: fused area sum, float threshold).
+    iou_mode = 'cpu'
+    #: detections copied back per image in the first device->host transfer (more are fetched on demand)
+    first_fetch = 512
+
+    def __init__(self, num_classes, input_shape):
+        super(DecodeBox, self).__init__()
+        self.num_classes = num_classes
+        self.bbox_attrs = 4 + num_classes
+        self.input_shape = input_shape
+        self._nms_ws = {}
+
+    def decode_box(self, inputs):
+        dbox, cls, origin_cls, anchors, strides = inputs
+        return _engine.decode_box(dbox, cls, anchors, strides, self.input_shape)
+
+    def yolo_correct_boxes(self, box_xy, box_wh, input_shape, image_shape, letterbox_image):
+        """numpy, host side, post-NMS (tiny): undo the letterbox; rows (y1, x1, y2, x2) in original-image pixels."""
+        yx, hw = box_xy[..., ::-1], box_wh[..., ::-1]
+        input_shape, image_shape = np.array(input_shape), np.array(image_shape)
+        if letterbox_image:
+            new_shape = np.round(image_shape * np.min(input_shape / image_shape))
+            offset = (input_shape - new_shape) / 2. / input_shape
+            scale = input_shape / new_shape
+            yx = (yx - offset) * scale
+            hw = hw * scale
+        lo, hi = yx - hw / 2., yx + hw / 2.
+        boxes = np.concatenate([lo[..., 0:1], lo[..., 1:2], hi[..., 0:1], hi[..., 1:2]], axis=-1)
+        return boxes * np.concatenate([image_shape, image_shape], axis=-1)
+
+    def nms_device(self, prediction, conf_thres=0.5, nms_thres=0.4):
+        """GPU part only: returns the NmsWorkspace (det/idx/cnt on the device, stream-ordered, no host sync)."""
+        if not (torch.is_tensor(prediction) and prediction.is_cuda):
+            raise RuntimeError("dcfa_b200 has no CPU path: non_max_suppression needs a CUDA tensor")
+        pred = prediction
+        if pred.dtype != torch.float32 or not pred.is_contiguous():
+            pred = pred.float().contiguous()
+        key = (pred.shape[0], pred.shape[1], str(pred.device))
+        ws = self._nms_ws.get(key)
+        if ws is None:
+            ws = self._nms_ws[key] = _engine.NmsWorkspace(pred.shape[0], pred.shape[1], pred.device)
+        mode = abi.IOU_TV_CUDA if self.iou_mode == 'cuda' else abi.IOU_TV_CPU
+        _engine.nms(pred, conf_thres, nms_thres, mode, ws)
+        if pred is not prediction:   # keep the reference's in-place xywh -> xyxy side effect (:97)
+            prediction[:, :, :4] = pred[:, :, :4].to(prediction.dtype)
+        return ws
+
+    def non_max_suppression(self, prediction, num_classes, input_shape, image_shape, letterbox_image, conf_thres=0.5,
+                            nms_thres=0.4):
+        ws = self.nms_device(prediction, conf_thres, nms_thres)
+        b, a = ws.b, ws.a
+        k = min(a, self.first_fetch)
+        head = torch.cat((ws.cnt.view(b, 1).float(), ws.det[:, :k].reshape(b, k * 6)), 1).cpu().numpy()  # one D2H
+        counts = head[:, 0].astype(np.int64)
+        output = [None for _ in range(b)]
+        for i in range(b):
+            n = int(counts[i])
+            if n == 0:
+                continue
+            det = head[i, 1:1 + n * 6].reshape(n, 6).copy() if n <= k else ws.det[i, :n].cpu().numpy()
+            box_xy, box_wh = (det[:, 0:2] + det[:, 2:4]) / 2, det[:, 2:4] - det[:, 0:2]
+            det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+            output[i] = det
+        return output

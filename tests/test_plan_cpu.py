@@ -1,0 +1,36 @@
+"""Host-logic tests (no GPU): the plan compiler's op list, executed by the CPU interpreter in oracle/, must
+reproduce the reference goldens within the bf16 tolerance north_star states (abs 2e-2, rel 1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+from test_oracle_cpu import GOLDEN_CASES, compare_x_maps, golden_state_dict, load_golden
+
+SMALL = [c for c in GOLDEN_CASES if "640" not in c]
+
+
+@pytest.mark.parametrize("name", SMALL + ["n640_stress"])
+def test_plan_interpreted_on_cpu_matches_reference_golden(name):
+    from dcfa_b200.plan import Plan
+    from oracle import forward as O
+    from oracle import plan_interp
+    z, meta, keys = load_golden(name)
+    sd = golden_state_dict(meta, keys)
+    rgb, nir = O.synth_inputs(meta["B"], meta["H"], meta["W"], meta["seed"] + 1000)
+    plan = Plan(sd, meta["phi"], meta["nc"], meta["B"], meta["H"], meta["W"])
+    dbox, cls, x = plan_interp.run_plan(plan, rgb, nir)
+    compare_x_maps(z, x, 2e-2, 1e-2)
+    np.testing.assert_allclose(cls.numpy(), z["cls"], atol=2e-2, rtol=1e-2)
+    np.testing.assert_allclose(dbox.numpy(), z["dbox"], atol=2e-2, rtol=1e-2)
+    assert plan.A == z["dbox"].shape[-1]
+
+
+def test_plan_flop_count_matches_survey():
+    """algorithmic conv FLOPs per image pair (2*MAC over every nn.Conv2d), nc=1, 640x640."""
+    from dcfa_b200.plan import Plan
+    from oracle import forward as O
+    import json, os
+    keys = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")))["n_nc1"]
+    sd = O.synth_state_dict({k: torch.empty(tuple(s), device="meta") for k, s in keys.items()}, 1, "default")
+    plan = Plan(sd, "n", 1, 1, 640, 640)
+    assert abs(plan.conv_flops / 7.361e9 - 1.0) < 0.01, plan.conv_flops
