@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the DCFA-YOLO inference hot path (forward + decode + NMS) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--phi s] [--batch 32] [--size 640]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  Metric: RGB-D image pairs / s at 640x640 for forward + decode + NMS
+(BASELINE.json), workload = BASELINE.json configs[1] (phi='s', batch 32 per GPU, 1 class, constructor init).
+
+  value      device-resident inputs, K replays of the CUDA graph holding forward+decode+NMS, CUDA events, max over ranks
+  e2e        the same step through the public drop-in API (YoloBody.forward -> DecodeBox.decode_box ->
+             DecodeBox.non_max_suppression) with pinned HOST inputs copied in and the detections copied out every step
+  roofline   conv implicit-GEMM kernel (tensor bound): sum of algorithmic conv FLOPs of its launches in one step /
+             sum of their CUDA-event durations, vs the measured sustained bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference   the CPU oracle port of the reference (oracle/, torch fp32 CPU ops + C NMS) on the
+             box's host cores: the reference itself is pure Python and is not present on the GPU box
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dcfa-yolo_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "RGB-D img-pairs/sec @640^2 fwd+decode+NMS"
+UNIT = "pairs/s"
+CONF, IOU = 0.5, 0.3   # reference facade defaults (yolo_mul.py:22-23)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--phi", default="s")
+    ap.add_argument("--batch", type=int, default=32, help="image pairs per GPU per step")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--ref-batch", type=int, default=1, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-ops", default="", help="write per-op CUDA-event timings (JSON) to this path")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, sustained)")
+    except Exception:
+        return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_model(phi, size, device=None):
+    from nets.yolo_mul import YoloBody
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = YoloBody([size, size], 1, phi)   # constructor init = the reference's weights_init N(0, 0.02)
+    net = net.eval()
+    return net.to(device) if device is not None else net
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step(sd, phi, rgb, nir, size):
+    from oracle import forward as O
+    from oracle import nms as onms
+    out = O.yolo_forward(sd, phi, rgb, nir, 1)
+    y = O.decode_box(out, (size, size)).numpy()
+    return onms.non_max_suppression(np.ascontiguousarray(y), [size, size], np.array([size, size]), True, CONF, IOU, 0)
+
+
+def cpu_baseline(phi, size, batch, seconds):
+    """Bounded sample of the same workload on the host cores (oracle port; all torch threads)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = build_model(phi, size)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    rgb, nir = torch.rand(batch, 3, size, size, generator=g), torch.rand(batch, 3, size, size, generator=g)
+    cpu_reference_step(sd, phi, rgb, nir, size)  # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        cpu_reference_step(sd, phi, rgb, nir, size)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or n >= 200:
+            break
+    return {"value": round(n * batch / dt, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of %d pair(s), phi=%s %dx%d fp32, oracle port (torch CPU conv + C NMS), %.1f s" % (
+                n, batch, phi, size, size, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = args.ref_batch
+    net = build_model(args.phi, args.size)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    rgb, nir = torch.rand(b, 3, args.size, args.size, generator=g), torch.rand(b, 3, args.size, args.size, generator=g)
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, args.phi, rgb, nir, args.size)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sd, args.phi, rgb, nir, args.size)
+    dt = time.perf_counter() - t0
+    v = args.steps * b / dt
+    cores = torch.get_num_threads()
+    sample = "each step = %d image pair(s) of the phi=%s %dx%d workload, fp32, oracle port of the reference on %d host threads" % (
+        b, args.phi, args.size, args.size, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DCFA-YOLO phi='%s' inference fwd+decode+NMS, %dx%d RGB+depth, 1 class" % (args.phi, args.size, args.size),
+                   "pairs_per_step": b, "device": "cpu"},
+        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+class Pipeline:
+    """forward + decode + NMS on device-resident inputs, captured once into a CUDA graph."""
+
+    def __init__(self, net, batch, size, device):
+        from dcfa_b200 import _lib
+        from utils.utils_bbox import DecodeBox
+        self.net, self.dec, self.lib = net, DecodeBox(1, (size, size)), _lib
+        self.rgb = torch.rand(batch, 3, size, size, device=device)
+        self.nir = torch.rand(batch, 3, size, size, device=device)
+        self.graph = None
+
+    def step(self):
+        out = self.net(self.rgb, self.nir)
+        y = self.dec.decode_box(out)
+        self.ws = self.dec.nms_device(y, CONF, IOU)
+        return self.ws
+
+    def capture(self):
+        self.step()
+        torch.cuda.synchronize()
+        n0 = self.lib.launch_count()
+        self.step()
+        self.launches_per_step = self.lib.launch_count() - n0
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        self.graph = g
+
+    def replay(self):
+        self.graph.replay()
+
+
+def profile_ops(net, batch, size, device, iters=5):
+    """Per-op CUDA-event timings of the forward plan (one dcfa_run_ops call per op)."""
+    import ctypes as C
+    from dcfa_b200 import _lib, abi
+    from dcfa_b200 import plan as P
+    eng = net._engine(batch, size, size, device)
+    rgb = torch.rand(batch, 3, size, size, device=device)
+    nir = torch.rand(batch, 3, size, size, device=device)
+    eng.run(rgb, nir)
+    torch.cuda.synchronize()
+    n = eng.n_ops
+    st = torch.cuda.current_stream(device)
+    tot = np.zeros(n)
+    for _ in range(iters):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record(st)
+        for i in range(n):
+            op1 = (abi.Op * 1)(eng.plan.ops[i])
+            _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+            evs[i + 1].record(st)
+        torch.cuda.synchronize()
+        tot += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n)])
+    ms = tot / iters
+    rows = []
+    for i, op in enumerate(eng.plan.ops):
+        flops = 0
+        if op.kind == abi.OP_CONV:
+            flops = 2 * op.n_img * op.Ho * op.Wo * op.Cout * op.K_real
+        rows.append({"i": i, "name": eng.plan.op_names[i], "kind": abi.OP_NAMES[op.kind], "ms": float(ms[i]), "flops": flops,
+                     "shape": [op.n_img, op.Hi, op.Wi, op.Cin, op.Cout, op.ksize, op.stride]})
+    return rows, eng
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, S, K, W = args.batch, args.size, args.steps, max(args.warmup, 3)
+
+    net = build_model(args.phi, S, device)
+    pipe = Pipeline(net, B, S, device)
+    pipe.capture()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, graph replay
+    for _ in range(W):
+        pipe.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            pipe.replay()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total / 1e3)
+    cand = pipe.ws.cand.cpu().numpy()
+    kept = pipe.ws.cnt.cpu().numpy()
+
+    # ---- e2e: public API, pinned host inputs in, detections out, every step
+    host_rgb = torch.rand(B, 3, S, S).pin_memory()
+    host_nir = torch.rand(B, 3, S, S).pin_memory()
+    from utils.utils_bbox import DecodeBox
+    dec = DecodeBox(1, (S, S))
+    img_shape = np.array([S, S])
+
+    def e2e_step():
+        r = host_rgb.to(device, non_blocking=True)
+        d = host_nir.to(device, non_blocking=True)
+        out = net(r, d)
+        y = dec.decode_box(out)
+        return dec.non_max_suppression(y, 1, [S, S], img_shape, True, conf_thres=CONF, nms_thres=IOU)
+
+    for _ in range(W):
+        res = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        res = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms)   # the step ends on the host (numpy detections), so wall clock bounds it
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * K / (e2e_ms / 1e3)
+    h2d = 2 * B * 3 * S * S * 4
+    d2h = B * (1 + min(pipe.ws.a, dec.first_fetch) * 6) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (conv implicit GEMM), measured live with CUDA events per launch
+    peaks = measured_peaks()
+    rows, eng = profile_ops(net, B, S, device)
+    conv = [r for r in rows if r["kind"] == "conv"]
+    conv_ms, conv_fl = sum(r["ms"] for r in conv), sum(r["flops"] for r in conv)
+    all_ms = sum(r["ms"] for r in rows)
+    achieved = conv_fl / (conv_ms / 1e3) / 1e12
+    by_kind = {}
+    for r in rows:
+        by_kind[r["kind"]] = by_kind.get(r["kind"], 0.0) + r["ms"]
+    if args.profile_ops:
+        with open(args.profile_ops, "w") as f:
+            json.dump({"batch": B, "size": S, "phi": args.phi, "ms_by_kind": by_kind, "ops": rows}, f, indent=1)
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": round(achieved, 2), "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["src"],
+                "launches_per_step": len(conv), "kernel_ms_per_step": round(conv_ms, 4),
+                "share_of_forward": round(conv_ms / all_ms, 3), "ms_by_kind": {k: round(v, 4) for k, v in by_kind.items()}}
+    flops_pair = eng.plan.conv_flops / B
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "DCFA-YOLO phi='%s' bf16 inference fwd+decode+NMS, batch %d per GPU, %dx%d RGB+depth, 1 class, "
+                               "constructor-init weights (BASELINE.json configs[1])" % (args.phi, B, S, S),
+                   "pairs_per_step_per_gpu": B, "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
+                   "l2": "inputs (%.0f MB fp32 per step) exceed the 126 MB L2" % (h2d / 1e6), "conf_thres": CONF, "nms_thres": IOU,
+                   "nms_candidates_per_image": float(cand.mean()), "kept_per_image": float(kept.mean())},
+        "tensor_roofline_frac_whole_step": round(value / world * flops_pair / (peaks["tflops"] * 1e12), 4),
+        "conv_gflop_per_pair": round(flops_pair / 1e9, 3),
+        "clocks": clk.summary(),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(e2e_ms / K, 4)},
+        "gpu_launches": int(pipe.launches_per_step * K),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.phi, S, args.ref_batch, args.cpu_baseline_seconds)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
