@@ -29,7 +29,7 @@ constexpr int kMmaWarp = 4;
 constexpr int kProdWarp0 = 5;
 constexpr int kProdWarps = 4;
 constexpr int kThreads = 32 * (kEpiWarps + 1 + kProdWarps);
-constexpr int kLag = 2;           // producer signals stage i once the cp.async groups up to i have landed
+constexpr int kMaxLag = 6;        // producer signals stage i-lag once its cp.async group has landed (lag = stages-2)
 constexpr int kMaxStages = 8;
 constexpr int kRowsPerProdThread = BM / (kProdWarps * 32 / 8);  // 8
 
@@ -51,8 +51,22 @@ struct ConvArgs {
   int m_tiles;            // M tiles per group
   int total_tiles;
   int stages;
+  int lag;
   uint32_t tmem_cols;
 };
+
+// cp.async.wait_group takes an immediate; n is warp-uniform
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: ptx::cp_async_wait<0>(); break;
+    case 1: ptx::cp_async_wait<1>(); break;
+    case 2: ptx::cp_async_wait<2>(); break;
+    case 3: ptx::cp_async_wait<3>(); break;
+    case 4: ptx::cp_async_wait<4>(); break;
+    case 5: ptx::cp_async_wait<5>(); break;
+    default: ptx::cp_async_wait<6>(); break;
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -104,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
     const uint32_t dst_thread =
         (uint32_t)(row_base >> 3) * 1024u + (uint32_t)(row_base & 7) * 128u + (uint32_t)((chunk ^ (row_base & 7)) << 4);
     uint32_t it = 0;
+    const uint32_t lag = (uint32_t)p.lag;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -155,20 +170,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
           ptx::cp_async_16(dst + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
         }
         ptx::cp_async_commit();
-        if (it >= (uint32_t)kLag) {
-          ptx::cp_async_wait<kLag>();
+        if (it >= lag) {
+          cp_async_wait_dyn(p.lag);   // the group issued `lag` iterations ago has landed
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_full + 8u * ((it - kLag) % (uint32_t)S));
+          if (lane == 0) ptx::mbar_arrive(bar_full + 8u * ((it - lag) % (uint32_t)S));
         }
       }
     }
-    // drain the last kLag stages
+    // drain the last `lag` stages
     ptx::cp_async_wait<0>();
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      const uint32_t first = it > (uint32_t)kLag ? it - kLag : 0u;
+      const uint32_t first = it > lag ? it - lag : 0u;
       for (uint32_t j = first; j < it; ++j) ptx::mbar_arrive(bar_full + 8u * (j % (uint32_t)S));
     }
   } else if (warp == kMmaWarp) {
@@ -357,8 +372,9 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   const int fixed = 1024 /*alignment slack*/ + 256 /*barriers*/;
   int stages = (max_smem - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  DCFA_REQUIRE(stages > kLag, "conv: not enough shared memory for the pipeline");
+  DCFA_REQUIRE(stages >= 3, "conv: not enough shared memory for the pipeline");
   a.stages = stages;
+  a.lag = stages - 2 < kMaxLag ? stages - 2 : kMaxLag;
   const int smem = fixed + stages * stage_bytes;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;

@@ -271,20 +271,24 @@ class Plan:
         N2 = 2 * B
         mods = ('backbone_rgb', 'backbone_nir')
 
-        # ---- stems (nets/yolo_mul.py:104-115): BN scale folded into fp32 weights [G][27][C0], k = (ky*3+kx)*3+ci
-        ws, bs = [], []
+        # ---- stems (nets/yolo_mul.py:104-115): one swizzled bf16 weight tile per modality, fp32 scale/bias epilogue
+        packed, scs, bis, meta = [], [], [], None
         for m in mods:
             sc, bi = self._bn(m + '.stem.conv.1', 1e-5)
-            w = s[m + '.stem.conv.0.weight'] * sc.view(-1, 1, 1, 1)
-            ws.append(w.permute(2, 3, 1, 0).reshape(27, bc).contiguous().reshape(-1))
-            bs.append(bi)
-        w_off = self.blob.add(torch.cat(ws))
-        b_off = self.blob.add(torch.cat(bs))
+            pk, meta = pack.pack_conv_weight(s[m + '.stem.conv.0.weight'])
+            packed.append(pk)
+            scs.append(pack.pad_channels(sc, meta['BN']))
+            bis.append(pack.pad_channels(bi, meta['BN']))
+        w_off = self.blob.add(torch.cat(packed))
+        sc_off = self.blob.add(torch.cat(scs))
+        b_off = self.blob.add(torch.cat(bis))
         h1, w1 = down2(H), down2(W)
         x = self._tensor(N2, h1, w1, bc)
         self._emit('stem', abi.new_op(abi.OP_STEM, x=_flat(BUF_RGB, 0), x2=_flat(BUF_NIR, 0), w=_flat(BUF_BLOB, w_off),
-                                      bias=_flat(BUF_BLOB, b_off), y=x.view(), n_img=N2, group_imgs=B, Hi=H, Wi=W,
-                                      Ho=h1, Wo=w1, Cout=bc, Cin=3, ksize=3, stride=1))
+                                      scale=_flat(BUF_BLOB, sc_off), bias=_flat(BUF_BLOB, b_off), y=x.view(), n_img=N2,
+                                      group_imgs=B, Hi=H, Wi=W, Ho=h1, Wo=w1, Cout=bc, Cin=3, ksize=3, stride=1,
+                                      BN=meta['BN'], n_tiles=1, k_blocks=1, K_real=27, w_gstride=meta['BN'] * 64,
+                                      sb_gstride=meta['BN']))
         self.conv_flops += 2 * N2 * H * W * bc * 27
 
         # ---- dark2..dark5 (nets/yolo_mul.py:258-277)

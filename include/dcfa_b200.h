@@ -96,9 +96,10 @@ typedef struct dcfa_view {
 /*
  * One op of the flat execution plan.  Field use per kind:
  *
- * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = fp32 [G][27][Cout]
- *        (BN scale folded, k = (ky*3+kx)*3+ci); bias = fp32 [G][Cout]; y = bf16 NHWC [n_img,Ho,Wo,Cout],
- *        Ho = Hi/2, Wo = Wi/2.
+ * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 packed [G][BN*64] (one
+ *        128B-swizzled K-major tile per group, K = (ky*3+kx)*3+ci padded to 64, rows = Cout padded to BN);
+ *        scale,bias = fp32 [G][BN] (folded BN); y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
+ *        BN, n_tiles = 1, k_blocks = 1, K_real = 27 describe the packing.
  * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed
  *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
  *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added
@@ -114,7 +115,7 @@ typedef struct dcfa_view {
  * UPSAMPLE    x (+ x2 if present, summed first) [n_img,Hi,Wi,Cin] -> y [n_img,Ho,Wo,Cin] bilinear,
  *             align_corners=True.
  * DFL    x = fp32 NCHW head maps of the 3 levels at a0.off/a1.off/a2.off inside buffers a0/a1/a2.buf
- *        ([n_img, 64+nc, H_l, W_l], H_l = Hi>>l, W_l = Wi>>l for l = 0,1,2 taken from Hi,Wi of level 0);
+ *        ([n_img, 64+nc, H_l, W_l]; level 0 is Hi x Wi, each further level halves with ceil);
  *        y = fp32 dbox [n_img,4,A]; x2 = fp32 cls logits out [n_img,nc,A].
  */
 typedef struct dcfa_op {

@@ -76,16 +76,18 @@ def run_ops(ops, bufs):
         n = op.n_img
         G = n // op.group_imgs if op.group_imgs > 0 else 1
         gi = n // G
-        if k == 1:  # STEM
+        if k == 1:  # STEM: bf16 inputs and weights, fp32 accumulate, fp32 scale/bias, ReLU, pool, bf16 store
             c0 = op.Cout
-            w = _f32(bufs[op.w.buf], op.w.off, G * 27 * c0).view(G, 3, 3, 3, c0)  # (ky,kx,ci,co)
-            b = _f32(bufs[op.bias.buf], op.bias.off, G * c0).view(G, c0)
+            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, op.BN, 1, 1)
+            sc = _f32(bufs[op.scale.buf], op.scale.off, G * op.sb_gstride).view(G, -1)
+            bi = _f32(bufs[op.bias.buf], op.bias.off, G * op.sb_gstride).view(G, -1)
             outs = []
             for g in range(G):
                 src = bufs[op.x.buf] if g == 0 else bufs[op.x2.buf]
-                x = src.view(torch.float32).view(gi, 3, op.Hi, op.Wi)
-                wt = w[g].permute(3, 2, 0, 1).contiguous()
-                y = F.max_pool2d(F.relu(F.conv2d(x, wt, b[g], 1, 1)), 3, 2, 1)
+                x = src.view(torch.float32).view(gi, 3, op.Hi, op.Wi).to(torch.bfloat16).float()
+                wt = wall[g, :c0, :27].view(c0, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                y = F.conv2d(x, wt, None, 1, 1) * sc[g, :c0].view(1, -1, 1, 1) + bi[g, :c0].view(1, -1, 1, 1)
+                y = F.max_pool2d(F.relu(y), 3, 2, 1)
                 outs.append(y.permute(0, 2, 3, 1))
             write_nhwc(bufs, op.y, torch.cat(outs))
         elif k == 2:  # CONV
