@@ -14,6 +14,12 @@
 //
 // Persistent CTAs (grid = min(tiles, SMs)), 9 warps:
 //   warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 MMA issue + TMEM alloc, warps 5-8 gather.
+//
+// The gather is the critical loop (ncu, round 1: producer warps were issue-latency bound at ~2400 cycles per
+// k-block).  Per tile each producer thread now precomputes, for its 8 rows, a base pointer and a 9-bit mask of
+// the taps that fall inside the image; per k-block a row costs one mask test, one 64-bit add and the cp.async.
+// 1x1 stride-1 convs over pixel-linear tensors skip the (n, y, x) decomposition entirely; all divisions use
+// host-computed magic numbers.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,6 +38,24 @@ constexpr int kThreads = 32 * (kEpiWarps + 1 + kProdWarps);
 constexpr int kMaxLag = 6;        // producer signals stage i-lag once its cp.async group has landed (lag = stages-2)
 constexpr int kMaxStages = 8;
 constexpr int kRowsPerProdThread = BM / (kProdWarps * 32 / 8);  // 8
+
+// n / d for 0 <= n < 2^31 with a host-computed magic multiplier (d == 1 -> mul == 0)
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shr) : n; }
+};
+
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    const uint32_t p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
 
 struct ConvArgs {
   View<const __nv_bfloat16> x;
@@ -52,6 +76,9 @@ struct ConvArgs {
   int total_tiles;
   int stages;
   int lag;
+  int x_linear;           // 1x1 stride-1 conv over a pixel-linear input: row m of group g is pixel g*Mg + m
+  int y_linear;           // bf16 output (and residual) are pixel-linear
+  FastDiv div_howo, div_wo, div_cin;
   uint32_t tmem_cols;
 };
 
@@ -117,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
     const int row_base = ptid >> 3;                  // 0..15 ; rows row_base + 16*i
     const uint32_t dst_thread =
         (uint32_t)(row_base >> 3) * 1024u + (uint32_t)(row_base & 7) * 128u + (uint32_t)((chunk ^ (row_base & 7)) << 4);
+    const int ntaps = p.ksize * p.ksize;
     uint32_t it = 0;
     const uint32_t lag = (uint32_t)p.lag;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -124,23 +152,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int g = rest / p.m_tiles;
-      int64_t img_off[kRowsPerProdThread];
-      int iy0[kRowsPerProdThread], ix0[kRowsPerProdThread];
+      const __nv_bfloat16* rowptr[kRowsPerProdThread];  // address of tap (0,0), channel 0 of the row's window
+      uint32_t tapmask[kRowsPerProdThread];             // bit t: tap t of this row lies inside the image
 #pragma unroll
       for (int i = 0; i < kRowsPerProdThread; ++i) {
         const int m = mt * BM + row_base + 16 * i;
+        rowptr[i] = p.x.p;
+        tapmask[i] = 0u;
         if (m < p.Mg) {
-          const int nl = m / HoWo;
-          const int rem = m - nl * HoWo;
-          const int oy = rem / p.Wo;
-          const int ox = rem - oy * p.Wo;
-          img_off[i] = p.x.img_off(g * p.group_imgs + nl);
-          iy0[i] = oy * p.stride - p.pad;
-          ix0[i] = ox * p.stride - p.pad;
-        } else {
-          img_off[i] = 0;
-          iy0[i] = -(1 << 28);  // always out of bounds -> zero rows
-          ix0[i] = 0;
+          if (p.x_linear) {
+            rowptr[i] = p.x.p + ((int64_t)g * p.Mg + m) * p.x.ld;
+            tapmask[i] = 1u;
+          } else {
+            const int nl = (int)p.div_howo.div((uint32_t)m);
+            const int rem = m - nl * HoWo;
+            const int oy = (int)p.div_wo.div((uint32_t)rem);
+            const int ox = rem - oy * p.Wo;
+            const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+            rowptr[i] = p.x.p + p.x.img_off(g * p.group_imgs + nl) + ((int64_t)iy0 * p.Wi + ix0) * p.x.ld;
+            uint32_t mk = 0u;
+            for (int t = 0; t < ntaps; ++t) {
+              const int dy = (t * 11) >> 5, dx = t - 3 * dy;  // t / 3, t % 3 for t < 9 (ksize 1: t == 0)
+              const int iy = iy0 + dy, ix = ix0 + dx;
+              if (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) mk |= 1u << t;
+            }
+            tapmask[i] = mk;
+          }
         }
       }
       const __nv_bfloat16* wtile = p.w + (int64_t)g * p.w_gstride + (int64_t)nt * p.k_blocks * (p.BN * BK);
@@ -154,20 +191,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
                         bar_full + 8u * s);
         }
         const int k = kb * BK + chunk * 8;
-        const bool kvalid = k < p.K_real;
-        const int tap = k / p.Cin;
-        const int ch = k - tap * p.Cin;
-        const int dy = tap / p.ksize;
-        const int dx = tap - dy * p.ksize;
+        int tap = 0, tap_off = 0;
+        uint32_t kbit = 0u;
+        if (k < p.K_real) {
+          tap = (int)p.div_cin.div((uint32_t)k);
+          const int ch = k - tap * p.Cin;
+          const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+          tap_off = (dy * p.Wi + dx) * p.x.ld + ch;
+          kbit = 1u << tap;
+        }
         const uint32_t dst = smem_a + s * A_STAGE_BYTES + dst_thread;
 #pragma unroll
         for (int i = 0; i < kRowsPerProdThread; ++i) {
-          const int iy = iy0[i] + dy;
-          const int ix = ix0[i] + dx;
-          const bool ok = kvalid && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi;
-          const __nv_bfloat16* src =
-              ok ? p.x.p + img_off[i] + (int64_t)(iy * p.Wi + ix) * p.x.ld + ch : p.x.p;
-          ptx::cp_async_16(dst + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
+          const bool ok = (tapmask[i] & kbit) != 0u;
+          ptx::cp_async_16(dst + (uint32_t)i * 2048u, ok ? rowptr[i] + tap_off : p.x.p, ok ? 16u : 0u);
         }
         ptx::cp_async_commit();
         if (it >= lag) {
@@ -230,23 +267,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
 
       const int m = mt * BM + r;
       const bool rvalid = m < p.Mg;
-      int n = 0, pix = 0;
-      if (rvalid) {
-        const int nl = m / HoWo;
-        pix = m - nl * HoWo;
-        n = g * p.group_imgs + nl;
-      }
       const float* sc = p.scale + (int64_t)g * p.sb_gstride + nt * p.BN;
       const float* bi = p.bias + (int64_t)g * p.sb_gstride + nt * p.BN;
       __nv_bfloat16* yb = nullptr;
       float* yf = nullptr;
       const __nv_bfloat16* rb = nullptr;
       if (rvalid) {
-        if (p.out_mode == DCFA_OUT_BF16_NHWC) {
-          yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld;
-          if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld;
+        if (p.out_mode == DCFA_OUT_BF16_NHWC && p.y_linear) {
+          const int64_t gm = (int64_t)g * p.Mg + m;
+          yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + gm * p.y.ld;
+          if (p.res.p) rb = p.res.p + gm * p.res.ld;
         } else {
-          yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)p.out_coff * HoWo + pix;
+          const int nl = (int)p.div_howo.div((uint32_t)m);
+          const int pix = m - nl * HoWo;
+          const int n = g * p.group_imgs + nl;
+          if (p.out_mode == DCFA_OUT_BF16_NHWC) {
+            yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld;
+            if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld;
+          } else {
+            yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)p.out_coff * HoWo + pix;
+          }
         }
       }
 
@@ -306,6 +346,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
   }
 }
 
+template <typename T>
+bool pixel_linear(const View<T>& v, int64_t hw) {
+  return v.img_stride == hw * v.ld && (v.gi <= 0 || v.gstride == (int64_t)v.gi * v.img_stride);
+}
+
 }  // namespace
 
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
@@ -341,6 +386,7 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(a.k_blocks == (a.K_real + BK - 1) / BK, "conv: k_blocks mismatch");
   DCFA_REQUIRE(((uintptr_t)a.x.p % 16) == 0 && a.x.ld % 8 == 0 && a.x.img_stride % 8 == 0 && a.x.gstride % 8 == 0,
                "conv: input view must be 16-byte aligned");
+  DCFA_REQUIRE((int64_t)a.Hi * a.Wi * a.x.ld < (1ll << 31), "conv: image too large for 32-bit tap offsets");
   DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0 && a.w_gstride % 8 == 0, "conv: weights must be 16-byte aligned");
   DCFA_REQUIRE(((uintptr_t)a.scale % 16) == 0 && ((uintptr_t)a.bias % 16) == 0 && a.sb_gstride % 4 == 0,
                "conv: scale/bias must be 16-byte aligned");
@@ -366,6 +412,16 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   const int64_t total = (int64_t)a.n_groups * a.m_tiles * a.n_tiles;
   DCFA_REQUIRE(total < (1ll << 31), "conv: too many tiles");
   a.total_tiles = (int)total;
+  a.div_howo = make_fastdiv((uint32_t)(a.Ho * a.Wo));
+  a.div_wo = make_fastdiv((uint32_t)a.Wo);
+  a.div_cin = make_fastdiv((uint32_t)a.Cin);
+  // group g's images are [g*group_imgs, (g+1)*group_imgs): with a pixel-linear tensor, GEMM row m of group g
+  // is simply pixel g*Mg + m (valid for 1x1 stride-1 inputs and for any output)
+  a.x_linear = (a.ksize == 1 && a.stride == 1 && pixel_linear(a.x, (int64_t)a.Hi * a.Wi)) ? 1 : 0;
+  a.y_linear = (a.out_mode == DCFA_OUT_BF16_NHWC && pixel_linear(a.y, (int64_t)a.Ho * a.Wo) &&
+                (!a.res.p || pixel_linear(a.res, (int64_t)a.Ho * a.Wo)))
+                   ? 1
+                   : 0;
 
   const int stage_bytes = A_STAGE_BYTES + a.BN * 128;
   const int max_smem = 227 * 1024;
