@@ -114,6 +114,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // launchers implemented in the individual .cu files (host side; bufs already resolved by the caller)
 int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_pool(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_mlp(const dcfa_op& op, void* const* bufs, cudaStream_t st);

@@ -20,6 +20,8 @@
 // the taps that fall inside the image; per k-block a row costs one mask test, one 64-bit add and the cp.async.
 // 1x1 stride-1 convs over pixel-linear tensors skip the (n, y, x) decomposition entirely; all divisions use
 // host-computed magic numbers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -35,7 +37,7 @@ constexpr int kMmaWarp = 4;
 constexpr int kProdWarp0 = 5;
 constexpr int kProdWarps = 4;
 constexpr int kThreads = 32 * (kEpiWarps + 1 + kProdWarps);
-constexpr int kMaxLag = 6;        // producer signals stage i-lag once its cp.async group has landed (lag = stages-2)
+
 constexpr int kMaxStages = 8;
 constexpr int kRowsPerProdThread = BM / (kProdWarps * 32 / 8);  // 8
 
@@ -75,25 +77,13 @@ struct ConvArgs {
   int m_tiles;            // M tiles per group
   int total_tiles;
   int stages;
-  int lag;
+
   int x_linear;           // 1x1 stride-1 conv over a pixel-linear input: row m of group g is pixel g*Mg + m
   int y_linear;           // bf16 output (and residual) are pixel-linear
   FastDiv div_howo, div_wo, div_cin;
   uint32_t tmem_cols;
+  int dbg;
 };
-
-// cp.async.wait_group takes an immediate; n is warp-uniform
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-  switch (n) {
-    case 0: ptx::cp_async_wait<0>(); break;
-    case 1: ptx::cp_async_wait<1>(); break;
-    case 2: ptx::cp_async_wait<2>(); break;
-    case 3: ptx::cp_async_wait<3>(); break;
-    case 4: ptx::cp_async_wait<4>(); break;
-    case 5: ptx::cp_async_wait<5>(); break;
-    default: ptx::cp_async_wait<6>(); break;
-  }
-}
 
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -117,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        ptx::mbar_init(bar_full + 8u * s, kProdWarps + 1);  // 4 warp arrivals + 1 expect_tx arrival
+        ptx::mbar_init(bar_full + 8u * s, kProdWarps * 32 + 1);  // 128 cp.async completions + 1 expect_tx arrival
         ptx::mbar_init(bar_empty + 8u * s, 1);              // one tcgen05.commit
       }
       for (int a = 0; a < 2; ++a) {
@@ -146,7 +136,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
         (uint32_t)(row_base >> 3) * 1024u + (uint32_t)(row_base & 7) * 128u + (uint32_t)((chunk ^ (row_base & 7)) << 4);
     const int ntaps = p.ksize * p.ksize;
     uint32_t it = 0;
-    const uint32_t lag = (uint32_t)p.lag;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -206,22 +195,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
           const bool ok = (tapmask[i] & kbit) != 0u;
           ptx::cp_async_16(dst + (uint32_t)i * 2048u, ok ? rowptr[i] + tap_off : p.x.p, ok ? 16u : 0u);
         }
-        ptx::cp_async_commit();
-        if (it >= lag) {
-          cp_async_wait_dyn(p.lag);   // the group issued `lag` iterations ago has landed
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_full + 8u * ((it - lag) % (uint32_t)S));
-        }
+        // arrives on the stage's full barrier when all cp.asyncs of this thread have landed; the producer
+        // never blocks on its own loads, so up to `stages` k-blocks are in flight per SM
+        ptx::cp_async_mbar_arrive_noinc(bar_full + 8u * s);
       }
-    }
-    // drain the last `lag` stages
-    ptx::cp_async_wait<0>();
-    ptx::fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t first = it > lag ? it - lag : 0u;
-      for (uint32_t j = first; j < it; ++j) ptx::mbar_arrive(bar_full + 8u * (j % (uint32_t)S));
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
@@ -237,8 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
         const uint32_t s = it % (uint32_t)S;
         const uint32_t ph = (it / (uint32_t)S) & 1u;
         ptx::mbar_wait(bar_full + 8u * s, ph);
-        ptx::tc_fence_after();
         if (lane == 0) {
+          if (p.dbg & 1) ptx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+          ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(smem_a + s * A_STAGE_BYTES);
           const uint64_t bdesc = ptx::make_sw128_kmajor_desc(smem_b + s * b_stage_bytes);
 #pragma unroll
@@ -354,6 +332,7 @@ bool pixel_linear(const View<T>& v, int64_t hw) {
 }  // namespace
 
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
+  if ((op.flags & 0xff) != 0) return launch_conv_tma(op, bufs, st);  // packed per (tap, channel block): TMA path
   ConvArgs a;
   a.x = resolve<const __nv_bfloat16>(op.x, bufs);
   a.res = resolve<const __nv_bfloat16>(op.x2, bufs);
@@ -430,11 +409,12 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   if (stages > kMaxStages) stages = kMaxStages;
   DCFA_REQUIRE(stages >= 3, "conv: not enough shared memory for the pipeline");
   a.stages = stages;
-  a.lag = stages - 2 < kMaxLag ? stages - 2 : kMaxLag;
+
   const int smem = fixed + stages * stage_bytes;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
+  { const char* e = getenv("DCFA_DBG"); a.dbg = e ? atoi(e) : 1; }
 
   static bool attr_set = false;
   if (!attr_set) {

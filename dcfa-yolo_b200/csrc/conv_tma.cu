@@ -1,0 +1,439 @@
+// DCFA_OP_CONV, TMA path: implicit-GEMM convolution whose A operand is fetched by the Tensor Memory
+// Accelerator instead of per-thread cp.async (ncu, round 1: the cp.async gather saturated at ~8 B/cycle/SM).
+//
+// The NHWC bf16 input view is described once per launch by a rank-4 tensor map (C, W, H, N).  An M tile is a
+// th x tw rectangle of output pixels of ONE image; the A tile of filter tap (dy, dx) and channel block cb is then
+// a single box load at coordinates (cb*BK, x0*s - pad + dx, y0*s - pad + dy, n):
+//   * out-of-image taps and partial tiles are zero-filled by the TMA (conv zero padding for free);
+//   * stride-2 convolutions use the map's elementStrides = 2 traversal;
+//   * the box lands in shared memory already in the K-major swizzled layout tcgen05.mma reads
+//     (SWIZZLE_128B / 64B / 32B for BK = 64 / 32 / 16 channels per stage).
+// One thread issues, per k-block, one cp.async.bulk.tensor (A) and one cp.async.bulk (pre-swizzled W tile);
+// both complete on the stage's mbarrier through transaction bytes.  One thread issues tcgen05.mma into a
+// double-buffered TMEM accumulator; two groups of four epilogue warps (one per accumulator stage) apply the
+// fused epilogue (folded-BN scale/bias, ReLU/SiLU, post-scale, residual) and store bf16 NHWC at a channel
+// offset or fp32 NCHW.  Persistent CTAs, 10 warps:
+//   warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer + TMEM alloc, warps 6-9 epilogue group 1.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dcfa {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int kTmaWarp = 4;
+constexpr int kMmaWarp = 5;
+constexpr int kThreads = 320;
+constexpr int kMaxStages = 8;
+
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shr) : n; }
+};
+
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    const uint32_t p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+
+struct TmaConvArgs {
+  View<const __nv_bfloat16> res;
+  View<void> y;
+  const __nv_bfloat16* w;
+  const float* scale;
+  const float* bias;
+  int64_t w_gstride;
+  int64_t sb_gstride;
+  int n_img, group_imgs;
+  int Ho, Wo, Cout, ksize, stride, pad;
+  int BN, n_tiles, k_blocks;
+  int bk;                 // channels per k-block (64 / 32 / 16)
+  int cblocks;            // Cin / bk
+  int act, out_mode, out_ctot, out_coff;
+  float post_scale;
+  int tw, th;             // spatial M tile (tw*th <= 128)
+  int tiles_x, tiles_img; // tiles per image row / per image
+  int total_tiles;
+  int stages;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  uint32_t layout_type;   // UMMA descriptor swizzle code (2 / 4 / 6)
+  uint32_t sbo;           // 8 rows * row pitch
+  FastDiv div_tw, div_tiles_img, div_tiles_x, div_ntiles, div_cblocks;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                               const TmaConvArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.stages;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + (uint32_t)S * p.a_stage_bytes;
+  const uint32_t bars = smem_b + (uint32_t)S * p.b_stage_bytes;
+  const uint32_t bar_full = bars;
+  const uint32_t bar_empty = bars + 8u * kMaxStages;
+  const uint32_t bar_tfull = bars + 16u * kMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16u;
+  const uint32_t tmem_slot = bar_tempty + 16u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        ptx::mbar_init(bar_full + 8u * s, 1);   // one arrive.expect_tx; A and W complete through tx bytes
+        ptx::mbar_init(bar_empty + 8u * s, 1);  // one tcgen05.commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(bar_tfull + 8u * a, 1);
+        ptx::mbar_init(bar_tempty + 8u * a, 4);  // the four warps of the stage's epilogue group
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
+        const int nt = tile - (int)rest * p.n_tiles;
+        const int n = (int)p.div_tiles_img.div(rest);
+        const int timg = (int)rest - n * p.tiles_img;
+        const int ty = (int)p.div_tiles_x.div((uint32_t)timg);
+        const int tx = timg - ty * p.tiles_x;
+        const int g = n / p.group_imgs;
+        const int x0 = tx * p.tw * p.stride - p.pad;
+        const int y0 = ty * p.th * p.stride - p.pad;
+        const __nv_bfloat16* wtile = p.w + (int64_t)g * p.w_gstride + (int64_t)nt * p.k_blocks * (p.BN * p.bk);
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)S;
+          const uint32_t ph = (it / (uint32_t)S) & 1u;
+          const int tap = (int)p.div_cblocks.div((uint32_t)kb);
+          const int cb = kb - tap * p.cblocks;
+          const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;  // tap / 3, tap % 3 (tap < 9)
+          ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(bar_full + 8u * s, p.a_tx_bytes + p.b_tx_bytes);
+          tma_load_4d(smem_a + s * p.a_stage_bytes, &tmap, cb * p.bk, x0 + dx, y0 + dy, n, bar_full + 8u * s);
+          ptx::bulk_g2s(smem_b + s * p.b_stage_bytes, wtile + (int64_t)kb * (p.BN * p.bk), p.b_tx_bytes,
+                        bar_full + 8u * s);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN);
+    const int kk = p.bk >> 4;  // MMAs (K = 16) per k-block
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1u;
+      const uint32_t aph = (tcount >> 1) & 1u;
+      ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * (uint32_t)p.BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t s = it % (uint32_t)S;
+        const uint32_t ph = (it / (uint32_t)S) & 1u;
+        ptx::mbar_wait(bar_full + 8u * s, ph);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_kmajor_desc(smem_a + s * p.a_stage_bytes, p.sbo, p.layout_type);
+          const uint64_t bdesc = make_kmajor_desc(smem_b + s * p.b_stage_bytes, p.sbo, p.layout_type);
+          for (int k = 0; k < kk; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(bar_empty + 8u * s);
+          if (kb == p.k_blocks - 1) ptx::umma_commit(bar_tfull + 8u * as);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: group 0 = warps 0-3, group 1 = warps 6-9
+    const int group = warp < 4 ? 0 : 1;
+    const int q4 = warp & 3;           // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;      // accumulator row
+    const int iy = (int)p.div_tw.div((uint32_t)r);
+    const int ix = r - iy * p.tw;
+    const int HoWo = p.Ho * p.Wo;
+    uint32_t lc = 0;                   // tiles handled by this group so far
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      if ((int)(tcount & 1u) != group) continue;
+      const uint32_t as = (uint32_t)group;
+      const uint32_t aph = lc & 1u;
+      ++lc;
+      const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
+      const int nt = tile - (int)rest * p.n_tiles;
+      const int n = (int)p.div_tiles_img.div(rest);
+      const int timg = (int)rest - n * p.tiles_img;
+      const int ty = (int)p.div_tiles_x.div((uint32_t)timg);
+      const int tx = timg - ty * p.tiles_x;
+      const int g = n / p.group_imgs;
+      const int oy = ty * p.th + iy, ox = tx * p.tw + ix;
+      const bool rvalid = iy < p.th && oy < p.Ho && ox < p.Wo;
+      const int pix = oy * p.Wo + ox;
+      const float* sc = p.scale + (int64_t)g * p.sb_gstride + nt * p.BN;
+      const float* bi = p.bias + (int64_t)g * p.sb_gstride + nt * p.BN;
+      __nv_bfloat16* yb = nullptr;
+      float* yf = nullptr;
+      const __nv_bfloat16* rb = nullptr;
+      if (rvalid) {
+        if (p.out_mode == DCFA_OUT_BF16_NHWC) {
+          yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld;
+          if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld;
+        } else {
+          yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)p.out_coff * HoWo + pix;
+        }
+      }
+      ptx::mbar_wait(bar_tfull + 8u * as, aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
+      for (int j = 0; j < p.BN / 16; ++j) {
+        uint32_t acc[16];
+        ptx::tmem_ld_x16(taddr0 + (uint32_t)(j * 16), acc);
+        ptx::tmem_ld_wait();
+        const int c0 = nt * p.BN + j * 16;
+        if (rvalid && c0 < p.Cout) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j * 16) + q);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j * 16) + q);
+            v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
+            v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
+            v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
+            v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], p.act) * p.post_scale;
+          if (p.out_mode == DCFA_OUT_BF16_NHWC) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (c0 + 8 * h + 8 <= p.Cout) {
+                if (rb) {
+                  float rr[8];
+                  unpack8(ldg128(rb + c0 + 8 * h), rr);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[8 * h + e] += rr[e];
+                }
+                stg128(yb + c0 + 8 * h, pack8(v + 8 * h));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c0 + e < p.Cout) yf[(int64_t)(c0 + e) * HoWo] = v[e];
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8u * as);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// spatial tile (tw, th) with tw*th <= 128, tw <= 128/stride... maximising useful rows per 128-row MMA tile
+void pick_tile(int Ho, int Wo, int* tw_out, int* th_out) {
+  double best = -1.0;
+  int btw = 1, bth = 1;
+  for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th < 1) continue;
+    const int64_t tiles = (int64_t)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+    const double util = (double)Ho * Wo / (double)(tiles * 128);
+    // prefer wider tiles on ties (longer contiguous runs per box row)
+    if (util > best + 1e-9 || (util > best - 1e-9 && tw > btw)) {
+      best = util;
+      btw = tw;
+      bth = th;
+    }
+  }
+  *tw_out = btw;
+  *th_out = bth;
+}
+
+}  // namespace
+
+// Returns DCFA_OK after launching, or a negative code.  Called by launch_conv when the op was packed for TMA.
+int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
+  TmaConvArgs a;
+  View<const __nv_bfloat16> x = resolve<const __nv_bfloat16>(op.x, bufs);
+  a.res = resolve<const __nv_bfloat16>(op.x2, bufs);
+  a.y = resolve<void>(op.y, bufs);
+  a.w = resolve_ptr<const __nv_bfloat16>(op.w, bufs);
+  a.scale = resolve_ptr<const float>(op.scale, bufs);
+  a.bias = resolve_ptr<const float>(op.bias, bufs);
+  a.w_gstride = op.w_gstride;
+  a.sb_gstride = op.sb_gstride;
+  a.n_img = op.n_img;
+  a.group_imgs = op.group_imgs > 0 ? op.group_imgs : op.n_img;
+  const int Hi = op.Hi, Wi = op.Wi, Cin = op.Cin;
+  a.Ho = op.Ho; a.Wo = op.Wo; a.Cout = op.Cout;
+  a.ksize = op.ksize; a.stride = op.stride; a.pad = op.ksize / 2;
+  a.BN = op.BN; a.n_tiles = op.n_tiles; a.k_blocks = op.k_blocks;
+  a.bk = op.flags & 0xff;
+  a.act = op.act; a.out_mode = op.out_mode; a.out_ctot = op.out_ctot; a.out_coff = op.out_coff;
+  a.post_scale = op.f0;
+
+  DCFA_REQUIRE(x.p && a.y.p && a.w && a.scale && a.bias, "conv(tma): missing tensor");
+  DCFA_REQUIRE(a.bk == 64 || a.bk == 32 || a.bk == 16, "conv(tma): bk %d unsupported", a.bk);
+  DCFA_REQUIRE(Cin % a.bk == 0, "conv(tma): Cin %d not a multiple of bk %d", Cin, a.bk);
+  DCFA_REQUIRE(a.n_img > 0 && a.n_img % a.group_imgs == 0, "conv(tma): bad grouping");
+  DCFA_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv(tma): ksize %d unsupported", a.ksize);
+  DCFA_REQUIRE(a.stride == 1 || a.stride == 2, "conv(tma): stride %d unsupported", a.stride);
+  DCFA_REQUIRE(a.Ho == (Hi + 2 * a.pad - a.ksize) / a.stride + 1 && a.Wo == (Wi + 2 * a.pad - a.ksize) / a.stride + 1,
+               "conv(tma): output size inconsistent");
+  DCFA_REQUIRE(a.BN >= 16 && a.BN <= 256 && a.BN % 16 == 0, "conv(tma): BN %d invalid", a.BN);
+  DCFA_REQUIRE(a.n_tiles >= 1 && a.n_tiles * a.BN >= a.Cout, "conv(tma): n_tiles*BN < Cout");
+  a.cblocks = Cin / a.bk;
+  DCFA_REQUIRE(a.k_blocks == a.ksize * a.ksize * a.cblocks && op.K_real == a.ksize * a.ksize * Cin,
+               "conv(tma): k_blocks %d inconsistent with packing", a.k_blocks);
+  DCFA_REQUIRE(x.gi <= 0 || x.gstride == (int64_t)x.gi * x.img_stride, "conv(tma): grouped input views unsupported");
+  DCFA_REQUIRE(((uintptr_t)x.p % 16) == 0 && x.ld % 8 == 0 && x.img_stride % 8 == 0, "conv(tma): input must be 16-byte aligned");
+  DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0 && a.w_gstride % 8 == 0, "conv(tma): weights must be 16-byte aligned");
+  DCFA_REQUIRE(((uintptr_t)a.scale % 16) == 0 && ((uintptr_t)a.bias % 16) == 0 && a.sb_gstride % 4 == 0,
+               "conv(tma): scale/bias must be 16-byte aligned");
+  if (a.out_mode == DCFA_OUT_BF16_NHWC) {
+    DCFA_REQUIRE(a.Cout % 8 == 0, "conv(tma): bf16 output needs Cout %% 8 == 0");
+    DCFA_REQUIRE(((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 && a.y.gstride % 8 == 0,
+                 "conv(tma): output view must be 16-byte aligned");
+    if (a.res.p)
+      DCFA_REQUIRE(((uintptr_t)a.res.p % 16) == 0 && a.res.ld % 8 == 0 && a.res.img_stride % 8 == 0 && a.res.gstride % 8 == 0,
+                   "conv(tma): residual view must be 16-byte aligned");
+  } else {
+    DCFA_REQUIRE(a.out_mode == DCFA_OUT_F32_NCHW, "conv(tma): bad out_mode");
+    DCFA_REQUIRE(!a.res.p, "conv(tma): residual unsupported with fp32 NCHW output");
+    DCFA_REQUIRE(a.out_coff >= 0 && a.out_coff + a.Cout <= a.out_ctot, "conv(tma): NCHW channel slot out of range");
+    DCFA_REQUIRE(a.y.img_stride == (int64_t)a.out_ctot * a.Ho * a.Wo, "conv(tma): NCHW img_stride mismatch");
+  }
+
+  pick_tile(a.Ho, a.Wo, &a.tw, &a.th);
+  a.tiles_x = (a.Wo + a.tw - 1) / a.tw;
+  const int tiles_y = (a.Ho + a.th - 1) / a.th;
+  a.tiles_img = a.tiles_x * tiles_y;
+  const int64_t total = (int64_t)a.n_img * a.tiles_img * a.n_tiles;
+  DCFA_REQUIRE(total < (1ll << 31), "conv(tma): too many tiles");
+  a.total_tiles = (int)total;
+  a.div_tw = make_fastdiv((uint32_t)a.tw);
+  a.div_tiles_img = make_fastdiv((uint32_t)a.tiles_img);
+  a.div_tiles_x = make_fastdiv((uint32_t)a.tiles_x);
+  a.div_ntiles = make_fastdiv((uint32_t)a.n_tiles);
+  a.div_cblocks = make_fastdiv((uint32_t)a.cblocks);
+
+  const uint32_t pitch = (uint32_t)a.bk * 2u;  // bytes per K row of a stage
+  a.layout_type = a.bk == 64 ? 2u : (a.bk == 32 ? 4u : 6u);
+  a.sbo = 8u * pitch;
+  a.a_stage_bytes = 128u * pitch;                                  // multiple of 1024 for every bk
+  a.b_tx_bytes = (uint32_t)a.BN * pitch;
+  a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
+  a.a_tx_bytes = (uint32_t)(a.tw * a.th) * pitch;
+  const int stage_bytes = (int)(a.a_stage_bytes + a.b_stage_bytes);
+  const int max_smem = 227 * 1024;
+  const int fixed = 1024 + 256;
+  int stages = (max_smem - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  DCFA_REQUIRE(stages >= 2, "conv(tma): not enough shared memory");
+  a.stages = stages;
+  const int smem = fixed + stages * stage_bytes;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
+  a.tmem_cols = cols;
+
+  // ---- tensor map over the input view: dims (C, W, H, N), innermost first
+  EncodeTiledFn enc = encode_tiled_fn();
+  DCFA_REQUIRE(enc != nullptr, "conv(tma): cuTensorMapEncodeTiled entry point unavailable");
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)a.n_img};
+  const cuuint64_t gstr[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)Wi * x.ld * 2, (cuuint64_t)x.img_stride * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)a.bk, (cuuint32_t)(a.tw * a.stride), (cuuint32_t)(a.th * a.stride), 1u};
+  const cuuint32_t estr[4] = {1u, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1u};
+  DCFA_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv(tma): box too large");
+  const CUtensorMapSwizzle swz = a.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x.p), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled failed with %d", (int)cr);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "conv(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  conv_tma_kernel<<<grid, kThreads, smem, st>>>(tmap, a);
+  DCFA_CHECK_LAUNCH("conv_tma_kernel");
+  return DCFA_OK;
+}
+
+}  // namespace dcfa

@@ -25,32 +25,46 @@ def conv_tiling(cout):
     return bn, n_tiles
 
 
+def pick_bk(cin):
+    """Channels per k-block of the TMA conv path (0: Cin is not a multiple of 16 -> cp.async gather path, flat K)."""
+    for bk in (64, 32, 16):
+        if cin % bk == 0:
+            return bk
+    return 0
+
+
 def swizzle_tile(tile):
-    """[rows, 64] bf16 K-major tile -> the 128B-swizzled image the UMMA descriptor (SWIZZLE_128B) reads:
-    16-byte chunk c of row r is stored at chunk position c ^ (r % 8)."""
-    rows = tile.shape[0]
-    t = tile.reshape(rows, 8, 8)
-    idx = (torch.arange(8)[None, :] ^ (torch.arange(rows) % 8)[:, None])  # XOR is an involution
-    return torch.gather(t, 1, idx[:, :, None].expand(rows, 8, 8)).reshape(rows, 64)
+    """[rows, bk] bf16 K-major tile (bk = 64 / 32 / 16) -> the swizzled image the UMMA descriptor reads
+    (SWIZZLE_128B / 64B / 32B): with n = bk/8 16-byte chunks per row, chunk c of row r is stored at chunk
+    position c ^ ((r * n // 8) % n)  (address bits [4,4+log2 n) XOR bits [7,7+log2 n))."""
+    rows, bk = tile.shape
+    n = bk // 8
+    t = tile.reshape(rows, n, 8)
+    idx = (torch.arange(n)[None, :] ^ ((torch.arange(rows) * n // 8) % n)[:, None])  # XOR is an involution
+    return torch.gather(t, 1, idx[:, :, None].expand(rows, n, 8)).reshape(rows, bk)
 
 
-def pack_conv_weight(w):
+def pack_conv_weight(w, bk=None):
     """w: [Cout, Cin, k, k] fp32 (input channels already in PHYSICAL order) ->
-    (packed bf16 [n_tiles*k_blocks*BN*64], meta dict).  K index = (ky*k + kx)*Cin + ci."""
+    (packed bf16 [n_tiles*k_blocks*BN*bk], meta dict).  K index = (ky*k + kx)*Cin + ci.
+    bk > 0: one k-block per (tap, channel block of bk) -- the TMA path; bk == 0: flat K padded to 64 (gather path)."""
     cout, cin, k, _ = w.shape
+    if bk is None:
+        bk = pick_bk(cin)
     bn, n_tiles = conv_tiling(cout)
     k_real = k * k * cin
-    k_blocks = math.ceil(k_real / BK)
+    tile_k = bk if bk else BK
+    k_blocks = math.ceil(k_real / tile_k)
     wk = w.permute(0, 2, 3, 1).reshape(cout, k_real)
-    full = torch.zeros(n_tiles * bn, k_blocks * BK, dtype=torch.float32)
+    full = torch.zeros(n_tiles * bn, k_blocks * tile_k, dtype=torch.float32)
     full[:cout, :k_real] = wk
     full = full.to(torch.bfloat16)
     tiles = []
     for nt in range(n_tiles):
         for kb in range(k_blocks):
-            tiles.append(swizzle_tile(full[nt * bn:(nt + 1) * bn, kb * BK:(kb + 1) * BK]).reshape(-1))
+            tiles.append(swizzle_tile(full[nt * bn:(nt + 1) * bn, kb * tile_k:(kb + 1) * tile_k]).reshape(-1))
     packed = torch.cat(tiles)
-    meta = dict(BN=bn, n_tiles=n_tiles, k_blocks=k_blocks, K_real=k_real, Cout=cout, Cin=cin, ksize=k)
+    meta = dict(BN=bn, n_tiles=n_tiles, k_blocks=k_blocks, K_real=k_real, Cout=cout, Cin=cin, ksize=k, bk=bk)
     return packed, meta
 
 

@@ -134,7 +134,7 @@ class Plan:
                         bias=_flat(BUF_BLOB, bi_off), n_img=src.n, group_imgs=src.n // g, Hi=src.h, Wi=src.w, Cin=src.c,
                         Ho=ho, Wo=wo, Cout=meta['Cout'], ksize=k, stride=stride, BN=meta['BN'], n_tiles=meta['n_tiles'],
                         k_blocks=meta['k_blocks'], K_real=meta['K_real'], w_gstride=packed[0].numel(),
-                        sb_gstride=meta['BN'] * meta['n_tiles'], f0=post_scale)
+                        sb_gstride=meta['BN'] * meta['n_tiles'], f0=post_scale, flags=meta['bk'])
         if f32_out is None:
             assert dst.n == src.n and dst.h == ho and dst.w == wo and dst.c == meta['Cout'], name
             op.out_mode = abi.OUT_BF16_NHWC

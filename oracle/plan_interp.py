@@ -46,18 +46,20 @@ def write_nhwc(bufs, v, t):
         torch.as_strided(base, (gi, h, w, c), (v.img_stride, w * v.ld, v.ld, 1), off).copy_(tb[g * gi:(g + 1) * gi])
 
 
-def unswizzle_weights(blob, off, groups, w_gstride, bn, n_tiles, k_blocks):
-    """Inverse of pack.pack_conv_weight -> float32 [groups, n_tiles*bn, k_blocks*64]."""
+def unswizzle_weights(blob, off, groups, w_gstride, bn, n_tiles, k_blocks, bk=0):
+    """Inverse of pack.pack_conv_weight -> float32 [groups, n_tiles*bn, k_blocks*tile_k] (tile_k = bk or 64)."""
+    tk = bk if bk else BK
+    nch = tk // 8
     flat = blob.view(torch.bfloat16)[off // 2: off // 2 + groups * w_gstride].float()
-    out = torch.zeros(groups, n_tiles * bn, k_blocks * BK)
-    idx = (torch.arange(8)[None, :] ^ (torch.arange(bn) % 8)[:, None])
+    out = torch.zeros(groups, n_tiles * bn, k_blocks * tk)
+    idx = (torch.arange(nch)[None, :] ^ ((torch.arange(bn) * nch // 8) % nch)[:, None])
     for g in range(groups):
-        tiles = flat[g * w_gstride: g * w_gstride + n_tiles * k_blocks * bn * BK].view(n_tiles, k_blocks, bn, 8, 8)
+        tiles = flat[g * w_gstride: g * w_gstride + n_tiles * k_blocks * bn * tk].view(n_tiles, k_blocks, bn, nch, 8)
         for nt in range(n_tiles):
             for kb in range(k_blocks):
                 t = tiles[nt, kb]
-                un = torch.gather(t, 1, idx[:, :, None].expand(bn, 8, 8)).reshape(bn, BK)
-                out[g, nt * bn:(nt + 1) * bn, kb * BK:(kb + 1) * BK] = un
+                un = torch.gather(t, 1, idx[:, :, None].expand(bn, nch, 8)).reshape(bn, tk)
+                out[g, nt * bn:(nt + 1) * bn, kb * tk:(kb + 1) * tk] = un
     return out
 
 
@@ -92,7 +94,7 @@ def run_ops(ops, bufs):
             write_nhwc(bufs, op.y, torch.cat(outs))
         elif k == 2:  # CONV
             x = read_nhwc(bufs, op.x, n, op.Hi, op.Wi, op.Cin).permute(0, 3, 1, 2)
-            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, op.BN, op.n_tiles, op.k_blocks)
+            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, op.BN, op.n_tiles, op.k_blocks, op.flags & 0xff)
             npad = op.BN * op.n_tiles
             sc = _f32(bufs[op.scale.buf], op.scale.off, G * op.sb_gstride).view(G, -1)[:, :npad]
             bi = _f32(bufs[op.bias.buf], op.bias.off, G * op.sb_gstride).view(G, -1)[:, :npad]

@@ -24,11 +24,11 @@ def bf16_round(t):
 
 def conv_op(x, w_list, scale_list, bias_list, y, *, ksize, stride, act, cin, c_off_in=0, c_off_out=0, res=None,
             c_off_res=0, out_mode=abi.OUT_BF16_NHWC, out_ctot=0, out_coff=0, group_imgs=0, post_scale=1.0,
-            cout=None, in_gi=0, in_gstride=0, out_gi=0, out_gstride=0):
+            cout=None, in_gi=0, in_gstride=0, out_gi=0, out_gstride=0, bk=None):
     """Returns (op, bufs).  w_list: per-group [Cout,Cin,k,k] fp32 CPU tensors."""
     packed, metas = [], None
     for w in w_list:
-        p, metas = pack.pack_conv_weight(w)
+        p, metas = pack.pack_conv_weight(w, bk)
         packed.append(p)
     wg = torch.stack(packed).to(x.device)
     npad = metas["BN"] * metas["n_tiles"]
@@ -44,7 +44,8 @@ def conv_op(x, w_list, scale_list, bias_list, y, *, ksize, stride, act, cin, c_o
                     n_img=n, group_imgs=group_imgs, Hi=hi, Wi=wi, Cin=cin, Ho=ho, Wo=wo,
                     Cout=cout if cout is not None else metas["Cout"], ksize=ksize, stride=stride,
                     BN=metas["BN"], n_tiles=metas["n_tiles"], k_blocks=metas["k_blocks"], K_real=metas["K_real"],
-                    w_gstride=packed[0].numel(), sb_gstride=npad, f0=post_scale, out_ctot=out_ctot, out_coff=out_coff)
+                    w_gstride=packed[0].numel(), sb_gstride=npad, f0=post_scale, out_ctot=out_ctot, out_coff=out_coff,
+                    flags=metas["bk"])
     if out_mode == abi.OUT_BF16_NHWC:
         op.y = nhwc_view(y, 4, c_off_out, out_gi, out_gstride)
     else:

@@ -44,11 +44,16 @@ CONV_CASES = [
     (4, 12, 12, 64, 192, 3, 1, 2, 2),   # two weight groups (modalities), N=192
     (3, 40, 40, 128, 128, 3, 1, 2, 1),  # many tiles > pipeline depth, persistent loop
     (2, 9, 7, 48, 80, 3, 1, 1, 1),      # odd sizes, Cin not a multiple of 64
+    (2, 160, 160, 32, 64, 3, 2, 2, 1),  # backbone-like: 64-byte swizzle, stride 2, wide tiles
+    (1, 21, 37, 64, 64, 3, 2, 2, 1),    # odd input size with stride 2
+    (2, 20, 20, 512, 256, 1, 1, 2, 1),  # 20x20 maps: partial spatial tiles
 ]
 
 
+@pytest.mark.parametrize("path", ["tma", "gather"])
 @pytest.mark.parametrize("n,h,w,cin,cout,k,s,act,groups", CONV_CASES)
-def test_conv_bf16_nhwc(cuda, n, h, w, cin, cout, k, s, act, groups):
+def test_conv_bf16_nhwc(cuda, n, h, w, cin, cout, k, s, act, groups, path):
+    """both A-operand paths: TMA box loads (one k-block per tap x channel block) and the cp.async gather (flat K)."""
     from dcfa_b200 import abi
     g = torch.Generator().manual_seed(1234 + cin + cout + k + s)
     x = bf16_round(torch.randn(n, cin, h, w, generator=g))
@@ -60,7 +65,9 @@ def test_conv_bf16_nhwc(cuda, n, h, w, cin, cout, k, s, act, groups):
     ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
     y = torch.full((n, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=cuda)
     gi = n // groups
-    op, bufs = conv_op(x_nhwc, ws, scs, bis, y, ksize=k, stride=s, act=act, cin=cin, group_imgs=gi)
+    op, bufs = conv_op(x_nhwc, ws, scs, bis, y, ksize=k, stride=s, act=act, cin=cin, group_imgs=gi,
+                       bk=None if path == "tma" else 0)
+    assert (op.flags != 0) == (path == "tma")
     _run([op], bufs)
     refs = []
     for gg in range(groups):
