@@ -16,6 +16,7 @@
 //   warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer + TMEM alloc, warps 6-9 epilogue group 1.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -28,7 +29,7 @@ constexpr int BM = 128;
 constexpr int kTmaWarp = 4;
 constexpr int kMmaWarp = 5;
 constexpr int kThreads = 320;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;
 
 struct FastDiv {
   uint32_t d, mul, shr;
@@ -69,9 +70,20 @@ struct TmaConvArgs {
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   uint32_t layout_type;   // UMMA descriptor swizzle code (2 / 4 / 6)
   uint32_t sbo;           // 8 rows * row pitch
-  FastDiv div_tw, div_tiles_img, div_tiles_x, div_ntiles, div_cblocks;
+  FastDiv div_tw, div_tiles_img, div_tiles_x, div_ntiles;
+  int tma_store;          // bf16 NHWC output written with TMA stores from a swizzled smem staging tile
+  int cbox;               // channels per store slab (64 / 32 / 16)
+  uint32_t out_stage_bytes;  // 128 rows * cbox * 2
   uint32_t tmem_cols;
 };
+
+#ifdef DCFA_TIMELINE
+// debug build only (make EXTRA=-DDCFA_TIMELINE): clock64 timestamps of CTA 0, read back by tools/timeline.py
+__device__ long long g_tl[8][2048];
+#define TL(role, idx) do { if (blockIdx.x == 0 && (idx) < 2048) g_tl[role][idx] = clock64(); } while (0)
+#else
+#define TL(role, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout_type) {
   uint64_t d = 0;
@@ -91,7 +103,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                               const __grid_constant__ CUtensorMap tmap_y,
                                                                const TmaConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -104,6 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t bar_tfull = bars + 16u * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16u;
   const uint32_t tmem_slot = bar_tempty + 16u;
+  const uint32_t sb_base = (tmem_slot + 4u + 15u) & ~15u;  // 2 groups x (256 scale + 256 bias) floats
+  const uint32_t stage_out = (sb_base + 4096u + 1023u) & ~1023u;  // [group][2] output staging tiles (TMA store)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -134,9 +165,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == kTmaWarp) {
-    // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0) {
-      uint32_t it = 0;
+    // ------------------------------------------------------------------ TMA producer (one elected thread)
+    // Everything in the per-k-block path is incremental (no divisions): the single issuing thread runs a
+    // serial instruction stream, and in round 1 that stream -- not memory -- was the bottleneck.
+    if (ptx::elect_one()) {
+      uint32_t s = 0, ph = 0;
+      [[maybe_unused]] uint32_t tl_it = 0;
+      uint32_t a_dst = smem_a, b_dst = smem_b, full = bar_full, empty = bar_empty;
+      const uint32_t tx_bytes = p.a_tx_bytes + p.b_tx_bytes;
+      const int64_t wstep = (int64_t)p.BN * p.bk;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
         const int nt = tile - (int)rest * p.n_tiles;
@@ -147,46 +184,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         const int g = n / p.group_imgs;
         const int x0 = tx * p.tw * p.stride - p.pad;
         const int y0 = ty * p.th * p.stride - p.pad;
-        const __nv_bfloat16* wtile = p.w + (int64_t)g * p.w_gstride + (int64_t)nt * p.k_blocks * (p.BN * p.bk);
-        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
-          const int tap = (int)p.div_cblocks.div((uint32_t)kb);
-          const int cb = kb - tap * p.cblocks;
-          const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;  // tap / 3, tap % 3 (tap < 9)
-          ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(bar_full + 8u * s, p.a_tx_bytes + p.b_tx_bytes);
-          tma_load_4d(smem_a + s * p.a_stage_bytes, &tmap, cb * p.bk, x0 + dx, y0 + dy, n, bar_full + 8u * s);
-          ptx::bulk_g2s(smem_b + s * p.b_stage_bytes, wtile + (int64_t)kb * (p.BN * p.bk), p.b_tx_bytes,
-                        bar_full + 8u * s);
+        const __nv_bfloat16* wp = p.w + (int64_t)g * p.w_gstride + (int64_t)nt * p.k_blocks * wstep;
+        for (int dy = 0; dy < p.ksize; ++dy) {
+          for (int dx = 0; dx < p.ksize; ++dx) {
+            for (int c = 0; c < p.cblocks * p.bk; c += p.bk) {
+              ptx::mbar_wait(empty, ph ^ 1u);
+              ptx::mbar_arrive_expect_tx(full, tx_bytes);
+              tma_load_4d(a_dst, &tmap, c, x0 + dx, y0 + dy, n, full);
+              ptx::bulk_g2s(b_dst, wp, p.b_tx_bytes, full);
+              TL(0, tl_it); ++tl_it;
+              wp += wstep;
+              a_dst += p.a_stage_bytes; b_dst += p.b_stage_bytes; full += 8u; empty += 8u;
+              if (++s == (uint32_t)S) {
+                s = 0; ph ^= 1u;
+                a_dst = smem_a; b_dst = smem_b; full = bar_full; empty = bar_empty;
+              }
+            }
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN);
-    const int kk = p.bk >> 4;  // MMAs (K = 16) per k-block
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t as = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
-      ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * (uint32_t)p.BN;
-      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-        const uint32_t s = it % (uint32_t)S;
-        const uint32_t ph = (it / (uint32_t)S) & 1u;
-        ptx::mbar_wait(bar_full + 8u * s, ph);
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN);
+      const int kk = p.bk >> 4;  // MMAs (K = 16) per k-block
+      // descriptors: only the 14-bit start-address field changes per stage / per K step
+      const uint64_t desc_hi = make_kmajor_desc(0u, p.sbo, p.layout_type);
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const uint32_t a_lo0 = (smem_a & 0x3FFFFu) >> 4, b_lo0 = (smem_b & 0x3FFFFu) >> 4;
+      uint32_t s = 0, ph = 0, a_lo = a_lo0, b_lo = b_lo0, full = bar_full, empty = bar_empty;
+      uint32_t as = 0, aph = 0;
+      [[maybe_unused]] uint32_t tl_it = 0, tl_tile = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
+        TL(3, tl_tile); ++tl_tile;
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_kmajor_desc(smem_a + s * p.a_stage_bytes, p.sbo, p.layout_type);
-          const uint64_t bdesc = make_kmajor_desc(smem_b + s * p.b_stage_bytes, p.sbo, p.layout_type);
-          for (int k = 0; k < kk; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(bar_empty + 8u * s);
-          if (kb == p.k_blocks - 1) ptx::umma_commit(bar_tfull + 8u * as);
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          ptx::mbar_wait(full, ph);
+          ptx::tc_fence_after();
+          TL(1, tl_it);
+          const uint64_t adesc = desc_hi | (uint64_t)a_lo, bdesc = desc_hi | (uint64_t)b_lo;
+          ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+          for (int k = 1; k < kk; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          ptx::umma_commit(empty);
+          TL(2, tl_it); ++tl_it;
+          a_lo += a_step; b_lo += b_step; full += 8u; empty += 8u;
+          if (++s == (uint32_t)S) {
+            s = 0; ph ^= 1u;
+            a_lo = a_lo0; b_lo = b_lo0; full = bar_full; empty = bar_empty;
+          }
         }
-        __syncwarp();
+        ptx::umma_commit(bar_tfull + 8u * as);
+        as ^= 1u;
+        if (as == 0u) aph ^= 1u;
       }
     }
   } else {
@@ -194,16 +247,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     const int group = warp < 4 ? 0 : 1;
     const int q4 = warp & 3;           // TMEM lane quarter this warp may access
     const int r = q4 * 32 + lane;      // accumulator row
+    const int gtid = q4 * 32 + lane;   // thread index inside the group
     const int iy = (int)p.div_tw.div((uint32_t)r);
     const int ix = r - iy * p.tw;
     const int HoWo = p.Ho * p.Wo;
-    uint32_t lc = 0;                   // tiles handled by this group so far
+    // per-group shared copy of the current (group, n-tile) scale/bias: with the whole 227 KB carved out as
+    // shared memory there is no L1 left, so __ldg would pay an L2 round trip per 16-channel chunk
+    float* sb = reinterpret_cast<float*>(smem_raw + (sb_base - ptx::smem_u32(smem_raw))) + group * 512;
+    int sb_key = -1;
+    uint32_t aph = 0;
+    uint32_t slab = 0;   // store slabs issued by this group (selects the staging buffer)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       if ((int)(tcount & 1u) != group) continue;
       const uint32_t as = (uint32_t)group;
-      const uint32_t aph = lc & 1u;
-      ++lc;
       const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
       const int nt = tile - (int)rest * p.n_tiles;
       const int n = (int)p.div_tiles_img.div(rest);
@@ -214,44 +271,96 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       const int oy = ty * p.th + iy, ox = tx * p.tw + ix;
       const bool rvalid = iy < p.th && oy < p.Ho && ox < p.Wo;
       const int pix = oy * p.Wo + ox;
-      const float* sc = p.scale + (int64_t)g * p.sb_gstride + nt * p.BN;
-      const float* bi = p.bias + (int64_t)g * p.sb_gstride + nt * p.BN;
+      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1));
+      if (g * p.n_tiles + nt != sb_key) {   // uniform across the group's 128 threads
+        sb_key = g * p.n_tiles + nt;
+        ptx::named_bar_sync(1 + group, 128);  // previous tile's readers are done
+        const float* sc = p.scale + (int64_t)g * p.sb_gstride + nt * p.BN;
+        const float* bi = p.bias + (int64_t)g * p.sb_gstride + nt * p.BN;
+        for (int c = gtid; c < p.BN; c += 128) { sb[c] = __ldg(sc + c); sb[256 + c] = __ldg(bi + c); }
+        ptx::named_bar_sync(1 + group, 128);
+      }
       __nv_bfloat16* yb = nullptr;
       float* yf = nullptr;
       const __nv_bfloat16* rb = nullptr;
       if (rvalid) {
         if (p.out_mode == DCFA_OUT_BF16_NHWC) {
-          yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld;
-          if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld;
+          yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld + nt * p.BN;
+          if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld + nt * p.BN;
         } else {
-          yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)p.out_coff * HoWo + pix;
+          yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)(p.out_coff + nt * p.BN) * HoWo + pix;
         }
       }
+      const int cvalid = min(p.BN, p.Cout - nt * p.BN);  // valid channels of this n-tile
       ptx::mbar_wait(bar_tfull + 8u * as, aph);
+      aph ^= 1u;
       ptx::tc_fence_after();
+      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 1);
       const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
-      for (int j = 0; j < p.BN / 16; ++j) {
-        uint32_t acc[16];
-        ptx::tmem_ld_x16(taddr0 + (uint32_t)(j * 16), acc);
+      const int nchunks = p.BN >> 4;
+      uint32_t acc[2][16];
+      ptx::tmem_ld_x16(taddr0, acc[0]);
+      for (int j = 0; j < nchunks; ++j) {
         ptx::tmem_ld_wait();
-        const int c0 = nt * p.BN + j * 16;
-        if (rvalid && c0 < p.Cout) {
-          float v[16];
+        if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), acc[(j + 1) & 1]);  // prefetch next chunk
+        const uint32_t* a = acc[j & 1];
+        const int c0 = j * 16;
+        float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j * 16) + q);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j * 16) + q);
-            v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
-            v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
-            v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
-            v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+        for (int q = 0; q < 4; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + 256 + c0 + 4 * q);
+          v[4 * q + 0] = fmaf(__uint_as_float(a[4 * q + 0]), s4.x, b4.x);
+          v[4 * q + 1] = fmaf(__uint_as_float(a[4 * q + 1]), s4.y, b4.y);
+          v[4 * q + 2] = fmaf(__uint_as_float(a[4 * q + 2]), s4.z, b4.z);
+          v[4 * q + 3] = fmaf(__uint_as_float(a[4 * q + 3]), s4.w, b4.w);
+        }
+        if (p.act == DCFA_ACT_SILU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = v[e] * sigmoid_fast(v[e]);
+        } else if (p.act == DCFA_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+        }
+        if (p.post_scale != 1.0f) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] *= p.post_scale;
+        }
+        if (p.tma_store) {
+          // ---- stage 16 channels of this row into the swizzled slab; a full slab leaves with one TMA store
+          const int cs = c0 % p.cbox;            // channel offset inside the slab
+          if (cs == 0) {
+            // the slab buffer about to be overwritten was read by the TMA store issued two slabs ago
+            if (gtid == 0) bulk_wait_read<1>();
+            ptx::named_bar_sync(1 + group, 128);
           }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], p.act) * p.post_scale;
+          const uint32_t pitch = (uint32_t)p.cbox * 2u;
+          const uint32_t rowb = stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes + (uint32_t)r * pitch;
+          // Swizzle<B,4,3>: 16-byte chunk index XOR (row bits above the 128-byte line)
+          const uint32_t xr = p.cbox == 64 ? (uint32_t)(r & 7) : (p.cbox == 32 ? (uint32_t)((r >> 1) & 3) : (uint32_t)((r >> 2) & 1));
+          const uint32_t ch = (uint32_t)(cs >> 3);
+          const uint4 lo = pack8(v), hi = pack8(v + 8);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (((ch) ^ xr) << 4)), "r"(lo.x), "r"(lo.y),
+                       "r"(lo.z), "r"(lo.w)
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (((ch + 1u) ^ xr) << 4)), "r"(hi.x),
+                       "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                       : "memory");
+          if (cs + 16 == p.cbox) {   // slab complete
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(1 + group, 128);
+            if (gtid == 0 && nt * p.BN + c0 + 16 - p.cbox < p.Cout) {
+              tma_store_4d(&tmap_y, stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes,
+                           nt * p.BN + c0 + 16 - p.cbox, tx * p.tw, ty * p.th, n);
+            }
+            if (gtid == 0) bulk_commit();
+            ++slab;
+          }
+        } else if (rvalid && c0 < cvalid) {
           if (p.out_mode == DCFA_OUT_BF16_NHWC) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (c0 + 8 * h + 8 <= p.Cout) {
+              if (c0 + 8 * h + 8 <= cvalid) {
                 if (rb) {
                   float rr[8];
                   unpack8(ldg128(rb + c0 + 8 * h), rr);
@@ -264,15 +373,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
-              if (c0 + e < p.Cout) yf[(int64_t)(c0 + e) * HoWo] = v[e];
+              if (c0 + e < cvalid) yf[(int64_t)(c0 + e) * HoWo] = v[e];
           }
         }
         __syncwarp();
       }
+      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8u * as);
+      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 3);
     }
+    if (p.tma_store && gtid == 0) bulk_wait<0>();   // staging smem must outlive the last TMA store
   }
 
   ptx::tc_fence_before();
@@ -388,7 +500,6 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.div_tiles_img = make_fastdiv((uint32_t)a.tiles_img);
   a.div_tiles_x = make_fastdiv((uint32_t)a.tiles_x);
   a.div_ntiles = make_fastdiv((uint32_t)a.n_tiles);
-  a.div_cblocks = make_fastdiv((uint32_t)a.cblocks);
 
   const uint32_t pitch = (uint32_t)a.bk * 2u;  // bytes per K row of a stage
   a.layout_type = a.bk == 64 ? 2u : (a.bk == 32 ? 4u : 6u);
@@ -399,9 +510,14 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.a_tx_bytes = (uint32_t)(a.tw * a.th) * pitch;
   const int stage_bytes = (int)(a.a_stage_bytes + a.b_stage_bytes);
   const int max_smem = 227 * 1024;
-  const int fixed = 1024 + 256;
+  a.tma_store = (a.out_mode == DCFA_OUT_BF16_NHWC && !a.res.p && a.y.gi <= 0) ? 1 : 0;
+  a.cbox = a.BN >= 64 ? 64 : a.BN;   // BN is 16, 32, 48 or a multiple of 64 below
+  if (a.tma_store && (a.BN % a.cbox != 0 || (a.cbox != 64 && a.cbox != 32 && a.cbox != 16))) a.tma_store = 0;
+  a.out_stage_bytes = 128u * (uint32_t)a.cbox * 2u;
+  const int fixed = 1024 + 512 + 4096 + 1024 + (a.tma_store ? 4 * (int)a.out_stage_bytes : 0);
   int stages = (max_smem - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  { const char* e = getenv("DCFA_STAGES"); if (e && atoi(e) > 1 && atoi(e) < stages) stages = atoi(e); }
   DCFA_REQUIRE(stages >= 2, "conv(tma): not enough shared memory");
   a.stages = stages;
   const int smem = fixed + stages * stage_bytes;
@@ -431,9 +547,28 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     attr_set = true;
   }
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
-  conv_tma_kernel<<<grid, kThreads, smem, st>>>(tmap, a);
+  alignas(64) CUtensorMap tmap_y;
+  memset(&tmap_y, 0, sizeof(tmap_y));
+  if (a.tma_store) {
+    const cuuint64_t ydim[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.n_img};
+    const cuuint64_t ystr[3] = {(cuuint64_t)a.y.ld * 2, (cuuint64_t)a.Wo * a.y.ld * 2, (cuuint64_t)a.y.img_stride * 2};
+    const cuuint32_t ybox[4] = {(cuuint32_t)a.cbox, (cuuint32_t)a.tw, (cuuint32_t)a.th, 1u};
+    const cuuint32_t yes[4] = {1u, 1u, 1u, 1u};
+    const CUtensorMapSwizzle yswz = a.cbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (a.cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cr = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.y.p, ydim, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE, yswz,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
+  }
+  conv_tma_kernel<<<grid, kThreads, smem, st>>>(tmap, tmap_y, a);
   DCFA_CHECK_LAUNCH("conv_tma_kernel");
   return DCFA_OK;
 }
 
 }  // namespace dcfa
+
+#ifdef DCFA_TIMELINE
+extern "C" int dcfa_debug_read_timeline(void* dst, int bytes) {
+  return cudaMemcpyFromSymbol(dst, dcfa::g_tl, bytes) == cudaSuccess ? 0 : -2;
+}
+#endif
