@@ -298,12 +298,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 1);
       const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
       const int nchunks = p.BN >> 4;
-      uint32_t acc[2][16];
-      ptx::tmem_ld_x16(taddr0, acc[0]);
-      for (int j = 0; j < nchunks; ++j) {
-        ptx::tmem_ld_wait();
-        if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), acc[(j + 1) & 1]);  // prefetch next chunk
-        const uint32_t* a = acc[j & 1];
+      // two register buffers with STATIC indexing (a dynamically indexed array would live in local memory,
+      // and with the whole L1 carved out as shared memory every local access is an L2 round trip)
+      uint32_t accA[16], accB[16];
+      auto process = [&](const uint32_t (&a)[16], const int j) {
         const int c0 = j * 16;
         float v[16];
 #pragma unroll
@@ -376,7 +374,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
               if (c0 + e < cvalid) yf[(int64_t)(c0 + e) * HoWo] = v[e];
           }
         }
+      };
+      ptx::tmem_ld_x16(taddr0, accA);
+      for (int j = 0; j < nchunks; j += 2) {
+        ptx::tmem_ld_wait();
+        if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), accB);  // prefetch the next chunk
+        process(accA, j);
         __syncwarp();
+        if (j + 1 < nchunks) {
+          ptx::tmem_ld_wait();
+          if (j + 2 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2) * 16), accA);
+          process(accB, j + 1);
+          __syncwarp();
+        }
       }
       if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 2);
       ptx::tc_fence_before();
