@@ -546,8 +546,13 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv(tma): box too large");
   const CUtensorMapSwizzle swz = a.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                             : (a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  // L2 fill granularity: a channel sub-view (Cin < ld) only touches Cin*2 contiguous bytes per pixel; promoting
+  // beyond that run would fetch the neighbouring channels from DRAM for nothing
+  const int64_t run = (Cin == x.ld) ? (int64_t)Cin * 2 * Wi : (int64_t)Cin * 2;
+  const CUtensorMapL2promotion promo = run >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : (run >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x.p), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled failed with %d", (int)cr);
 
   static bool attr_set = false;

@@ -82,9 +82,9 @@ class DecodeBox():
             prediction[:, :, :4] = pred[:, :, :4].to(prediction.dtype)
         return ws
 
-    def non_max_suppression(self, prediction, num_classes, input_shape, image_shape, letterbox_image, conf_thres=0.5,
-                            nms_thres=0.4):
-        ws = self.nms_device(prediction, conf_thres, nms_thres)
+    def fetch_detections(self, ws, input_shape, image_shape, letterbox_image):
+        """Host half of non_max_suppression: one device->host copy of (count, first rows) per image, then the
+        reference's numpy un-letterbox (:170-173).  Returns list of None | float32 (n_i, 6) rows (y1,x1,y2,x2,conf,cls)."""
         b, a = ws.b, ws.a
         k = min(a, self.first_fetch)
         head = torch.cat((ws.cnt.view(b, 1).float(), ws.det[:, :k].reshape(b, k * 6)), 1).cpu().numpy()  # one D2H
@@ -99,3 +99,8 @@ class DecodeBox():
             det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
             output[i] = det
         return output
+
+    def non_max_suppression(self, prediction, num_classes, input_shape, image_shape, letterbox_image, conf_thres=0.5,
+                            nms_thres=0.4):
+        ws = self.nms_device(prediction, conf_thres, nms_thres)
+        return self.fetch_detections(ws, input_shape, image_shape, letterbox_image)
