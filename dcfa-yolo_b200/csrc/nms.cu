@@ -34,18 +34,19 @@ __device__ __forceinline__ uint32_t orderable(float f) {
 
 struct PrepArgs {
   float* pred;
-  uint64_t* keys;
+  uint64_t* keys;   // [B][Apad], candidates compacted to the front (any order: the key is a total order)
+  int32_t* cand;    // [B] candidate counters, zeroed before the launch
   int B, A, Apad, nc;
   float conf_thres;
 };
 
 __global__ void __launch_bounds__(256) nms_prepare_kernel(const PrepArgs p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)p.B * p.Apad) return;
+  // Apad is a multiple of 32 (or the whole image fits one warp), so a warp never straddles two images
   const int b = (int)(i / p.Apad);
   const int a = (int)(i - (int64_t)b * p.Apad);
   uint64_t key = kSentinel;
-  if (a < p.A) {
+  if (b < p.B && a < p.A) {
     float* row = p.pred + ((int64_t)b * p.A + a) * (4 + p.nc);
     const float cx = row[0], cy = row[1], w = row[2], h = row[3];
     const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
@@ -65,39 +66,55 @@ __global__ void __launch_bounds__(256) nms_prepare_kernel(const PrepArgs p) {
       key = ((uint64_t)bi << 56) | ((uint64_t)(~orderable(conf)) << 24) | (uint64_t)a;
     }
   }
-  p.keys[i] = key;
+  // warp-aggregated append
+  const unsigned mask = __ballot_sync(0xffffffffu, key != kSentinel);
+  if (mask) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(p.cand + b, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key != kSentinel) p.keys[(int64_t)b * p.Apad + base + __popc(mask & ((1u << lane) - 1u))] = key;
+  }
 }
 
 struct SortArgs {
-  uint64_t* keys;  // [B][Apad]
+  uint64_t* keys;        // [B][Apad]
+  const int32_t* cand;   // [B]
   int Apad;
-  int use_smem;
 };
 
+// one CTA per image: bitonic sort of the n candidate keys, padded with sentinels to the next power of two
 __global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p) {
   extern __shared__ uint64_t s_keys[];
   uint64_t* g = p.keys + (int64_t)blockIdx.x * p.Apad;
-  uint64_t* k = p.use_smem ? s_keys : g;
-  const int N = p.Apad;
-  if (p.use_smem) {
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) s_keys[i] = g[i];
+  const int n = p.cand[blockIdx.x];
+  if (n <= 1) return;
+  int N = 2;
+  while (N < n) N <<= 1;
+  const bool use_smem = N <= kSmemSortMax;
+  uint64_t* k = use_smem ? s_keys : g;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) s_keys[i] = i < n ? g[i] : kSentinel;
+  } else {
+    for (int i = n + threadIdx.x; i < N; i += kNmsThreads) g[i] = kSentinel;  // N <= Apad
   }
   __syncthreads();
+  const int half = N >> 1;
   for (int kk = 2; kk <= N; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < N; i += kNmsThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t a = k[i], b = k[ixj];
-          const bool asc = (i & kk) == 0;
-          if ((a > b) == asc) { k[i] = b; k[ixj] = a; }
-        }
+      for (int t = threadIdx.x; t < half; t += kNmsThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // t-th index with bit j clear
+        const int ixj = i | j;
+        const uint64_t a = k[i], b = k[ixj];
+        const bool asc = (i & kk) == 0;
+        if ((a > b) == asc) { k[i] = b; k[ixj] = a; }
       }
       __syncthreads();
     }
   }
-  if (p.use_smem) {
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) g[i] = s_keys[i];
+  if (use_smem) {
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) g[i] = s_keys[i];
   }
 }
 
@@ -127,6 +144,7 @@ struct GreedyArgs {
   int32_t* out_idx;
   int32_t* out_cnt;
   int32_t* out_cand;
+  const int32_t* cand;
   int B, A, Apad, nc;
   float thr_f;
   double thr_d;
@@ -140,7 +158,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   __shared__ unsigned long long c_mask[kChunk];
   __shared__ float4 k_box[kChunk];
   __shared__ int k_cls[kChunk];
-  __shared__ int s_kc, s_total, s_n;
+  __shared__ int s_total;
+  __shared__ unsigned s_alive[2];
+  __shared__ unsigned long long s_keep;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -148,15 +168,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   const float* pred = p.pred + (int64_t)b * p.A * (4 + p.nc);
   float4* sbox = p.sbox + (int64_t)b * p.A;
 
-  // number of candidates = keys below the sentinel (they are sorted first)
-  int cnt = 0;
-  for (int i = tid; i < p.A; i += kNmsThreads) cnt += (keys[i] != kSentinel) ? 1 : 0;
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if (tid == 0) { s_n = 0; s_total = 0; }
+  const int n = p.cand[b];
+  if (tid == 0) s_total = 0;
   __syncthreads();
-  if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
-  __syncthreads();
-  const int n = s_n;
   for (int j = tid; j < n; j += kNmsThreads) {
     const int a = (int)(keys[j] & 0xFFFFFFull);
     const float* row = pred + (int64_t)a * (4 + p.nc);
@@ -167,63 +181,69 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
 
   for (int c0 = 0; c0 < n; c0 += kChunk) {
     const int cn = min(kChunk, n - c0);
-    // (1) stage the chunk
+    // (1) stage the chunk; the alive bits of its 64 entries become one 64-bit mask
     int alive = 0;
     if (tid < kChunk) {
       c_mask[tid] = 0ull;
-      if (tid < cn) {
+      if (tid < cn && !s_removed[c0 + tid]) {
+        alive = 1;
         c_box[tid] = sbox[c0 + tid];
         c_cls[tid] = (int)(keys[c0 + tid] >> 56);
-        alive = s_removed[c0 + tid] ? 0 : 1;
       }
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if ((tid & 31) == 0) s_alive[tid >> 5] = bal;
     }
     const int any_alive = __syncthreads_or(alive);
     if (!any_alive) continue;  // uniform: every box of the chunk is already suppressed
-    // (2) 64x64 suppression bits, 4 pairs per thread: bit i of c_mask[j] <=> box i (earlier) suppresses box j
+    const unsigned long long alive64 = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
+    // (2) suppression bits among ALIVE entries, 4 pairs per thread: bit i of c_mask[j] <=> box i suppresses box j
     {
       const int j = tid >> 4;           // 0..63
       const int i0 = (tid & 15) << 2;   // 0,4,..,60
-      if (j < cn) {
+      if ((alive64 >> j) & 1ull) {
         unsigned long long bits = 0ull;
         const float4 bj = c_box[j];
         const int cj = c_cls[j];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = i0 + q;
-          if (i < j && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d)) bits |= 1ull << i;
+          if (i < j && ((alive64 >> i) & 1ull) && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d))
+            bits |= 1ull << i;
         }
         if (bits) atomicOr(&c_mask[j], bits);
       }
     }
     __syncthreads();
-    // (3) serial resolution of the chunk by one thread
+    // (3) serial resolution over the alive entries only (one thread, bit tricks, no global traffic)
     if (tid == 0) {
-      unsigned long long keep = 0ull;
-      int kc = 0;
-      const int base = s_total;
-      for (int j = 0; j < cn; ++j) {
-        if (s_removed[c0 + j]) continue;
-        if (c_mask[j] & keep) { s_removed[c0 + j] = 1; continue; }
-        keep |= 1ull << j;
-        k_box[kc] = c_box[j];
-        k_cls[kc] = c_cls[j];
-        const uint64_t key = keys[c0 + j];
-        const int a = (int)(key & 0xFFFFFFull);
-        const int pos = base + kc;
-        float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
-        const float4 bx = c_box[j];
-        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-        o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[j]];
-        o[5] = (float)c_cls[j];
-        p.out_idx[(int64_t)b * p.A + pos] = a;
-        ++kc;
+      unsigned long long rem = alive64, keep = 0ull;
+      while (rem) {
+        const int j = __ffsll((long long)rem) - 1;
+        rem &= rem - 1ull;
+        if (!(c_mask[j] & keep)) keep |= 1ull << j;
       }
-      s_kc = kc;
-      s_total = base + kc;
+      s_keep = keep;
     }
     __syncthreads();
+    const unsigned long long keep64 = s_keep;
+    const int kc = __popcll(keep64);
+    const int base = s_total;           // read before thread 0 updates it below (separated by the next barrier)
+    if (tid < kChunk && ((keep64 >> tid) & 1ull)) {   // kept entries write themselves out in parallel, in order
+      const int rank = __popcll(keep64 & ((1ull << tid) - 1ull));
+      k_box[rank] = c_box[tid];
+      k_cls[rank] = c_cls[tid];
+      const int a = (int)(keys[c0 + tid] & 0xFFFFFFull);
+      const int pos = base + rank;
+      float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
+      const float4 bx = c_box[tid];
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+      o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[tid]];
+      o[5] = (float)c_cls[tid];
+      p.out_idx[(int64_t)b * p.A + pos] = a;
+    }
+    __syncthreads();
+    if (tid == 0) s_total = base + kc;
     // (4) kept boxes of this chunk suppress later candidates
-    const int kc = s_kc;
     if (kc > 0) {
       for (int j = c0 + kChunk + tid; j < n; j += kNmsThreads) {
         if (s_removed[j]) continue;
@@ -242,8 +262,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   }
 }
 
+// padded keys per image: a power of two >= 32 (so that a warp of the prepare kernel never straddles two images)
 int next_pow2(int v) {
-  int r = 1;
+  int r = 32;
   while (r < v) r <<= 1;
   return r;
 }
@@ -255,7 +276,7 @@ extern "C" int64_t dcfa_nms_workspace_bytes(int B, int A) {
   if (B <= 0 || A <= 0) return 0;
   const int64_t apad = dcfa::next_pow2(A);
   const int64_t key_bytes = ((int64_t)B * apad * 8 + 255) / 256 * 256;
-  return key_bytes + (int64_t)B * A * 16 + 256;
+  return key_bytes + (int64_t)B * A * 16 + 256 + (((int64_t)B * 4 + 255) / 256) * 256;
 }
 
 extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, double nms_thres, int iou_mode,
@@ -275,13 +296,16 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
   const int64_t key_bytes = ((int64_t)B * Apad * 8 + 255) / 256 * 256;
   float4* sbox = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + key_bytes);
 
-  PrepArgs pa{pred, keys, B, A, Apad, nc, conf_thres};
+  int32_t* cand = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(sbox) + (((int64_t)B * A * 16 + 255) / 256) * 256);
+  cudaError_t me = cudaMemsetAsync(cand, 0, (size_t)B * 4, st);
+  if (me != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaMemsetAsync: %s", cudaGetErrorString(me));
+  PrepArgs pa{pred, keys, cand, B, A, Apad, nc, conf_thres};
   const int64_t tot = (int64_t)B * Apad;
   nms_prepare_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pa);
   DCFA_CHECK_LAUNCH("nms_prepare_kernel");
 
-  SortArgs sa{keys, Apad, Apad <= kSmemSortMax ? 1 : 0};
-  const size_t sort_smem = sa.use_smem ? (size_t)Apad * 8 : 0;
+  SortArgs sa{keys, cand, Apad};
+  const size_t sort_smem = (size_t)(Apad < kSmemSortMax ? Apad : kSmemSortMax) * 8;
   static bool attr_sort = false, attr_g0 = false, attr_g1 = false;
   if (!attr_sort) {
     cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSortMax * 8);
@@ -291,7 +315,7 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
   nms_sort_kernel<<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa);
   DCFA_CHECK_LAUNCH("nms_sort_kernel");
 
-  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, B, A, Apad, nc, (float)nms_thres, nms_thres};
+  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, (float)nms_thres, nms_thres};
   const size_t g_smem = (size_t)((A + 15) / 16) * 16;
   if (iou_mode == DCFA_IOU_TV_CUDA) {
     if (!attr_g1) {
