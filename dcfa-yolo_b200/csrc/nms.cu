@@ -123,6 +123,10 @@ __device__ __forceinline__ bool suppresses(const float4& a, const float4& b, flo
   // a = earlier (higher score) box, b = later box; both (x1, y1, x2, y2)
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  // Disjoint boxes: inter == 0, so the IoU is +-0 or NaN and never exceeds a threshold >= 0 -- skip the
+  // divide (most pairs).  Negative thresholds take the full path.
+  const bool nonneg = (MODE == DCFA_IOU_TV_CUDA) ? (thr_f >= 0.0f) : (thr_d >= 0.0);
+  if (nonneg && !(right > left && bottom > top)) return false;
   const float w = fmaxf(__fsub_rn(right, left), 0.0f), h = fmaxf(__fsub_rn(bottom, top), 0.0f);
   const float inter = __fmul_rn(w, h);
   const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
@@ -159,7 +163,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   __shared__ float4 k_box[kChunk];
   __shared__ int k_cls[kChunk];
   __shared__ int s_total;
-  __shared__ unsigned s_alive[2];
+  __shared__ int c_pos[kChunk];
+  __shared__ int s_wcnt[32];
+  __shared__ int s_found, s_next;
   __shared__ unsigned long long s_keep;
 
   const int b = blockIdx.x;
@@ -179,82 +185,101 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   }
   __syncthreads();
 
-  for (int c0 = 0; c0 < n; c0 += kChunk) {
-    const int cn = min(kChunk, n - c0);
-    // (1) stage the chunk; the alive bits of its 64 entries become one 64-bit mask
-    int alive = 0;
-    if (tid < kChunk) {
-      c_mask[tid] = 0ull;
-      if (tid < cn && !s_removed[c0 + tid]) {
-        alive = 1;
-        c_box[tid] = sbox[c0 + tid];
-        c_cls[tid] = (int)(keys[c0 + tid] >> 56);
+  // Each round takes the next (up to) 64 ALIVE candidates in sorted order -- found by an ordered block-wide
+  // compaction over a window of 1024 positions -- so the number of rounds scales with the candidates that
+  // survive the boxes kept so far, not with the number of candidates.
+  const int warp = tid >> 5, lane = tid & 31;
+  int pos0 = 0;
+  while (pos0 < n) {
+    // (1) ordered compaction of the alive positions in [pos0, pos0 + 1024)
+    const int j0 = pos0 + tid;
+    const int alive = (j0 < n && !s_removed[j0]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {   // exclusive prefix over the 32 warp counts
+      const int c = s_wcnt[lane];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, alive);
-      if ((tid & 31) == 0) s_alive[tid >> 5] = bal;
+      s_wcnt[lane] = incl - c;
+      if (lane == 31) s_found = incl;
     }
-    const int any_alive = __syncthreads_or(alive);
-    if (!any_alive) continue;  // uniform: every box of the chunk is already suppressed
-    const unsigned long long alive64 = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
-    // (2) suppression bits among ALIVE entries, 4 pairs per thread: bit i of c_mask[j] <=> box i suppresses box j
+    __syncthreads();
+    const int found = s_found;
+    if (found == 0) { pos0 += kNmsThreads; continue; }   // uniform
+    const int rank = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
+    if (alive && rank < kChunk) {
+      c_pos[rank] = j0;
+      c_box[rank] = sbox[j0];
+      c_cls[rank] = (int)(keys[j0] >> 56);
+      c_mask[rank] = 0ull;
+      if (rank == kChunk - 1) s_next = j0 + 1;   // the next round resumes right after the 64th alive entry
+    }
+    if (tid == 0 && found < kChunk) s_next = pos0 + kNmsThreads;
+    __syncthreads();
+    const int cn = min(found, kChunk);
+    const int next = s_next;
+    // (2) suppression bits inside the chunk, 4 pairs per thread: bit i of c_mask[j] <=> box i suppresses box j
     {
       const int j = tid >> 4;           // 0..63
       const int i0 = (tid & 15) << 2;   // 0,4,..,60
-      if ((alive64 >> j) & 1ull) {
+      if (j < cn) {
         unsigned long long bits = 0ull;
         const float4 bj = c_box[j];
         const int cj = c_cls[j];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = i0 + q;
-          if (i < j && ((alive64 >> i) & 1ull) && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d))
-            bits |= 1ull << i;
+          if (i < j && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d)) bits |= 1ull << i;
         }
         if (bits) atomicOr(&c_mask[j], bits);
       }
     }
     __syncthreads();
-    // (3) serial resolution over the alive entries only (one thread, bit tricks, no global traffic)
+    // (3) serial resolution (one thread, bit tricks, shared memory only)
     if (tid == 0) {
-      unsigned long long rem = alive64, keep = 0ull;
-      while (rem) {
-        const int j = __ffsll((long long)rem) - 1;
-        rem &= rem - 1ull;
+      unsigned long long keep = 0ull;
+      for (int j = 0; j < cn; ++j)
         if (!(c_mask[j] & keep)) keep |= 1ull << j;
-      }
       s_keep = keep;
     }
     __syncthreads();
     const unsigned long long keep64 = s_keep;
     const int kc = __popcll(keep64);
     const int base = s_total;           // read before thread 0 updates it below (separated by the next barrier)
-    if (tid < kChunk && ((keep64 >> tid) & 1ull)) {   // kept entries write themselves out in parallel, in order
-      const int rank = __popcll(keep64 & ((1ull << tid) - 1ull));
-      k_box[rank] = c_box[tid];
-      k_cls[rank] = c_cls[tid];
-      const int a = (int)(keys[c0 + tid] & 0xFFFFFFull);
-      const int pos = base + rank;
-      float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
-      const float4 bx = c_box[tid];
-      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-      o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[tid]];
-      o[5] = (float)c_cls[tid];
-      p.out_idx[(int64_t)b * p.A + pos] = a;
+    if (tid < cn) {
+      if ((keep64 >> tid) & 1ull) {     // kept entries write themselves out in parallel, in order
+        const int r = __popcll(keep64 & ((1ull << tid) - 1ull));
+        k_box[r] = c_box[tid];
+        k_cls[r] = c_cls[tid];
+        const int a = (int)(keys[c_pos[tid]] & 0xFFFFFFull);
+        const int pos = base + r;
+        float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
+        const float4 bx = c_box[tid];
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[tid]];
+        o[5] = (float)c_cls[tid];
+        p.out_idx[(int64_t)b * p.A + pos] = a;
+      }
+      s_removed[c_pos[tid]] = 1;        // every entry of the chunk is now decided
     }
     __syncthreads();
     if (tid == 0) s_total = base + kc;
-    // (4) kept boxes of this chunk suppress later candidates
-    if (kc > 0) {
-      for (int j = c0 + kChunk + tid; j < n; j += kNmsThreads) {
-        if (s_removed[j]) continue;
-        const float4 bj = sbox[j];
-        const int cj = (int)(keys[j] >> 56);
-        for (int k = 0; k < kc; ++k) {
-          if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { s_removed[j] = 1; break; }
-        }
+    // (4) the boxes kept in this round suppress the later candidates
+    for (int j = next + tid; j < n; j += kNmsThreads) {
+      if (s_removed[j]) continue;
+      const float4 bj = sbox[j];
+      const int cj = (int)(keys[j] >> 56);
+      for (int k = 0; k < kc; ++k) {
+        if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { s_removed[j] = 1; break; }
       }
     }
     __syncthreads();
+    pos0 = next;
   }
   if (tid == 0) {
     p.out_cnt[b] = s_total;
