@@ -1,314 +1,379 @@
 // DCFA_OP_STEM: Conv_maxpool (nets/yolo_mul.py:104-115) fused into one pass on tcgen05 tensor cores:
 //   fp32 NCHW image -> conv3x3 s1 p1 (3 -> C0) -> BN scale/bias -> ReLU -> maxpool 3x3 s2 p1 -> bf16 NHWC.
-// The full-resolution conv map (the largest tensor of the network) only ever exists as a shared-memory tile.
+// The full-resolution conv map (the largest tensor of the network) never leaves the SM.
 // Both modalities run in one launch (weight group = image / group_imgs).
 //
-// Persistent CTAs; per tile of 4 x 32 pooled pixels (= 9 x 65 conv pixels = 11 x 67 x 3 input patch):
-//   1. the fp32 patch is staged in shared memory (zero outside the image = conv zero padding);
-//   2. im2col: for 5 M-tiles of 128 conv pixels, threads build the K-major, 128B-swizzled A tile
-//      (27 taps -> bf16, K padded to 32) in a double-buffered 16 KB buffer and one thread issues
-//      2 x tcgen05.mma (M=128, N=BN, K=16) per M-tile into TMEM columns [t*BN, (t+1)*BN);
-//   3. epilogue: tcgen05.ld, fp32 scale/bias, ReLU (0 outside the image), bf16 conv tile in shared memory;
-//   4. 3x3/2 max-pool from shared memory, 128-bit stores of the pooled NHWC tile.
-// Post-ReLU values are >= 0 and every pool window holds a valid pixel, so writing 0 for out-of-image conv
-// positions is equivalent to the reference's -inf pool padding.
+// Round-1 profile of the first tensor-core version: 1 740 instructions per thread per tile, IPC 1.6 -- bound
+// by the CUDA-core work around the MMA (im2col, per-conv-pixel epilogue, pooling through shared memory).
+// This version turns the GEMM around:
+//     D[channel, pixel] = W[channel, K=27] * im2col[pixel, K]^T        (M = 128 channel rows, N = 240 pixels)
+//   * the accumulator of one CHANNEL is one TMEM lane and the conv PIXELS are its columns, so after
+//     tcgen05.ld a thread holds a 7 x 5 window of one channel in registers and the 3x3/2 max-pool is pure
+//     register arithmetic (no shared-memory round trip for the conv map);
+//   * C0 < 128 channels are replicated over the 128 MMA rows, so every TMEM lane quarter (= every epilogue
+//     warp) works, each replica pooling a different strip of the tile;
+//   * BN + ReLU are applied AFTER pooling (4x fewer elements).  Exact: with scale >= 0, x -> fma(x, s, b) and ReLU
+//     are monotone, so they commute with max; channels with negative scale are packed with negated weights and
+//     |scale| (pack time), so the pooled quantity is always monotone-increasing in the accumulator;
+//   * the fp32 input patch arrives by TMA (cp.async.bulk.tensor over the NCHW image): out-of-image pixels are
+//     zero-filled by the hardware (= conv zero padding), the copy is asynchronous and double-buffered.
+// Tile: 3 x 16 pooled pixels = 7 x 33 conv pixels = 9 x 35 x 3 input patch; 256 threads, 256 TMEM columns
+// -> two CTAs per SM overlap each other's phases.  Out-of-image conv positions are excluded from the max
+// (reference: -inf pool padding).
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace dcfa {
 namespace {
 
-constexpr int TPH = 4, TPW = 32;              // pooled tile
-constexpr int CH = 2 * TPH + 1;               // 9 conv rows
-constexpr int CW = 2 * TPW + 1;               // 65 conv cols
-constexpr int NPIX = CH * CW;                 // 585 conv pixels
-constexpr int MT = (NPIX + 127) / 128;        // 5 M-tiles
-constexpr int PH = CH + 2, PW = CW + 2;       // 11 x 67 input patch
-constexpr int PWP = 68;                       // padded patch row
+constexpr int TPH = 3, TPW = 16;              // pooled tile
+constexpr int CH = 2 * TPH + 1;               // 7 conv rows
+constexpr int CW = 2 * TPW + 1;               // 33 conv cols
+constexpr int NPIX = CH * CW;                 // 231 conv pixels, GEMM column m = cx * CH + cy
+constexpr int UMMA_N = 240;                   // NPIX rounded up to a multiple of 16
+constexpr int PH = CH + 2;                    // 9 patch rows
+constexpr int PWB = 36;                       // patch row pitch in floats (35 needed; 16-byte multiple for the TMA box)
+constexpr int PATCH_FLOATS = 3 * PH * PWB;    // 972
+constexpr int PATCH_BYTES = PATCH_FLOATS * 4; // 3888
 constexpr int kStemThreads = 256;
-constexpr int A_BYTES = 128 * 128;            // one M-tile of A: 128 rows x 128 B (64 bf16, 32 used)
+constexpr int KROW = 64;                      // bytes per K row: 32 bf16 (27 used), SWIZZLE_64B
+constexpr int B_BYTES = 256 * KROW;           // im2col tile (240 rows used)
+constexpr int A_BYTES = 128 * KROW;           // replicated weight tile
+constexpr uint32_t kTmemCols = 256;
 
 struct StemArgs {
-  const float* x0;
-  const float* x1;
-  const __nv_bfloat16* w;  // [G][BN*64] swizzled tile image (pack_conv_weight of [C0,3,3,3])
-  const float* scale;      // [G][BN]
-  const float* bias;       // [G][BN]
+  const float* x[2];
+  const __nv_bfloat16* w;  // [G][128*32] swizzled (SWIZZLE_64B) replicated weight tile
+  const float* scale;      // [G][C0pad]  (>= 0, sign folded into the weights)
+  const float* bias;       // [G][C0pad]
   View<__nv_bfloat16> y;
-  int n_img, group_imgs, Hi, Wi, Ho, Wo, C0, BN;
+  int n_img, group_imgs, Hi, Wi, Ho, Wo, C0, C0pad;
   int tiles_x, tiles_y, tiles_per_group, total_tiles;
-  uint32_t tmem_cols;
+  int use_tma;
 };
 
-// 16 consecutive im2col entries k = HALF*16 .. HALF*16+15 of one conv pixel, k = (ky*3 + kx)*3 + ci (27..31 = 0)
-template <int HALF>
-__device__ __forceinline__ void gather16(const float* pin, float* v) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int k = HALF * 16 + j;
-    if (k < 27) {
-      const int ci = k % 3, kk = k / 3;
-      const int kx = kk % 3, ky = kk / 3;
-      v[j] = pin[(ci * PH + ky) * PWP + kx];
-    } else {
-      v[j] = 0.0f;
-    }
-  }
+__device__ __forceinline__ void tma_load_patch(uint32_t dst, const CUtensorMap* map, int x, int y, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(0), "r"(n), "r"(bar)
+      : "memory");
 }
 
-__global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs p) {
+struct TileCoord {
+  int g, nl, n, py0, px0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const StemArgs& p, int tile) {
+  TileCoord t;
+  t.g = tile / p.tiles_per_group;
+  int r = tile - t.g * p.tiles_per_group;
+  const int tx = r % p.tiles_x; r /= p.tiles_x;
+  const int ty = r % p.tiles_y;
+  t.nl = r / p.tiles_y;
+  t.n = t.g * p.group_imgs + t.nl;
+  t.py0 = ty * TPH;
+  t.px0 = tx * TPW;
+  return t;
+}
+
+__global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_constant__ CUtensorMap map0,
+                                                               const __grid_constant__ CUtensorMap map1,
+                                                               const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: A[2] (32 KB) | B (BN*128, <= 16 KB) | patch (3*11*68 fp32) | conv tile (NPIX*C0 bf16) | barriers
-  const uint32_t s_a = base;
-  const uint32_t s_b = s_a + 2 * A_BYTES;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-  float* s_in = reinterpret_cast<float*>(gbase + 2 * A_BYTES + 16384);
-  __nv_bfloat16* s_conv = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(s_in) + 3 * PH * PWP * 4);
-  const uint32_t bars = s_b + 16384u + 3u * PH * PWP * 4u + (uint32_t)NPIX * p.C0 * 2u;
-  const uint32_t bar_buf = (bars + 7u) & ~7u;          // 2 barriers: A buffer free
-  const uint32_t bar_done = bar_buf + 16u;             // all MMAs of the tile complete
-  const uint32_t tmem_slot = bar_done + 8u;
+  // layout: B im2col (16 KB) | A weights (8 KB) | patch[2] (2 x 3888, padded to 4096) | staging (48 px * C0pad bf16) | barriers
+  const uint32_t s_b = base;
+  const uint32_t s_a = s_b + B_BYTES;
+  const uint32_t s_patch = s_a + A_BYTES;
+  float* patch_ptr = reinterpret_cast<float*>(gbase + B_BYTES + A_BYTES);
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(gbase + B_BYTES + A_BYTES + 2 * 4096);
+  const uint32_t bars = s_patch + 2u * 4096u + (uint32_t)(TPH * TPW) * 128u * 2u;
+  const uint32_t bar_patch = bars;            // 2 barriers
+  const uint32_t bar_mma = bars + 16u;
+  const uint32_t tmem_slot = bars + 24u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_init(bar_buf, 1);
-      ptx::mbar_init(bar_buf + 8u, 1);
-      ptx::mbar_init(bar_done, 1);
+      ptx::mbar_init(bar_patch, 1);
+      ptx::mbar_init(bar_patch + 8u, 1);
+      ptx::mbar_init(bar_mma, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t idesc = ptx::make_idesc_bf16_f32(128, p.BN);
+  const uint32_t idesc = ptx::make_idesc_bf16_f32(128, UMMA_N);
+
+  // ---- static per-thread roles
+  // im2col: thread m < NPIX builds GEMM column (row of the K-major B tile) m = cx*CH + cy
+  const int icx = tid / CH, icy = tid - icx * CH;
+  // epilogue: TMEM lane = 32*(warp%4) + lane -> MMA row; channel = row % C0pad; replica = row / C0pad
+  const int q4 = warp & 3, half = warp >> 2;
+  const int mrow = q4 * 32 + lane;
+  const int ch = mrow % p.C0pad;
+  const int rep = mrow / p.C0pad;
+  const int nrep = 128 / p.C0pad;             // 4, 2 or 1 replicas
+  const int nsub = nrep * 2;                  // strips: (replica, warp half)
+  const int units_per_sub = (TPW / 2) / nsub; // units of 2 pooled columns per strip: 1, 2 or 4
+  const int sub = rep * 2 + half;
+  const bool ch_valid = ch < p.C0;
 
   int cur_group = -1;
-  uint32_t buf_phase[2] = {0u, 0u};   // parity of the next completion to wait for, per A buffer
-  uint32_t done_phase = 0u;
-  uint32_t buf_uses[2] = {0u, 0u};
+  float sc = 0.0f, bi = 0.0f;
+  uint32_t it = 0;            // tiles processed by this CTA: buffer = it & 1, its mbarrier parity = (it >> 1) & 1
+  uint32_t mma_phase = 0u;
 
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    // tiles are ordered group-major so that a CTA reloads its weights at most once
-    const int g = tile / p.tiles_per_group;
-    int t = tile - g * p.tiles_per_group;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    const int nl = t / p.tiles_y;
-    const int n = g * p.group_imgs + nl;
-    const float* img = (g == 0 ? p.x0 : p.x1) + (int64_t)nl * 3 * p.Hi * p.Wi;
-    const int py0 = ty * TPH, px0 = tx * TPW;
-    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // conv-map origin of the tile
-    const int iy0 = cy0 - 1, ix0 = cx0 - 1;          // input origin of the patch
+  // prologue: request the first tile's patch
+  int tile = blockIdx.x;
+  if (tile < p.total_tiles && p.use_tma && tid == 0) {
+    const TileCoord t = decode_tile(p, tile);
+    ptx::mbar_arrive_expect_tx(bar_patch, PATCH_BYTES);
+    // (no pointer select between the two maps: that would copy a __grid_constant__ parameter to local memory)
+    if (t.g == 0) tma_load_patch(s_patch, &map0, 2 * t.px0 - 2, 2 * t.py0 - 2, t.nl, bar_patch);
+    else tma_load_patch(s_patch, &map1, 2 * t.px0 - 2, 2 * t.py0 - 2, t.nl, bar_patch);
+  }
 
-    if (g != cur_group) {  // (re)load the pre-swizzled weight tile of this modality
-      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)g * p.BN * 64);
-      uint4* dst = reinterpret_cast<uint4*>(gbase + 2 * A_BYTES);
-      for (int i = tid; i < (int)(b_bytes / 16); i += kStemThreads) dst[i] = __ldg(src + i);
-      cur_group = g;
+  int buf = 0;
+  for (; tile < p.total_tiles; tile += gridDim.x, buf ^= 1, ++it) {
+    const TileCoord t = decode_tile(p, tile);
+    const int cy0 = 2 * t.py0 - 1, cx0 = 2 * t.px0 - 1;  // conv-map origin of the tile (patch origin is one less)
+    float* s_in = patch_ptr + buf * 1024;                 // [3][PH][PWB]
+
+    if (t.g != cur_group) {  // (re)load this modality's weight tile and this thread's scale/bias
+      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)t.g * 128 * 32);
+      uint4* dst = reinterpret_cast<uint4*>(gbase + B_BYTES);
+      for (int i = tid; i < A_BYTES / 16; i += kStemThreads) dst[i] = __ldg(src + i);
+      sc = __ldg(p.scale + (int64_t)t.g * p.C0pad + ch);
+      bi = __ldg(p.bias + (int64_t)t.g * p.C0pad + ch);
+      cur_group = t.g;
     }
-    for (int i = tid; i < 3 * PH * PW; i += kStemThreads) {
-      const int c = i / (PH * PW);
-      const int r = (i - c * PH * PW) / PW;
-      const int q = i - c * PH * PW - r * PW;
-      const int iy = iy0 + r, ix = ix0 + q;
-      float v = 0.0f;
-      if (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) v = __ldg(img + ((int64_t)c * p.Hi + iy) * p.Wi + ix);
-      s_in[(c * PH + r) * PWP + q] = v;
-    }
-    __syncthreads();
-
-    // ---- im2col + MMA over the 5 M-tiles
-    for (int mt = 0; mt < MT; ++mt) {
-      const int b = mt & 1;
-      if (buf_uses[b] > 0) {  // wait until the MMAs that read this buffer have completed
-        ptx::mbar_wait(bar_buf + 8u * b, buf_phase[b]);
-        buf_phase[b] ^= 1u;
+    if (p.use_tma) {
+      ptx::mbar_wait(bar_patch + 8u * buf, (it >> 1) & 1u);
+    } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
+      const float* img = p.x[t.g] + (int64_t)t.nl * 3 * p.Hi * p.Wi;
+      for (int i = tid; i < 3 * PH * 35; i += kStemThreads) {
+        const int c = i / (PH * 35);
+        const int r = (i - c * PH * 35) / 35;
+        const int q = i - c * PH * 35 - r * 35;
+        const int iy = cy0 - 1 + r, ix = cx0 - 1 + q;
+        float v = 0.0f;
+        if (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) v = __ldg(img + ((int64_t)c * p.Hi + iy) * p.Wi + ix);
+        s_in[(c * PH + r) * PWB + q] = v;
       }
-      buf_uses[b]++;
-      // two threads per row: half 0 builds k = 0..15, half 1 builds k = 16..31 (27..31 are zero)
-      const int r = tid >> 1, half = tid & 1;
-      const int m = mt * 128 + r;
-      uint32_t pk[8];
-      if (m < NPIX) {
-        const int cy = m / CW, cx = m - cy * CW;
-        float v[16];
-        const float* pin = s_in + cy * PWP + cx;
-        if (half == 0) gather16<0>(pin, v); else gather16<1>(pin, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = 0u;
-      }
-      uint8_t* arow = gbase + b * A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-      const int c0 = half * 2;  // 16-byte chunks c0, c0+1 of the 128-byte row, swizzled by (r & 7)
-      *reinterpret_cast<uint4*>(arow + (((c0) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(arow + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      ptx::fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0) {
-        ptx::tc_fence_after();
-        const uint64_t adesc = ptx::make_sw128_kmajor_desc(s_a + b * A_BYTES);
-        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(s_b);
-        const uint32_t d = tmem_base + (uint32_t)(mt * p.BN);
-        ptx::umma_bf16(d, adesc, bdesc, idesc, 0u);
-        ptx::umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
-        ptx::umma_commit(bar_buf + 8u * b);
-        if (mt == MT - 1) ptx::umma_commit(bar_done);
-      }
     }
 
-    // ---- epilogue: TMEM -> scale/bias/ReLU -> bf16 conv tile in shared memory
-    ptx::mbar_wait(bar_done, done_phase);
-    done_phase ^= 1u;
+    // ---- im2col: one conv pixel per thread, K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes
+    if (tid < NPIX) {
+      const float* pin = s_in + icy * PWB + icx;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v0 = 0.0f, v1 = 0.0f;
+        {
+          constexpr int dummy = 0; (void)dummy;
+          const int k0 = 2 * j, k1 = 2 * j + 1;
+          if (k0 < 27) v0 = pin[((k0 % 3) * PH + (k0 / 9)) * PWB + ((k0 / 3) % 3)];
+          if (k1 < 27) v1 = pin[((k1 % 3) * PH + (k1 / 9)) * PWB + ((k1 / 3) % 3)];
+        }
+        pk[j] = pack_bf16x2(v0, v1);
+      }
+      const uint32_t rowb = s_b + (uint32_t)tid * KROW;
+      const uint32_t xr = (uint32_t)((tid >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
+                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                     : "memory");
+    }
+    ptx::fence_proxy_async_smem();
+    __syncthreads();   // B tile (and A tile) visible; the patch buffer `buf` has been consumed
+
+    if (tid == 0) {
+      // prefetch the NEXT tile's patch into the other buffer (free since the previous tile's im2col)
+      const int nxt = tile + gridDim.x;
+      if (p.use_tma && nxt < p.total_tiles) {
+        const TileCoord tn = decode_tile(p, nxt);
+        ptx::mbar_arrive_expect_tx(bar_patch + 8u * (buf ^ 1), PATCH_BYTES);
+        if (tn.g == 0)
+          tma_load_patch(s_patch + (uint32_t)(buf ^ 1) * 4096u, &map0, 2 * tn.px0 - 2, 2 * tn.py0 - 2, tn.nl, bar_patch + 8u * (buf ^ 1));
+        else
+          tma_load_patch(s_patch + (uint32_t)(buf ^ 1) * 4096u, &map1, 2 * tn.px0 - 2, 2 * tn.py0 - 2, tn.nl, bar_patch + 8u * (buf ^ 1));
+      }
+      ptx::tc_fence_after();
+      // SWIZZLE_64B K-major descriptors: SBO = 8 rows * 64 B, layout code 4
+      uint64_t adesc = (uint64_t)((s_a & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+                       ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+      uint64_t bdesc = (uint64_t)((s_b & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+                       ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+      ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+      ptx::umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);   // K 16..31: +32 bytes
+      ptx::umma_commit(bar_mma);
+    }
+    ptx::mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1u;
     ptx::tc_fence_after();
-    {
-      const float* sc = p.scale + (int64_t)g * p.BN;
-      const float* bi = p.bias + (int64_t)g * p.BN;
-      const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
-      for (int mt = (warp >> 2); mt < MT; mt += 2) { // warps 0-3: tiles 0,2,4; warps 4-7: tiles 1,3
-        const int m = mt * 128 + q4 * 32 + lane;
-        bool inside = false;
-        if (m < NPIX) {
-          const int cy = m / CW, cx = m - cy * CW;
-          const int gy = cy0 + cy, gx = cx0 + cx;
-          inside = gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
-        }
-        for (int j = 0; j < p.BN / 16; ++j) {
-          uint32_t acc[16];
-          ptx::tmem_ld_x16(tmem_base + (uint32_t)(mt * p.BN + j * 16) + ((uint32_t)(q4 * 32) << 16), acc);
-          ptx::tmem_ld_wait();
-          if (m < NPIX && j * 16 < p.C0) {
-            float v[16];
+
+    // ---- epilogue: per unit of 2 pooled columns, 5 conv columns x 7 conv rows = 35 consecutive TMEM columns
+    const bool border = cy0 < 0 || cx0 < 0 || cy0 + CH > p.Hi || cx0 + CW > p.Wi;
+    for (int u = 0; u < units_per_sub; ++u) {
+      const int pc0 = 2 * (sub * units_per_sub + u);    // first pooled column of the unit (tile-local)
+      const int j0 = 2 * pc0;                           // first conv column
+      uint32_t raw[48];
+      const uint32_t taddr = tmem_base + (uint32_t)(j0 * CH) + ((uint32_t)(q4 * 32) << 16);
+      ptx::tmem_ld_x16(taddr, raw);
+      ptx::tmem_ld_x16(taddr + 16u, raw + 16);
+      ptx::tmem_ld_x16(taddr + 32u, raw + 32);          // columns 32..34 needed (35..47 are the next unit's / spare)
+      ptx::tmem_ld_wait();
+      float v[5][CH];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j * 16) + q);
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j * 16) + q);
-              v[4 * q + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x), 0.0f);
-              v[4 * q + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y), 0.0f);
-              v[4 * q + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z), 0.0f);
-              v[4 * q + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w), 0.0f);
-            }
-            if (!inside) {
+      for (int jj = 0; jj < 5; ++jj)
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = 0.0f;
-            }
-            __nv_bfloat16* dst = s_conv + (int64_t)m * p.C0 + j * 16;
-            *reinterpret_cast<uint4*>(dst) = pack8(v);
-            if (j * 16 + 8 < p.C0) *reinterpret_cast<uint4*>(dst + 8) = pack8(v + 8);
+        for (int i = 0; i < CH; ++i) v[jj][i] = __uint_as_float(raw[jj * CH + i]);
+      if (border) {   // exclude out-of-image conv positions from the max (reference: -inf pool padding)
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+          const int gx = cx0 + j0 + jj;
+          const bool xok = gx >= 0 && gx < p.Wi;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int gy = cy0 + i;
+            if (!(xok && gy >= 0 && gy < p.Hi)) v[jj][i] = -INFINITY;
           }
-          __syncwarp();
         }
+      }
+      // vertical 3-max at stride 2 for each conv column, then horizontal 3-max at stride 2
+      float vm[5][TPH];
+#pragma unroll
+      for (int jj = 0; jj < 5; ++jj)
+#pragma unroll
+        for (int pr = 0; pr < TPH; ++pr) vm[jj][pr] = fmaxf(fmaxf(v[jj][2 * pr], v[jj][2 * pr + 1]), v[jj][2 * pr + 2]);
+      if (ch_valid) {
+#pragma unroll
+        for (int pr = 0; pr < TPH; ++pr)
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            const float m = fmaxf(fmaxf(vm[2 * pc][pr], vm[2 * pc + 1][pr]), vm[2 * pc + 2][pr]);
+            const float o = fmaxf(fmaf(m, sc, bi), 0.0f);
+            stage[(pr * TPW + pc0 + pc) * p.C0pad + ch] = __float2bfloat16_rn(o);
+          }
       }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    __syncthreads();   // staging complete; TMEM and the B tile may be overwritten by the next tile
 
-    // ---- 3x3 stride-2 max-pool of the conv tile, pooled NHWC store
+    // ---- pooled NHWC tile -> global, 16 bytes per thread, channel-contiguous
     const int c8n = p.C0 >> 3;
     for (int i = tid; i < TPH * TPW * c8n; i += kStemThreads) {
       const int c8 = i % c8n;
       const int pp = i / c8n;
       const int pxl = pp % TPW, pyl = pp / TPW;
-      const int py = py0 + pyl, px = px0 + pxl;
-      if (py >= p.Ho || px >= p.Wo) continue;
-      __nv_bfloat162 mx[4];
-      {
-        const uint4 v = *reinterpret_cast<const uint4*>(s_conv + (int64_t)((2 * pyl) * CW + 2 * pxl) * p.C0 + c8 * 8);
-        mx[0] = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-        mx[1] = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-        mx[2] = *reinterpret_cast<const __nv_bfloat162*>(&v.z);
-        mx[3] = *reinterpret_cast<const __nv_bfloat162*>(&v.w);
+      const int py = t.py0 + pyl, px = t.px0 + pxl;
+      if (py < p.Ho && px < p.Wo) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + pp * p.C0pad + c8 * 8);
+        stg128(p.y.p + p.y.img_off(t.n) + (int64_t)(py * p.Wo + px) * p.y.ld + c8 * 8, val);
       }
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (r == 0 && q == 0) continue;
-          const uint4 v =
-              *reinterpret_cast<const uint4*>(s_conv + (int64_t)((2 * pyl + r) * CW + 2 * pxl + q) * p.C0 + c8 * 8);
-          mx[0] = __hmax2(mx[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x));
-          mx[1] = __hmax2(mx[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y));
-          mx[2] = __hmax2(mx[2], *reinterpret_cast<const __nv_bfloat162*>(&v.z));
-          mx[3] = __hmax2(mx[3], *reinterpret_cast<const __nv_bfloat162*>(&v.w));
-        }
-      uint4 o;
-      o.x = *reinterpret_cast<uint32_t*>(&mx[0]);
-      o.y = *reinterpret_cast<uint32_t*>(&mx[1]);
-      o.z = *reinterpret_cast<uint32_t*>(&mx[2]);
-      o.w = *reinterpret_cast<uint32_t*>(&mx[3]);
-      stg128(p.y.p + p.y.img_off(n) + (int64_t)(py * p.Wo + px) * p.y.ld + c8 * 8, o);
     }
-    __syncthreads();  // conv tile and patch are reused by the next tile
+    __syncthreads();   // staging is rewritten by the next tile's epilogue
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn stem_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
 }
 
 }  // namespace
 
 int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   StemArgs a;
-  a.x0 = resolve_ptr<const float>(op.x, bufs);
-  a.x1 = resolve_ptr<const float>(op.x2, bufs);
+  a.x[0] = resolve_ptr<const float>(op.x, bufs);
+  a.x[1] = resolve_ptr<const float>(op.x2, bufs);
   a.w = resolve_ptr<const __nv_bfloat16>(op.w, bufs);
   a.scale = resolve_ptr<const float>(op.scale, bufs);
   a.bias = resolve_ptr<const float>(op.bias, bufs);
   a.y = resolve<__nv_bfloat16>(op.y, bufs);
   a.n_img = op.n_img;
   a.group_imgs = op.group_imgs > 0 ? op.group_imgs : op.n_img;
-  a.Hi = op.Hi; a.Wi = op.Wi; a.Ho = op.Ho; a.Wo = op.Wo; a.C0 = op.Cout; a.BN = op.BN;
-  DCFA_REQUIRE(a.x0 && a.w && a.scale && a.bias && a.y.p, "stem: missing tensor");
-  DCFA_REQUIRE(a.n_img == a.group_imgs || (a.n_img == 2 * a.group_imgs && a.x1), "stem: needs 1 or 2 groups");
+  a.Hi = op.Hi; a.Wi = op.Wi; a.Ho = op.Ho; a.Wo = op.Wo; a.C0 = op.Cout; a.C0pad = op.BN;
+  DCFA_REQUIRE(a.x[0] && a.w && a.scale && a.bias && a.y.p, "stem: missing tensor");
+  DCFA_REQUIRE(a.n_img == a.group_imgs || (a.n_img == 2 * a.group_imgs && a.x[1]), "stem: needs 1 or 2 groups");
   DCFA_REQUIRE(a.Hi > 0 && a.Wi > 0 && a.Ho == (a.Hi - 1) / 2 + 1 && a.Wo == (a.Wi - 1) / 2 + 1,
                "stem: pooled size %dx%d inconsistent with %dx%d", a.Ho, a.Wo, a.Hi, a.Wi);
-  DCFA_REQUIRE(a.C0 % 8 == 0 && a.C0 >= 8 && a.C0 <= 96, "stem: C0 %d unsupported", a.C0);
-  DCFA_REQUIRE(a.BN % 16 == 0 && a.BN >= a.C0 && a.BN <= 96 && op.k_blocks == 1 && op.n_tiles == 1 && op.K_real == 27,
-               "stem: weight packing mismatch (BN %d, C0 %d)", a.BN, a.C0);
+  DCFA_REQUIRE(a.C0 % 8 == 0 && a.C0 >= 8 && a.C0 <= 128, "stem: C0 %d unsupported", a.C0);
+  DCFA_REQUIRE((a.C0pad == 32 || a.C0pad == 64 || a.C0pad == 128) && a.C0pad >= a.C0 && op.K_real == 27,
+               "stem: weight packing mismatch (C0pad %d, C0 %d)", a.C0pad, a.C0);
   DCFA_REQUIRE(((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 && a.y.gstride % 8 == 0,
                "stem: output view must be 16-byte aligned");
-  DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0 && ((uintptr_t)a.scale % 16) == 0 && ((uintptr_t)a.bias % 16) == 0,
-               "stem: parameters must be 16-byte aligned");
+  DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0, "stem: weights must be 16-byte aligned");
   a.tiles_x = ceil_div(a.Wo, TPW);
   a.tiles_y = ceil_div(a.Ho, TPH);
   const int64_t per_group = (int64_t)a.group_imgs * a.tiles_x * a.tiles_y;
-  const int64_t total = per_group * (a.n_img / a.group_imgs);
+  const int groups = a.n_img / a.group_imgs;
+  const int64_t total = per_group * groups;
   DCFA_REQUIRE(total < (1ll << 31), "stem: too many tiles");
   a.tiles_per_group = (int)per_group;
   a.total_tiles = (int)total;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(MT * a.BN)) cols <<= 1;
-  a.tmem_cols = cols;
-  const size_t smem = 1024 + 2 * A_BYTES + 16384 + (size_t)3 * PH * PWP * 4 + (size_t)NPIX * a.C0 * 2 + 64;
-  static int max_set = 0;
-  if ((int)smem > max_set) {
+
+  // ---- tensor maps over the fp32 NCHW inputs: dims (W, H, C, N), box (36, 9, 3, 1), zero fill outside
+  alignas(64) CUtensorMap maps[2];
+  memset(maps, 0, sizeof(maps));
+  a.use_tma = (a.Wi % 4 == 0 && ((uintptr_t)a.x[0] % 16) == 0 && (groups == 1 || ((uintptr_t)a.x[1] % 16) == 0)) ? 1 : 0;
+  if (a.use_tma) {
+    EncodeTiledFn enc = stem_encode_fn();
+    DCFA_REQUIRE(enc != nullptr, "stem: cuTensorMapEncodeTiled entry point unavailable");
+    for (int g = 0; g < groups; ++g) {
+      const cuuint64_t gdim[4] = {(cuuint64_t)a.Wi, (cuuint64_t)a.Hi, 3, (cuuint64_t)a.group_imgs};
+      const cuuint64_t gstr[3] = {(cuuint64_t)a.Wi * 4, (cuuint64_t)a.Wi * a.Hi * 4, (cuuint64_t)a.Wi * a.Hi * 12};
+      const cuuint32_t box[4] = {(cuuint32_t)PWB, (cuuint32_t)PH, 3u, 1u};
+      const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+      CUresult cr = enc(&maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x[g]), gdim, gstr, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled failed with %d", (int)cr);
+    }
+  }
+  const size_t smem = 1024 + B_BYTES + A_BYTES + 2 * 4096 + (size_t)TPH * TPW * 128 * 2 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "stem: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    max_set = (int)smem;
+    attr_set = true;
   }
-  // CTAs per SM: limited by shared memory and by TMEM columns (512 per SM)
-  int per_sm = (int)((227 * 1024) / smem);
-  if (per_sm > (int)(512 / cols)) per_sm = (int)(512 / cols);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
-  int64_t grid = (int64_t)sm_count() * per_sm;
+  int64_t grid = (int64_t)sm_count() * 2;   // two CTAs per SM: 2 x 256 TMEM columns, 2 x ~46 KB shared memory
   if (grid > total) grid = total;
-  stem_kernel<<<(unsigned)grid, kStemThreads, smem, st>>>(a);
+  stem_kernel<<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
   DCFA_CHECK_LAUNCH("stem_kernel");
   return DCFA_OK;
 }

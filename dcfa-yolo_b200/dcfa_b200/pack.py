@@ -68,6 +68,25 @@ def pack_conv_weight(w, bk=None):
     return packed, meta
 
 
+def pack_stem(w, scale, bias):
+    """Stem conv [C0,3,3,3] + folded BN -> (weight tile bf16 [128*32], scale [C0pad], bias [C0pad], C0pad).
+
+    The stem GEMM puts CHANNELS on the 128 MMA rows (replicated C0pad-periodically so every TMEM lane quarter holds
+    a copy) and pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative
+    BN scale get negated weights and |scale| (scale * conv(w) == |scale| * conv(sign * w))."""
+    c0 = w.shape[0]
+    c0pad = 32 if c0 <= 32 else (64 if c0 <= 64 else 128)
+    sgn = torch.where(scale < 0, -torch.ones_like(scale), torch.ones_like(scale))
+    wk = (w * sgn.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(c0, 27)     # K = (ky*3 + kx)*3 + ci
+    tile = torch.zeros(128, 32, dtype=torch.float32)
+    for m in range(128):
+        c = m % c0pad
+        if c < c0:
+            tile[m, :27] = wk[c]
+    packed = swizzle_tile(tile.to(torch.bfloat16)).reshape(-1)
+    return packed, pad_channels(scale.abs(), c0pad), pad_channels(bias, c0pad), c0pad
+
+
 def pad_channels(v, n, fill=0.0):
     out = torch.full((n,), fill, dtype=torch.float32)
     out[:v.numel()] = v.float()

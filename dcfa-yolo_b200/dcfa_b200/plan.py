@@ -271,14 +271,14 @@ class Plan:
         N2 = 2 * B
         mods = ('backbone_rgb', 'backbone_nir')
 
-        # ---- stems (nets/yolo_mul.py:104-115): one swizzled bf16 weight tile per modality, fp32 scale/bias epilogue
-        packed, scs, bis, meta = [], [], [], None
+        # ---- stems (nets/yolo_mul.py:104-115): replicated, sign-folded bf16 weight tile per modality (pack.pack_stem)
+        packed, scs, bis, c0pad = [], [], [], 32
         for m in mods:
             sc, bi = self._bn(m + '.stem.conv.1', 1e-5)
-            pk, meta = pack.pack_conv_weight(s[m + '.stem.conv.0.weight'])
+            pk, sca, bia, c0pad = pack.pack_stem(s[m + '.stem.conv.0.weight'], sc, bi)
             packed.append(pk)
-            scs.append(pack.pad_channels(sc, meta['BN']))
-            bis.append(pack.pad_channels(bi, meta['BN']))
+            scs.append(sca)
+            bis.append(bia)
         w_off = self.blob.add(torch.cat(packed))
         sc_off = self.blob.add(torch.cat(scs))
         b_off = self.blob.add(torch.cat(bis))
@@ -287,8 +287,7 @@ class Plan:
         self._emit('stem', abi.new_op(abi.OP_STEM, x=_flat(BUF_RGB, 0), x2=_flat(BUF_NIR, 0), w=_flat(BUF_BLOB, w_off),
                                       scale=_flat(BUF_BLOB, sc_off), bias=_flat(BUF_BLOB, b_off), y=x.view(), n_img=N2,
                                       group_imgs=B, Hi=H, Wi=W, Ho=h1, Wo=w1, Cout=bc, Cin=3, ksize=3, stride=1,
-                                      BN=meta['BN'], n_tiles=1, k_blocks=1, K_real=27, w_gstride=meta['BN'] * 64,
-                                      sb_gstride=meta['BN']))
+                                      BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad))
         self.conv_flops += 2 * N2 * H * W * bc * 27
 
         # ---- dark2..dark5 (nets/yolo_mul.py:258-277)

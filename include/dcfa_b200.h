@@ -96,10 +96,10 @@ typedef struct dcfa_view {
 /*
  * One op of the flat execution plan.  Field use per kind:
  *
- * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 packed [G][BN*64] (one
- *        128B-swizzled K-major tile per group, K = (ky*3+kx)*3+ci padded to 64, rows = Cout padded to BN);
- *        scale,bias = fp32 [G][BN] (folded BN); y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
- *        BN, n_tiles = 1, k_blocks = 1, K_real = 27 describe the packing.
+ * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 [G][128*32]: one 64B-swizzled
+ *        K-major tile per group whose 128 rows are the Cout channels repeated with period BN (= Cout rounded up
+ *        to 32/64/128), K = (ky*3+kx)*3+ci padded to 32, rows of channels with a negative BN scale negated;
+ *        scale (>= 0), bias = fp32 [G][BN]; y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
  * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed
  *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
  *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added

@@ -80,7 +80,8 @@ def run_ops(ops, bufs):
         gi = n // G
         if k == 1:  # STEM: bf16 inputs and weights, fp32 accumulate, fp32 scale/bias, ReLU, pool, bf16 store
             c0 = op.Cout
-            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, op.BN, 1, 1)
+            # weight tile: 128 replicated rows x 32 K (SWIZZLE_64B); rows 0..C0-1 are one replica, sign-folded
+            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, 128, 1, 1, 32)
             sc = _f32(bufs[op.scale.buf], op.scale.off, G * op.sb_gstride).view(G, -1)
             bi = _f32(bufs[op.bias.buf], op.bias.off, G * op.sb_gstride).view(G, -1)
             outs = []

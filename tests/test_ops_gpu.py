@@ -118,7 +118,7 @@ def test_conv_f32_nchw_out(cuda):
 
 
 @pytest.mark.parametrize("b,h,w,c0,groups", [(1, 32, 64, 16, 1), (2, 40, 72, 32, 2), (1, 70, 130, 32, 1), (3, 33, 47, 48, 2),
-                                            (1, 64, 64, 80, 1)])
+                                            (1, 64, 64, 80, 1), (2, 96, 128, 64, 2), (1, 640, 640, 32, 1)])
 def test_stem(cuda, b, h, w, c0, groups):
     """fused conv3x3+BN+ReLU+maxpool3/2 vs F.conv2d + F.max_pool2d (nets/yolo_mul.py:104-115)."""
     from dcfa_b200 import abi
@@ -129,22 +129,21 @@ def test_stem(cuda, b, h, w, c0, groups):
     from dcfa_b200 import pack
     ws = [bf16_round(wt) for wt in ws]
     xs = [bf16_round(t) for t in xs]
-    scs = [torch.rand(c0, generator=g) + 0.5 for _ in range(groups)]
-    packed, meta = [], None
-    for wt in ws:
-        pk, meta = pack.pack_conv_weight(wt)
-        packed.append(pk)
-    bn = meta["BN"]
+    scs = [torch.rand(c0, generator=g) - 0.3 for _ in range(groups)]   # some negative BN scales (sign folding)
+    packed, sks, bks, c0pad = [], [], [], 32
+    for i in range(groups):
+        pk, sca, bia, c0pad = pack.pack_stem(ws[i], scs[i], bs[i])
+        packed.append(pk); sks.append(sca); bks.append(bia)
     wk = torch.stack(packed).to(cuda)
-    sk = torch.stack([pack.pad_channels(t, bn) for t in scs]).to(cuda)
-    bk = torch.stack([pack.pad_channels(t, bn) for t in bs]).to(cuda)
+    sk = torch.stack(sks).to(cuda)
+    bk = torch.stack(bks).to(cuda)
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     y = torch.zeros(groups * b, ho, wo, c0, dtype=torch.bfloat16, device=cuda)
     xg = [t.to(cuda) for t in xs]
     bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
     op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
                     bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
-                    Ho=ho, Wo=wo, Cout=c0, BN=bn, n_tiles=1, k_blocks=1, K_real=27, w_gstride=bn * 64, sb_gstride=bn)
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad)
     _run([op], bufs)
     bs = [bs[i] for i in range(groups)]
     ws = [ws[i] * 1.0 for i in range(groups)]
