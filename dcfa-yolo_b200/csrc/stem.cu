@@ -21,6 +21,7 @@
 // -> two CTAs per SM overlap each other's phases.  Out-of-image conv positions are excluded from the max
 // (reference: -inf pool padding).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,20 +30,32 @@
 namespace dcfa {
 namespace {
 
-constexpr int TPH = 3, TPW = 16;              // pooled tile
+#ifndef DCFA_STEM_TPW
+#define DCFA_STEM_TPW 16
+#endif
+constexpr int TPH = 3, TPW = DCFA_STEM_TPW;   // pooled tile
 constexpr int CH = 2 * TPH + 1;               // 7 conv rows
 constexpr int CW = 2 * TPW + 1;               // 33 conv cols
 constexpr int NPIX = CH * CW;                 // 231 conv pixels, GEMM column m = cx * CH + cy
-constexpr int UMMA_N = 240;                   // NPIX rounded up to a multiple of 16
+constexpr int UMMA_N = (NPIX + 15) / 16 * 16;  // 128 (TPW 8) or 240 (TPW 16)
 constexpr int PH = CH + 2;                    // 9 patch rows
-constexpr int PWB = 36;                       // patch row pitch in floats (35 needed; 16-byte multiple for the TMA box)
+#ifndef DCFA_STEM_PWB
+#define DCFA_STEM_PWB (2 * DCFA_STEM_TPW + 8)
+#endif
+constexpr int PWB = DCFA_STEM_PWB;            // patch row pitch in floats: 35 needed + XOFF, 16-byte multiple for the TMA box
+constexpr int XOFF = 2;                       // the TMA box must start on a 16-byte boundary of the innermost (x) dimension:
+                                              // it starts at image column 2*px0 - 4, two columns left of the patch
+constexpr int PATCH_BUF = (3 * (2 * TPH + 3) * PWB * 4 + 1023) / 1024 * 1024;   // bytes reserved per patch buffer
+constexpr int NBUF = 4;                       // patch ring: loads run NBUF-1 tiles ahead (round 1: with one box in flight
+                                              // per CTA the kernel was bound by the TMA round-trip latency)
 constexpr int PATCH_FLOATS = 3 * PH * PWB;    // 972
 constexpr int PATCH_BYTES = PATCH_FLOATS * 4; // 3888
-constexpr int kStemThreads = 256;
+constexpr int kStemThreads = TPW == 16 ? 256 : 128;
+constexpr int kStemCtasPerSm = TPW == 16 ? 2 : 4;
 constexpr int KROW = 64;                      // bytes per K row: 32 bf16 (27 used), SWIZZLE_64B
-constexpr int B_BYTES = 256 * KROW;           // im2col tile (240 rows used)
+constexpr int B_BYTES = (TPW == 16 ? 256 : 128) * KROW;   // im2col tile
 constexpr int A_BYTES = 128 * KROW;           // replicated weight tile
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = TPW == 16 ? 256 : 128;
 
 struct StemArgs {
   const float* x[2];
@@ -62,24 +75,32 @@ __device__ __forceinline__ void tma_load_patch(uint32_t dst, const CUtensorMap* 
       : "memory");
 }
 
-struct TileCoord {
-  int g, nl, n, py0, px0;
+// Tile coordinates advanced incrementally (tile index += gridDim.x): the per-tile path has no divisions.
+// Tiles are ordered (image over both groups, tile row, tile column).
+struct TileIter {
+  int tx, ty, n;       // tile column, tile row, image index over both groups
+  int sx, sy, sn;      // mixed-radix digits of the step gridDim.x
+  __device__ __forceinline__ void init(int tile, int step, int tiles_x, int tiles_y) {
+    const int per_img = tiles_x * tiles_y;
+    n = tile / per_img;
+    int r = tile - n * per_img;
+    ty = r / tiles_x;
+    tx = r - ty * tiles_x;
+    sn = step / per_img;
+    r = step - sn * per_img;
+    sy = r / tiles_x;
+    sx = r - sy * tiles_x;
+  }
+  __device__ __forceinline__ void advance(int tiles_x, int tiles_y) {
+    tx += sx;
+    if (tx >= tiles_x) { tx -= tiles_x; ty += 1; }
+    ty += sy;
+    if (ty >= tiles_y) { ty -= tiles_y; n += 1; }
+    n += sn;
+  }
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const StemArgs& p, int tile) {
-  TileCoord t;
-  t.g = tile / p.tiles_per_group;
-  int r = tile - t.g * p.tiles_per_group;
-  const int tx = r % p.tiles_x; r /= p.tiles_x;
-  const int ty = r % p.tiles_y;
-  t.nl = r / p.tiles_y;
-  t.n = t.g * p.group_imgs + t.nl;
-  t.py0 = ty * TPH;
-  t.px0 = tx * TPW;
-  return t;
-}
-
-__global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_constant__ CUtensorMap map0,
+__global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(const __grid_constant__ CUtensorMap map0,
                                                                const __grid_constant__ CUtensorMap map1,
                                                                const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -90,18 +111,17 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_cons
   const uint32_t s_a = s_b + B_BYTES;
   const uint32_t s_patch = s_a + A_BYTES;
   float* patch_ptr = reinterpret_cast<float*>(gbase + B_BYTES + A_BYTES);
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(gbase + B_BYTES + A_BYTES + 2 * 4096);
-  const uint32_t bars = s_patch + 2u * 4096u + (uint32_t)(TPH * TPW) * 128u * 2u;
-  const uint32_t bar_patch = bars;            // 2 barriers
-  const uint32_t bar_mma = bars + 16u;
-  const uint32_t tmem_slot = bars + 24u;
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(gbase + B_BYTES + A_BYTES + NBUF * PATCH_BUF);
+  const uint32_t bars = s_patch + (uint32_t)(NBUF * PATCH_BUF) + (uint32_t)(TPH * TPW) * 128u * 2u;
+  const uint32_t bar_patch = bars;            // NBUF barriers
+  const uint32_t bar_mma = bars + 8u * NBUF;
+  const uint32_t tmem_slot = bar_mma + 8u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_init(bar_patch, 1);
-      ptx::mbar_init(bar_patch + 8u, 1);
+      for (int i = 0; i < NBUF; ++i) ptx::mbar_init(bar_patch + 8u * i, 1);
       ptx::mbar_init(bar_mma, 1);
       ptx::fence_mbar_init();
     }
@@ -124,69 +144,93 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_cons
   const int ch = mrow % p.C0pad;
   const int rep = mrow / p.C0pad;
   const int nrep = 128 / p.C0pad;             // 4, 2 or 1 replicas
-  const int nsub = nrep * 2;                  // strips: (replica, warp half)
+  const int nsub = nrep * (kStemThreads / 128); // strips: (replica, warp half)
   const int units_per_sub = (TPW / 2) / nsub; // units of 2 pooled columns per strip: 1, 2 or 4
-  const int sub = rep * 2 + half;
+  const int sub = rep * (kStemThreads / 128) + half;
   const bool ch_valid = ch < p.C0;
+
+  // pooled-tile store mapping (tile-invariant): 16-byte chunk idx -> (pooled pixel pp, channel chunk c8)
+  constexpr int kMaxChunks = (TPH * TPW * 16 + kStemThreads - 1) / kStemThreads;   // C0 <= 128 -> 16 chunks / pixel
+  const int c8n = p.C0 >> 3;
+  const int nchunks = TPH * TPW * c8n;
+  int st_pp[kMaxChunks], st_c8[kMaxChunks];
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int i = tid + k * kStemThreads;
+    st_pp[k] = i < nchunks ? i / c8n : -1;
+    st_c8[k] = i < nchunks ? i - (i / c8n) * c8n : 0;
+  }
 
   int cur_group = -1;
   float sc = 0.0f, bi = 0.0f;
-  uint32_t it = 0;            // tiles processed by this CTA: buffer = it & 1, its mbarrier parity = (it >> 1) & 1
+  uint32_t it = 0;            // tiles processed by this CTA: ring slot = it % NBUF, its mbarrier parity = (it / NBUF) & 1
   uint32_t mma_phase = 0u;
 
-  // prologue: request the first tile's patch
-  int tile = blockIdx.x;
-  if (tile < p.total_tiles && p.use_tma && tid == 0) {
-    const TileCoord t = decode_tile(p, tile);
-    ptx::mbar_arrive_expect_tx(bar_patch, PATCH_BYTES);
+  TileIter cur;               // the tile being processed (all threads)
+  cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+  TileIter pre = cur;         // the tile whose patch is requested next (thread 32 only), NBUF-1 tiles ahead
+
+  // issue the TMA load of one tile's patch into ring slot `slot` (one thread)
+  auto issue_patch = [&](const TileIter& tc, int slot) {
+    const uint32_t bar = bar_patch + 8u * slot;
+    const uint32_t dst = s_patch + (uint32_t)slot * (uint32_t)PATCH_BUF;
+    const int g = tc.n >= p.group_imgs ? 1 : 0;
+    const int x = 2 * tc.tx * TPW - 2 - XOFF, y = 2 * tc.ty * TPH - 2;
+    ptx::mbar_arrive_expect_tx(bar, PATCH_BYTES);
     // (no pointer select between the two maps: that would copy a __grid_constant__ parameter to local memory)
-    if (t.g == 0) tma_load_patch(s_patch, &map0, 2 * t.px0 - 2, 2 * t.py0 - 2, t.nl, bar_patch);
-    else tma_load_patch(s_patch, &map1, 2 * t.px0 - 2, 2 * t.py0 - 2, t.nl, bar_patch);
+    if (g == 0) tma_load_patch(dst, &map0, x, y, tc.n, bar);
+    else tma_load_patch(dst, &map1, x, y, tc.n - p.group_imgs, bar);
+  };
+  if (p.use_tma && tid == 32) {   // prologue: request the first NBUF-1 patches
+    for (int d = 0; d < NBUF - 1; ++d) {
+      if (pre.n < p.n_img) issue_patch(pre, d);
+      pre.advance(p.tiles_x, p.tiles_y);
+    }
   }
 
   int buf = 0;
-  for (; tile < p.total_tiles; tile += gridDim.x, buf ^= 1, ++it) {
-    const TileCoord t = decode_tile(p, tile);
-    const int cy0 = 2 * t.py0 - 1, cx0 = 2 * t.px0 - 1;  // conv-map origin of the tile (patch origin is one less)
-    float* s_in = patch_ptr + buf * 1024;                 // [3][PH][PWB]
+  for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), buf = (buf + 1 == NBUF ? 0 : buf + 1), ++it) {
+    const int g = cur.n >= p.group_imgs ? 1 : 0;
+    const int nl = cur.n - g * p.group_imgs;
+    const int py0 = cur.ty * TPH, px0 = cur.tx * TPW;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // conv-map origin of the tile (patch origin is one less)
+    float* s_in = patch_ptr + buf * (PATCH_BUF / 4);   // [3][PH][PWB]
 
-    if (t.g != cur_group) {  // (re)load this modality's weight tile and this thread's scale/bias
-      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)t.g * 128 * 32);
+    if (g != cur_group) {  // (re)load this modality's weight tile and this thread's scale/bias
+      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)g * 128 * 32);
       uint4* dst = reinterpret_cast<uint4*>(gbase + B_BYTES);
       for (int i = tid; i < A_BYTES / 16; i += kStemThreads) dst[i] = __ldg(src + i);
-      sc = __ldg(p.scale + (int64_t)t.g * p.C0pad + ch);
-      bi = __ldg(p.bias + (int64_t)t.g * p.C0pad + ch);
-      cur_group = t.g;
+      sc = __ldg(p.scale + (int64_t)g * p.C0pad + ch);
+      bi = __ldg(p.bias + (int64_t)g * p.C0pad + ch);
+      cur_group = g;
     }
     if (p.use_tma) {
-      ptx::mbar_wait(bar_patch + 8u * buf, (it >> 1) & 1u);
+      ptx::mbar_wait(bar_patch + 8u * buf, (it / NBUF) & 1u);
     } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
-      const float* img = p.x[t.g] + (int64_t)t.nl * 3 * p.Hi * p.Wi;
-      for (int i = tid; i < 3 * PH * 35; i += kStemThreads) {
-        const int c = i / (PH * 35);
-        const int r = (i - c * PH * 35) / 35;
-        const int q = i - c * PH * 35 - r * 35;
+      const float* img = (g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
+      constexpr int PC = CW + 2;   // patch columns actually used
+      for (int i = tid; i < 3 * PH * PC; i += kStemThreads) {
+        const int c = i / (PH * PC);
+        const int r = (i - c * PH * PC) / PC;
+        const int q = i - c * PH * PC - r * PC;
         const int iy = cy0 - 1 + r, ix = cx0 - 1 + q;
         float v = 0.0f;
         if (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) v = __ldg(img + ((int64_t)c * p.Hi + iy) * p.Wi + ix);
-        s_in[(c * PH + r) * PWB + q] = v;
+        s_in[(c * PH + r) * PWB + q + XOFF] = v;
       }
       __syncthreads();
     }
 
     // ---- im2col: one conv pixel per thread, K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes
     if (tid < NPIX) {
-      const float* pin = s_in + icy * PWB + icx;
+      const float* pin = s_in + icy * PWB + icx + XOFF;
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float v0 = 0.0f, v1 = 0.0f;
-        {
-          constexpr int dummy = 0; (void)dummy;
-          const int k0 = 2 * j, k1 = 2 * j + 1;
-          if (k0 < 27) v0 = pin[((k0 % 3) * PH + (k0 / 9)) * PWB + ((k0 / 3) % 3)];
-          if (k1 < 27) v1 = pin[((k1 % 3) * PH + (k1 / 9)) * PWB + ((k1 / 3) % 3)];
-        }
+        const int k0 = 2 * j, k1 = 2 * j + 1;   // compile-time after unrolling
+        if (k0 < 27) v0 = pin[((k0 % 3) * PH + (k0 / 9)) * PWB + ((k0 / 3) % 3)];
+        if (k1 < 27) v1 = pin[((k1 % 3) * PH + (k1 / 9)) * PWB + ((k1 / 3) % 3)];
         pk[j] = pack_bf16x2(v0, v1);
       }
       const uint32_t rowb = s_b + (uint32_t)tid * KROW;
@@ -197,26 +241,24 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_cons
                      "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
                      : "memory");
     }
-    ptx::fence_proxy_async_smem();
-    __syncthreads();   // B tile (and A tile) visible; the patch buffer `buf` has been consumed
+    __syncthreads();   // B tile (and A tile) written; the patch slot `buf` has been consumed
 
+    if (tid == 32 && p.use_tma) {
+      // request the patch NBUF-1 tiles ahead into the slot the previous tile released.  Issued by a different
+      // thread than the MMA issuer: fence.proxy.async waits for the executing thread's own outstanding bulk
+      // copies, which would serialise the prefetch ring behind every MMA.
+      if (pre.n < p.n_img) issue_patch(pre, buf == 0 ? NBUF - 1 : buf - 1);
+      pre.advance(p.tiles_x, p.tiles_y);
+    }
     if (tid == 0) {
-      // prefetch the NEXT tile's patch into the other buffer (free since the previous tile's im2col)
-      const int nxt = tile + gridDim.x;
-      if (p.use_tma && nxt < p.total_tiles) {
-        const TileCoord tn = decode_tile(p, nxt);
-        ptx::mbar_arrive_expect_tx(bar_patch + 8u * (buf ^ 1), PATCH_BYTES);
-        if (tn.g == 0)
-          tma_load_patch(s_patch + (uint32_t)(buf ^ 1) * 4096u, &map0, 2 * tn.px0 - 2, 2 * tn.py0 - 2, tn.nl, bar_patch + 8u * (buf ^ 1));
-        else
-          tma_load_patch(s_patch + (uint32_t)(buf ^ 1) * 4096u, &map1, 2 * tn.px0 - 2, 2 * tn.py0 - 2, tn.nl, bar_patch + 8u * (buf ^ 1));
-      }
+      // consumer-side proxy fence: the other threads' st.shared (ordered before this point by the barrier)
+      // become visible to the async proxy that reads the MMA operands
+      ptx::fence_proxy_async_smem();
       ptx::tc_fence_after();
       // SWIZZLE_64B K-major descriptors: SBO = 8 rows * 64 B, layout code 4
-      uint64_t adesc = (uint64_t)((s_a & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-                       ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-      uint64_t bdesc = (uint64_t)((s_b & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-                       ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+      const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+      const uint64_t adesc = desc_hi | (uint64_t)((s_a & 0x3FFFFu) >> 4);
+      const uint64_t bdesc = desc_hi | (uint64_t)((s_b & 0x3FFFFu) >> 4);
       ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
       ptx::umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);   // K 16..31: +32 bytes
       ptx::umma_commit(bar_mma);
@@ -230,11 +272,11 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_cons
     for (int u = 0; u < units_per_sub; ++u) {
       const int pc0 = 2 * (sub * units_per_sub + u);    // first pooled column of the unit (tile-local)
       const int j0 = 2 * pc0;                           // first conv column
-      uint32_t raw[48];
+      uint32_t raw[36];
       const uint32_t taddr = tmem_base + (uint32_t)(j0 * CH) + ((uint32_t)(q4 * 32) << 16);
       ptx::tmem_ld_x16(taddr, raw);
       ptx::tmem_ld_x16(taddr + 16u, raw + 16);
-      ptx::tmem_ld_x16(taddr + 32u, raw + 32);          // columns 32..34 needed (35..47 are the next unit's / spare)
+      ptx::tmem_ld_x4(taddr + 32u, raw + 32);           // columns 32..34 are needed; stay inside the allocation
       ptx::tmem_ld_wait();
       float v[5][CH];
 #pragma unroll
@@ -274,15 +316,17 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const __grid_cons
     __syncthreads();   // staging complete; TMEM and the B tile may be overwritten by the next tile
 
     // ---- pooled NHWC tile -> global, 16 bytes per thread, channel-contiguous
-    const int c8n = p.C0 >> 3;
-    for (int i = tid; i < TPH * TPW * c8n; i += kStemThreads) {
-      const int c8 = i % c8n;
-      const int pp = i / c8n;
-      const int pxl = pp % TPW, pyl = pp / TPW;
-      const int py = t.py0 + pyl, px = t.px0 + pxl;
-      if (py < p.Ho && px < p.Wo) {
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + pp * p.C0pad + c8 * 8);
-        stg128(p.y.p + p.y.img_off(t.n) + (int64_t)(py * p.Wo + px) * p.y.ld + c8 * 8, val);
+    __nv_bfloat16* ybase = p.y.p + p.y.img_off(cur.n);
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      const int pp = st_pp[k];
+      if (pp >= 0) {
+        const int pyl = pp / TPW, pxl = pp - pyl * TPW;   // TPW is a compile-time power of two
+        const int py = py0 + pyl, px = px0 + pxl;
+        if (py < p.Ho && px < p.Wo) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + pp * p.C0pad + st_c8[k] * 8);
+          stg128(ybase + (int64_t)(py * p.Wo + px) * p.y.ld + st_c8[k] * 8, val);
+        }
       }
     }
     __syncthreads();   // staging is rewritten by the next tile's epilogue
@@ -364,14 +408,14 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
       if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled failed with %d", (int)cr);
     }
   }
-  const size_t smem = 1024 + B_BYTES + A_BYTES + 2 * 4096 + (size_t)TPH * TPW * 128 * 2 + 64;
+  const size_t smem = 1024 + B_BYTES + A_BYTES + NBUF * PATCH_BUF + (size_t)TPH * TPW * 128 * 2 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "stem: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  int64_t grid = (int64_t)sm_count() * 2;   // two CTAs per SM: 2 x 256 TMEM columns, 2 x ~46 KB shared memory
+  int64_t grid = (int64_t)sm_count() * kStemCtasPerSm;   // CTAs per SM bounded by TMEM columns (512 / kTmemCols)
   if (grid > total) grid = total;
   stem_kernel<<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
   DCFA_CHECK_LAUNCH("stem_kernel");
