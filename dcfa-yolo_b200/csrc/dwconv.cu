@@ -3,13 +3,259 @@
 //   RepGhostModule cheap_operation + fusion_bn identity branch nets/repghost.py:98-115 (the identity-BN
 //   is folded into the centre tap exactly as switch_to_deploy does, :117-123), optional SiLU (:105-106,115)
 //   and the bottleneck's identity shortcut (:279).
-// Memory-bound: each thread owns 8 channels (one 128-bit word) of 4 horizontally adjacent output pixels,
-// so the 72 fp32 weights it needs are loaded once and the 3x6 input window is read with 18 vector loads.
+//
+// Memory-bound (9 MAC per element).  Two paths:
+//   dwconv_tma_kernel   plain [N,H,W,C] views: persistent CTAs; per tile one cp.async.bulk.tensor box load of
+//       the (TH+2) x (TW+2) x 64-channel halo window (out-of-image pixels zero-filled by the TMA = conv
+//       padding), double-buffered; threads read 128-bit channel vectors from shared memory, accumulate in
+//       fp32, stage the bf16 result and one thread issues the TMA store (partial tiles clipped by hardware).
+//       Round-1 profile of the first version (direct global loads, 4 pixels x 8 channels per thread):
+//       1.4 TB/s, 16 warps/SM at 91 registers, latency-bound.
+//   dwconv3x3_kernel    fallback for grouped / oddly strided views (direct 128-bit global loads).
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcfa {
 namespace {
 
+// ------------------------------------------------------------------------------------------ TMA path
+constexpr int TH = 8, TW = 16;                 // output tile (pixels)
+constexpr int HH = TH + 2, HW = TW + 2;        // halo window
+constexpr int CB = 64;                         // channels per tile (128-byte rows)
+constexpr int kDwThreads = 256;
+constexpr int IN_BYTES = HH * HW * CB * 2;     // 23040
+constexpr int IN_BUF = (IN_BYTES + 1023) / 1024 * 1024;
+constexpr int OUT_BYTES = TH * TW * CB * 2;    // 16384
+constexpr int NIN = 2;                         // input ring: the next tile's box loads while this one computes
+                                               // (~98 KB per CTA -> two CTAs per SM)
+
+struct DwTmaArgs {
+  const float* w;     // [G][9][C]
+  const float* bias;  // [G][C]
+  int n_img, group_imgs, H, W, C, act;
+  int cblocks;        // C / 64 (C % 64 == 0) or 1 with cb = C (C in {16, 32})
+  int cb;             // channels per tile
+  int tiles_x, tiles_y;
+  int total_tiles;
+  int has_res;
+};
+
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, uint32_t src, int c, int x, int y, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c), "r"(x), "r"(y), "r"(n)
+               : "memory");
+}
+
+struct DwTile {
+  int cbi, tx, ty, n;
+};
+__device__ __forceinline__ DwTile dw_decode(const DwTmaArgs& p, int tile) {
+  DwTile t;
+  t.cbi = tile % p.cblocks; tile /= p.cblocks;
+  t.tx = tile % p.tiles_x; tile /= p.tiles_x;
+  t.ty = tile % p.tiles_y;
+  t.n = tile / p.tiles_y;
+  return t;
+}
+
+// One thread = one 8-channel chunk (c8) of one tile column, R consecutive output rows (R * c8n * TW * parts == 256 * R
+// covers the TH x TW tile).  Per kernel column q the 3 weight vectors stay in registers while the thread walks
+// down R + 2 input rows, each input vector feeding up to 3 output rows: 3*(R+2) + 9 shared-memory loads for R
+// outputs instead of 27 per output.
+template <int R>
+__device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_t* in, const uint8_t* res, uint8_t* out,
+                                                const float* w_s, const float* b_s, int tid, int row_bytes) {
+  const int c8n = p.cb >> 3;
+  const int c8 = tid % c8n;
+  const int col = (tid / c8n) % TW;
+  const int oy0 = (tid / (c8n * TW)) * R;
+  float acc[R][8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(b_s + c8 * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(b_s + c8 * 8 + 4);
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+      acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float w[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8 + 4);
+      w[r][0] = w0.x; w[r][1] = w0.y; w[r][2] = w0.z; w[r][3] = w0.w;
+      w[r][4] = w1.x; w[r][5] = w1.y; w[r][6] = w1.z; w[r][7] = w1.w;
+    }
+#pragma unroll
+    for (int ri = 0; ri < R + 2; ++ri) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(in + ((oy0 + ri) * HW + col + q) * row_bytes + c8 * 16), v);
+#pragma unroll
+      for (int o = 0; o < R; ++o) {
+        const int r = ri - o;   // kernel row that maps input row ri to output row o (compile-time after unrolling)
+        if (r >= 0 && r < 3) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(v[e], w[r][e], acc[o][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < R; ++o) {
+    const int pp = (oy0 + o) * TW + col;
+    if (p.act == DCFA_ACT_SILU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] = acc[o][e] * sigmoid_fast(acc[o][e]);
+    } else if (p.act == DCFA_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] = fmaxf(acc[o][e], 0.0f);
+    }
+    if (p.has_res) {
+      float rr[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + pp * row_bytes + c8 * 16), rr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] += rr[e];
+    }
+    *reinterpret_cast<uint4*>(out + pp * row_bytes + c8 * 16) = pack8(acc[o]);
+  }
+}
+
+__global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                   const __grid_constant__ CUtensorMap map_y,
+                                                                   const __grid_constant__ CUtensorMap map_r,
+                                                                   const DwTmaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
+  // layout: in[NIN] | res (one tile, optional) | out[2] | w (9*64 fp32) | bias (64 fp32) | barriers
+  const uint32_t s_in = base;
+  const uint32_t s_res = s_in + NIN * IN_BUF;
+  const uint32_t s_out = s_res + OUT_BYTES;
+  float* w_s = reinterpret_cast<float*>(gbase + NIN * IN_BUF + 3 * OUT_BYTES);
+  float* b_s = w_s + 9 * CB;
+  const uint32_t bars = s_out + 2 * OUT_BYTES + (9 * CB + CB) * 4;
+  const uint32_t bar_in = bars;               // NIN barriers (input box [+ residual box] landed)
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < NIN; ++i) ptx::mbar_init(bar_in + 8u * i, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int row_bytes = p.cb * 2;             // bytes per pixel row in shared memory (dense, no swizzle)
+  const uint32_t in_bytes = (uint32_t)(HH * HW) * row_bytes;
+  const uint32_t out_bytes = (uint32_t)(TH * TW) * row_bytes;
+
+  auto issue = [&](int tile, int slot) {      // one thread: input halo box (+ residual box) of `tile`
+    const DwTile t = dw_decode(p, tile);
+    const uint32_t bar = bar_in + 8u * slot;
+    ptx::mbar_arrive_expect_tx(bar, in_bytes + (p.has_res ? out_bytes : 0u));
+    tma_load_box(s_in + (uint32_t)slot * IN_BUF, &map_x, t.cbi * p.cb, t.tx * TW - 1, t.ty * TH - 1, t.n, bar);
+    if (p.has_res) tma_load_box(s_res + 0u, &map_r, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n, bar);
+  };
+  // NOTE: the residual buffer is single: the residual box of tile i+k must not land before tile i consumed its
+  // own, so with a residual the ring runs one tile ahead only (handled below by `ahead`).
+  const int ahead = p.has_res ? 1 : NIN - 1;
+  int tile = blockIdx.x;
+  if (tid == 32) {
+    for (int d = 0; d < ahead; ++d)
+      if (tile + d * (int)gridDim.x < p.total_tiles) issue(tile + d * (int)gridDim.x, d);
+  }
+
+  // per-thread mapping: 16-byte channel chunk c8 of output pixel (py, px); c8n chunks per pixel
+  const int c8n = p.cb >> 3;
+  int cur_key = -1;
+  uint32_t it = 0;
+  int slot = 0;
+  for (; tile < p.total_tiles; tile += gridDim.x, ++it, slot = (slot + 1 == NIN ? 0 : slot + 1)) {
+    const DwTile t = dw_decode(p, tile);
+    const int g = t.n / p.group_imgs;
+    const int key = g * p.cblocks + t.cbi;
+    if (key != cur_key) {                     // this (group, channel block)'s weights and bias
+      __syncthreads();
+      for (int i = tid; i < 9 * p.cb; i += kDwThreads) {
+        const int tap = i / p.cb, c = i - tap * p.cb;
+        w_s[tap * CB + c] = __ldg(p.w + ((int64_t)g * 9 + tap) * p.C + t.cbi * p.cb + c);
+      }
+      for (int i = tid; i < p.cb; i += kDwThreads) b_s[i] = __ldg(p.bias + (int64_t)g * p.C + t.cbi * p.cb + i);
+      cur_key = key;
+      __syncthreads();
+    }
+    ptx::mbar_wait(bar_in + 8u * slot, (it / NIN) & 1u);
+    const uint8_t* in = gbase + slot * IN_BUF;
+    const uint8_t* res = gbase + NIN * IN_BUF;
+    uint8_t* out = gbase + NIN * IN_BUF + OUT_BYTES + (it & 1u) * OUT_BYTES;
+
+    // the staging buffer (it & 1) was last read by the TMA store issued two tiles ago
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+
+    if (c8n == 8) dw_tile_compute<4>(p, in, res, out, w_s, b_s, tid, row_bytes);
+    else if (c8n == 4) dw_tile_compute<2>(p, in, res, out, w_s, b_s, tid, row_bytes);
+    else dw_tile_compute<1>(p, in, res, out, w_s, b_s, tid, row_bytes);
+    ptx::fence_proxy_async_smem();   // staged tile -> async proxy (TMA store); no bulk loads are owned by these threads
+    __syncthreads();                 // input slot and residual buffer consumed, staging complete
+    if (tid == 32) {                 // refill the ring (this thread owns all bulk loads)
+      const int nxt = tile + ahead * (int)gridDim.x;
+      if (nxt < p.total_tiles) issue(nxt, (slot + ahead) % NIN);
+    }
+    if (tid == 0) {                  // this thread owns all bulk stores
+      tma_store_box(&map_y, s_out + (it & 1u) * OUT_BYTES, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn dw_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// rank-4 map (C, W, H, N) over a plain NHWC bf16 view, box (cb, bw, bh, 1), no swizzle
+int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int ld, int64_t img_stride, int cb, int bw, int bh) {
+  EncodeTiledFn enc = dw_encode_fn();
+  if (!enc) return fail(DCFA_E_CUDA, "dwconv: cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)img_stride * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+  const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  const int64_t run = (C == ld) ? (int64_t)C * 2 * W : (int64_t)C * 2;
+  const CUtensorMapL2promotion promo = run >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : (run >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
+  CUresult cr = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "dwconv: cuTensorMapEncodeTiled failed with %d", (int)cr);
+  return DCFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fallback path
 constexpr int XT = 4;
 
 struct DwArgs {
@@ -95,6 +341,11 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
   }
 }
 
+template <typename T>
+bool plain_view(const View<T>& v) {
+  return v.gi <= 0 || v.gstride == (int64_t)v.gi * v.img_stride;
+}
+
 }  // namespace
 
 int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
@@ -117,6 +368,45 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     DCFA_REQUIRE(((uintptr_t)a.res.p % 16) == 0 && a.res.ld % 8 == 0 && a.res.img_stride % 8 == 0 && a.res.gstride % 8 == 0,
                  "dwconv: residual view must be 16-byte aligned");
   DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0 && ((uintptr_t)a.bias % 16) == 0, "dwconv: params must be 16-byte aligned");
+
+  // ---- TMA path: plain views, channel count a multiple of 64 or exactly 16 / 32
+  const bool cb_ok = (a.C % CB == 0) || a.C == 32 || a.C == 16;
+  if (cb_ok && plain_view(a.x) && plain_view(a.y) && (!a.res.p || plain_view(a.res))) {
+    DwTmaArgs t;
+    t.w = a.w; t.bias = a.bias;
+    t.n_img = a.n_img; t.group_imgs = a.group_imgs; t.H = a.H; t.W = a.W; t.C = a.C; t.act = a.act;
+    t.cb = a.C % CB == 0 ? CB : a.C;
+    t.cblocks = a.C / t.cb;
+    t.tiles_x = ceil_div(a.W, TW);
+    t.tiles_y = ceil_div(a.H, TH);
+    const int64_t total = (int64_t)a.n_img * t.tiles_x * t.tiles_y * t.cblocks;
+    DCFA_REQUIRE(total < (1ll << 31), "dwconv: too many tiles");
+    t.total_tiles = (int)total;
+    t.has_res = a.res.p ? 1 : 0;
+    alignas(64) CUtensorMap mx, my, mr;
+    memset(&mr, 0, sizeof(mr));
+    int rc = make_map(&mx, a.x.p, a.C, a.W, a.H, a.n_img, a.x.ld, a.x.img_stride, t.cb, HW, HH);
+    if (rc) return rc;
+    rc = make_map(&my, a.y.p, a.C, a.W, a.H, a.n_img, a.y.ld, a.y.img_stride, t.cb, TW, TH);
+    if (rc) return rc;
+    if (a.res.p) {
+      rc = make_map(&mr, a.res.p, a.C, a.W, a.H, a.n_img, a.res.ld, a.res.img_stride, t.cb, TW, TH);
+      if (rc) return rc;
+    }
+    const size_t smem = 1024 + NIN * IN_BUF + 3 * OUT_BYTES + (9 * CB + CB) * 4 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(DCFA_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    int64_t grid = (int64_t)sm_count() * 2;
+    if (grid > total) grid = total;
+    dwconv_tma_kernel<<<(unsigned)grid, kDwThreads, smem, st>>>(mx, my, mr, t);
+    DCFA_CHECK_LAUNCH("dwconv_tma_kernel");
+    return DCFA_OK;
+  }
+
   a.xg = ceil_div(a.W, XT);
   a.total = (int64_t)a.n_img * a.H * a.xg * (a.C >> 3);
   int64_t blocks = (a.total + 255) / 256;

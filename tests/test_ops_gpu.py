@@ -153,7 +153,9 @@ def test_stem(cuda, b, h, w, c0, groups):
 
 
 @pytest.mark.parametrize("n,h,w,c,act,groups,use_res", [(2, 9, 11, 16, 0, 1, False), (4, 20, 20, 64, 2, 2, True),
-                                                      (2, 13, 6, 128, 2, 1, True)])
+                                                      (2, 13, 6, 128, 2, 1, True), (2, 40, 40, 32, 0, 2, False),
+                                                      (3, 33, 50, 256, 2, 1, True), (2, 160, 160, 32, 0, 2, False),
+                                                      (2, 21, 19, 24, 2, 1, True)])
 def test_dwconv(cuda, n, h, w, c, act, groups, use_res):
     from dcfa_b200 import abi
     g = torch.Generator().manual_seed(9)
