@@ -7,6 +7,8 @@
 // Used at the six fusion sites (:346-353, :403-415) and inside SPPF_CBAM (:18-31, hidden width 1).
 // All channel accesses are 128-bit (8 x bf16); reductions are warp shuffles / fixed-order loops, so the
 // result is deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dcfa {
@@ -20,32 +22,44 @@ struct PoolArgs {
   int n_img, HW, C, parts, pix_per_part;
 };
 
+constexpr int kU = 4;  // independent 128-bit loads in flight per thread in the streaming loops below
+
+// Thread mapping shared by POOL / STATS / APPLY: the CTA's 256 threads form `planes` pixel planes of c8n
+// threads; a thread keeps ONE 8-channel chunk for its whole life (its gate values stay in registers) and walks
+// pixels plane, plane + planes, ...   (c8n <= 256; threads beyond planes * c8n idle when 256 % c8n != 0)
 __global__ void __launch_bounds__(256) cbam_pool_kernel(const PoolArgs p) {
   extern __shared__ float s_red[];  // [planes][2][C]
   const int c8n = p.C >> 3;          // <= 256 (C <= 2048)
-  const int planes = 256 / c8n;      // pixel planes: threads with the same channel chunk
+  const int planes = 256 / c8n;
   const int n = blockIdx.x / p.parts;
   const int part = blockIdx.x - n * p.parts;
   const int p0 = part * p.pix_per_part;
   const int p1 = min(p.HW, p0 + p.pix_per_part);
-  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n);
   const int c8 = (int)threadIdx.x % c8n;
   const int plane = (int)threadIdx.x / c8n;
   if (plane < planes) {
+    const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + c8 * 8;
     float s[8], m[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.0f; m[e] = -INFINITY; }
-    for (int px = p0 + plane; px < p1; px += planes) {
-      float v[8];
-      unpack8(ldg128(xin + (int64_t)px * p.x.ld + c8 * 8), v);
+    for (int px = p0 + plane; px < p1; px += planes * kU) {
+      uint4 r[kU];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += v[e]; m[e] = fmaxf(m[e], v[e]); }
-    }
+      for (int u = 0; u < kU; ++u)
+        if (px + u * planes < p1) r[u] = ldg128(xin + (int64_t)(px + u * planes) * p.x.ld);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s_red[(plane * 2 + 0) * p.C + c8 * 8 + e] = s[e];
-      s_red[(plane * 2 + 1) * p.C + c8 * 8 + e] = m[e];
+      for (int u = 0; u < kU; ++u)
+        if (px + u * planes < p1) {
+          float v[8];
+          unpack8(r[u], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { s[e] += v[e]; m[e] = fmaxf(m[e], v[e]); }
+        }
     }
+    float4* ds = reinterpret_cast<float4*>(s_red + (plane * 2 + 0) * p.C + c8 * 8);
+    float4* dm = reinterpret_cast<float4*>(s_red + (plane * 2 + 1) * p.C + c8 * 8);
+    ds[0] = make_float4(s[0], s[1], s[2], s[3]); ds[1] = make_float4(s[4], s[5], s[6], s[7]);
+    dm[0] = make_float4(m[0], m[1], m[2], m[3]); dm[1] = make_float4(m[4], m[5], m[6], m[7]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += 256) {
@@ -116,47 +130,71 @@ struct StatsArgs {
   const float* gate;  // [n_img][C]
   float* stats;       // [n_img][HW][2]
   int n_img, HW, C;
-  int L;              // lanes cooperating on one pixel (power of two, <= 32)
-  int64_t total_pix;
+  int chunk;          // pixels per CTA (grid = chunks per image x images)
 };
 
+// Per pixel: mean and max over channels of x * gate.  Each thread reduces its own 8 channels, the per-chunk
+// partials of one round of planes * kU pixels meet in shared memory ([pixel][c8n + 1] float2, double buffered:
+// one barrier per round) and one thread per pixel adds them up in channel order.
 __global__ void __launch_bounds__(256) cbam_stats_kernel(const StatsArgs p) {
+  extern __shared__ float2 s_part[];  // [2][planes * kU][c8n + 1]
   const int c8n = p.C >> 3;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % p.L;        // lane inside the pixel group
-  const int grp = lane / p.L;        // pixel group inside the warp
-  const int gpw = 32 / p.L;          // pixels per warp iteration
-  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int planes = 256 / c8n;
+  const int round_px = planes * kU;
+  const int pitch = c8n + 1;
+  const int n = blockIdx.y;
+  const int q0 = blockIdx.x * p.chunk;
+  const int q1 = min(p.HW, q0 + p.chunk);
+  const int c8 = (int)threadIdx.x % c8n;
+  const int plane = (int)threadIdx.x / c8n;
+  const bool active = plane < planes;
+  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + c8 * 8;
+  float g[8];
+  {
+    const float4* gp = reinterpret_cast<const float4*>(p.gate + (int64_t)n * p.C + c8 * 8);
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+  }
   const float inv_c = 1.0f / (float)p.C;
-  for (int64_t base = warp_id * gpw; base < p.total_pix; base += nwarps * gpw) {
-    const int64_t pi = base + grp;
-    const bool ok = pi < p.total_pix;
-    float s = 0.0f, m = -INFINITY;
-    if (ok) {
-      const int n = (int)(pi / p.HW);
-      const int px = (int)(pi - (int64_t)n * p.HW);
-      const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + (int64_t)px * p.x.ld;
-      const float* gt = p.gate + (int64_t)n * p.C;
-      for (int c8 = sub; c8 < c8n; c8 += p.L) {
-        float v[8];
-        unpack8(ldg128(xin + c8 * 8), v);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + c8 * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + c8 * 8) + 1);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  int buf = 0;
+  for (int base = q0; base < q1; base += round_px, buf ^= 1) {
+    float2* part = s_part + buf * round_px * pitch;
+    if (active) {
+      uint4 r[kU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float t = v[e] * gg[e];
-          s += t;
-          m = fmaxf(m, t);
+      for (int u = 0; u < kU; ++u) {
+        const int px = base + u * planes + plane;
+        if (px < q1) r[u] = ldg128(xin + (int64_t)px * p.x.ld);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int px = base + u * planes + plane;
+        if (px < q1) {
+          float v[8];
+          unpack8(r[u], v);
+          float sm = 0.0f, mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float t = v[e] * g[e];
+            sm += t;
+            mx = fmaxf(mx, t);
+          }
+          part[(u * planes + plane) * pitch + c8] = make_float2(sm, mx);
         }
       }
     }
-    for (int o = p.L >> 1; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    const int px = base + (int)threadIdx.x;
+    if ((int)threadIdx.x < round_px && px < q1) {
+      const float2* row = part + threadIdx.x * pitch;
+      float sm = 0.0f, mx = -INFINITY;
+      for (int k = 0; k < c8n; ++k) {
+        const float2 t = row[k];
+        sm += t.x;
+        mx = fmaxf(mx, t.y);
+      }
+      *reinterpret_cast<float2*>(p.stats + ((int64_t)n * p.HW + px) * 2) = make_float2(sm * inv_c, mx);
     }
-    if (ok && sub == 0) *reinterpret_cast<float2*>(p.stats + pi * 2) = make_float2(s * inv_c, m);
   }
 }
 
@@ -208,22 +246,36 @@ __global__ void __launch_bounds__(256) cbam_apply_kernel(const ApplyArgs p) {
   }
   __syncthreads();
   const int c8n = p.C >> 3;
-  const int rows = min(RB, p.H - y0);
-  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n);
-  __nv_bfloat16* yout = p.y.p + p.y.img_off(n);
-  const float* gt = p.gate + (int64_t)n * p.C;
-  for (int i = threadIdx.x; i < rows * p.W * c8n; i += blockDim.x) {
-    const int c8 = i % c8n;
-    const int lp = i / c8n;  // pixel inside the band
-    const int64_t pix = (int64_t)y0 * p.W + lp;
-    float v[8];
-    unpack8(ldg128(xin + pix * p.x.ld + c8 * 8), v);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + c8 * 8));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + c8 * 8) + 1);
-    const float sp = s_s[lp];
-    v[0] *= g0.x * sp; v[1] *= g0.y * sp; v[2] *= g0.z * sp; v[3] *= g0.w * sp;
-    v[4] *= g1.x * sp; v[5] *= g1.y * sp; v[6] *= g1.z * sp; v[7] *= g1.w * sp;
-    stg128(yout + pix * p.y.ld + c8 * 8, pack8(v));
+  const int planes = 256 / c8n;
+  const int c8 = (int)threadIdx.x % c8n;
+  const int plane = (int)threadIdx.x / c8n;
+  if (plane >= planes) return;
+  const int npix = min(RB, p.H - y0) * p.W;
+  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + (int64_t)y0 * p.W * p.x.ld + c8 * 8;
+  __nv_bfloat16* yout = p.y.p + p.y.img_off(n) + (int64_t)y0 * p.W * p.y.ld + c8 * 8;
+  float gt8[8];
+  {
+    const float4* gp = reinterpret_cast<const float4*>(p.gate + (int64_t)n * p.C + c8 * 8);
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+    gt8[0] = g0.x; gt8[1] = g0.y; gt8[2] = g0.z; gt8[3] = g0.w; gt8[4] = g1.x; gt8[5] = g1.y; gt8[6] = g1.z; gt8[7] = g1.w;
+  }
+  for (int lp0 = plane; lp0 < npix; lp0 += planes * kU) {
+    uint4 r[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lp0 + u * planes < npix) r[u] = ldg128(xin + (int64_t)(lp0 + u * planes) * p.x.ld);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int lp = lp0 + u * planes;
+      if (lp < npix) {
+        float v[8];
+        unpack8(r[u], v);
+        const float sp = s_s[lp];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= gt8[e] * sp;
+        stg128(yout + (int64_t)lp * p.y.ld, pack8(v));
+      }
+    }
   }
 }
 
@@ -282,15 +334,17 @@ int launch_cbam_stats(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(view_aligned(a.x.p, a.x.ld, a.x.img_stride, a.x.gstride) && ((uintptr_t)a.gate % 16) == 0 &&
                    ((uintptr_t)a.stats % 8) == 0,
                "cbam_stats: misaligned tensor");
-  int L = 1;
-  while (L < 32 && L < (a.C >> 3)) L <<= 1;
-  a.L = L;
-  a.total_pix = (int64_t)a.n_img * a.HW;
-  const int gpw = 32 / L;
-  int64_t blocks = (a.total_pix + (int64_t)8 * gpw - 1) / ((int64_t)8 * gpw);
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  cbam_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DCFA_REQUIRE(a.C <= 2048, "cbam_stats: C %d unsupported", a.C);
+  const int c8n = a.C >> 3;
+  const int planes = 256 / c8n;
+  const int round_px = planes * kU;
+  // about 8 CTAs per SM over the whole grid, each CTA a whole number of rounds
+  int chunks = ceil_div(sm_count() * 8, a.n_img);
+  chunks = std::max(1, std::min(chunks, ceil_div(a.HW, round_px)));
+  a.chunk = ceil_div(ceil_div(a.HW, chunks), round_px) * round_px;
+  chunks = ceil_div(a.HW, a.chunk);
+  const size_t smem = (size_t)2 * round_px * (c8n + 1) * sizeof(float2);
+  cbam_stats_kernel<<<dim3((unsigned)chunks, (unsigned)a.n_img), 256, smem, st>>>(a);
   DCFA_CHECK_LAUNCH("cbam_stats_kernel");
   return DCFA_OK;
 }

@@ -84,21 +84,14 @@ struct SortArgs {
   int Apad;
 };
 
-// one CTA per image: bitonic sort of the n candidate keys, padded with sentinels to the next power of two
-__global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p) {
-  extern __shared__ uint64_t s_keys[];
-  uint64_t* g = p.keys + (int64_t)blockIdx.x * p.Apad;
+// Fallback for images with more than 16384 candidates: one CTA per image, bitonic sort in global memory.
+__global__ void __launch_bounds__(kNmsThreads) nms_sort_global_kernel(const SortArgs p) {
+  uint64_t* k = p.keys + (int64_t)blockIdx.x * p.Apad;
   const int n = p.cand[blockIdx.x];
-  if (n <= 1) return;
+  if (n <= kSmemSortMax) return;            // nms_sort_kernel handled it
   int N = 2;
   while (N < n) N <<= 1;
-  const bool use_smem = N <= kSmemSortMax;
-  uint64_t* k = use_smem ? s_keys : g;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) s_keys[i] = i < n ? g[i] : kSentinel;
-  } else {
-    for (int i = n + threadIdx.x; i < N; i += kNmsThreads) g[i] = kSentinel;  // N <= Apad
-  }
+  for (int i = n + threadIdx.x; i < N; i += kNmsThreads) k[i] = kSentinel;  // N <= Apad
   __syncthreads();
   const int half = N >> 1;
   for (int kk = 2; kk <= N; kk <<= 1) {
@@ -113,9 +106,80 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p)
       __syncthreads();
     }
   }
-  if (use_smem) {
-    for (int i = threadIdx.x; i < n; i += kNmsThreads) g[i] = s_keys[i];
+}
+
+// One CTA per image, bitonic sort of up to 1024*E keys.  Thread t owns the E consecutive keys t*E .. t*E+E-1 in
+// registers, so compare-exchange distances below E are register moves, distances below 32*E are warp shuffles,
+// and only the larger ones go through (padded, conflict-free) shared memory: 15 block-wide passes for 8192 keys
+// instead of 91.  Stages beyond next_pow2(n) only see sentinels and are skipped.
+__device__ __forceinline__ int sort_pad(int i) { return i + (i >> 4); }
+
+template <int E>
+__global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p) {
+  extern __shared__ uint64_t s_keys[];      // sort_pad(1024*E) entries
+  uint64_t* g = p.keys + (int64_t)blockIdx.x * p.Apad;
+  const int n = p.cand[blockIdx.x];
+  constexpr int N = kNmsThreads * E;
+  if (n <= 1 || n > N) return;
+  int Neff = 2;
+  while (Neff < n) Neff <<= 1;
+  const int t = threadIdx.x, lane = t & 31;
+  const int base = t * E;
+  uint64_t v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = base + e < n ? g[base + e] : kSentinel;
+
+  for (int kk = 2; kk <= Neff; kk <<= 1) {
+    int j = kk >> 1;
+    if (j >= 32 * E) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) s_keys[sort_pad(base + e)] = v[e];
+      __syncthreads();
+      for (; j >= 32 * E; j >>= 1) {
+        for (int c = t; c < N / 2; c += kNmsThreads) {
+          const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));   // c-th index with bit j clear
+          const int pi = sort_pad(i), pj = sort_pad(i | j);
+          const uint64_t a = s_keys[pi], b = s_keys[pj];
+          const bool asc = (i & kk) == 0;
+          if ((a > b) == asc) { s_keys[pi] = b; s_keys[pj] = a; }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = s_keys[sort_pad(base + e)];
+    }
+    // distances E .. 16E: the partner key sits in lane ^ (j / E)
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      if (d * E <= (kk >> 1)) {
+        const bool lower = (lane & d) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const uint64_t o = __shfl_xor_sync(0xffffffffu, v[e], d);
+          const bool asc = ((base + e) & kk) == 0;
+          const uint64_t lo = v[e] < o ? v[e] : o, hi = v[e] < o ? o : v[e];
+          v[e] = (lower == asc) ? lo : hi;
+        }
+      }
+    }
+    // distances below E: both keys are in this thread's registers
+#pragma unroll
+    for (int jj = E / 2; jj >= 1; jj >>= 1) {
+      if (jj <= (kk >> 1)) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & jj) == 0) {
+            const bool asc = ((base + e) & kk) == 0;
+            const uint64_t a = v[e], b = v[e | jj];
+            if ((a > b) == asc) { v[e] = b; v[e | jj] = a; }
+          }
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (base + e < n) g[base + e] = v[e];
 }
 
 template <int MODE>
@@ -143,79 +207,95 @@ __device__ __forceinline__ bool suppresses(const float4& a, const float4& b, flo
 struct GreedyArgs {
   const float* pred;     // xyxy already
   const uint64_t* keys;  // sorted
-  float4* sbox;          // [B][A] scratch: boxes in sorted order
+  float4* sbox;          // [B][A] scratch: boxes in sorted order (used only when an image has more than `cap` candidates)
   float* out_det;
   int32_t* out_idx;
   int32_t* out_cnt;
   int32_t* out_cand;
   const int32_t* cand;
   int B, A, Apad, nc;
+  int cap;               // candidates per image whose boxes + classes fit the shared-memory carve-out
   float thr_f;
   double thr_d;
 };
 
+// state of a sorted candidate
+constexpr uint8_t kAlive = 0, kGone = 1, kKept = 2;
+
+// exclusive rank of this thread's flag among the CTA's 1024 threads (ordered), total in `found`.
+// One barrier: every warp redoes the 32-entry scan of the warp counts itself.
+__device__ __forceinline__ int block_rank(int flag, int* s_wcnt, int& found) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_wcnt[warp] = __popc(bal);
+  __syncthreads();
+  const int c = s_wcnt[lane];
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  found = __shfl_sync(0xffffffffu, incl, 31);
+  const int wbase = __shfl_sync(0xffffffffu, incl - c, warp);
+  return wbase + __popc(bal & ((1u << lane) - 1u));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArgs p) {
-  extern __shared__ uint8_t s_removed[];  // [A]
+  // dynamic shared memory: float4 box[cap] | uint8 state[A16] | uint8 cls[cap]
+  extern __shared__ __align__(16) uint8_t g_smem[];
   __shared__ float4 c_box[kChunk];
   __shared__ int c_cls[kChunk];
   __shared__ unsigned long long c_mask[kChunk];
   __shared__ float4 k_box[kChunk];
   __shared__ int k_cls[kChunk];
-  __shared__ int s_total;
   __shared__ int c_pos[kChunk];
-  __shared__ int s_wcnt[32];
-  __shared__ int s_found, s_next;
+  __shared__ int s_wcnt[2][32];
+  __shared__ int s_next;
   __shared__ unsigned long long s_keep;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const uint64_t* keys = p.keys + (int64_t)b * p.Apad;
   const float* pred = p.pred + (int64_t)b * p.A * (4 + p.nc);
-  float4* sbox = p.sbox + (int64_t)b * p.A;
-
   const int n = p.cand[b];
-  if (tid == 0) s_total = 0;
-  __syncthreads();
+
+  // Boxes and classes of the sorted candidates live in shared memory when they fit (the common case: the round
+  // loop below is a chain of dependent steps, so its latency -- not its arithmetic -- is the cost); otherwise in
+  // the global scratch, read back through L2.
+  const bool fits = n <= p.cap;
+  float4* s_box = reinterpret_cast<float4*>(g_smem);
+  uint8_t* state = g_smem + (size_t)p.cap * 16;
+  uint8_t* s_cls = state + (size_t)((p.A + 15) / 16) * 16;
+  float4* box = fits ? s_box : p.sbox + (int64_t)b * p.A;
+
   for (int j = tid; j < n; j += kNmsThreads) {
-    const int a = (int)(keys[j] & 0xFFFFFFull);
+    const uint64_t key = keys[j];
+    const int a = (int)(key & 0xFFFFFFull);
     const float* row = pred + (int64_t)a * (4 + p.nc);
-    sbox[j] = make_float4(row[0], row[1], row[2], row[3]);
-    s_removed[j] = 0;
+    box[j] = make_float4(row[0], row[1], row[2], row[3]);
+    if (fits) s_cls[j] = (uint8_t)(key >> 56);
+    state[j] = kAlive;
   }
   __syncthreads();
 
   // Each round takes the next (up to) 64 ALIVE candidates in sorted order -- found by an ordered block-wide
   // compaction over a window of 1024 positions -- so the number of rounds scales with the candidates that
   // survive the boxes kept so far, not with the number of candidates.
-  const int warp = tid >> 5, lane = tid & 31;
-  int pos0 = 0;
+  int pos0 = 0, par = 0;
   while (pos0 < n) {
     // (1) ordered compaction of the alive positions in [pos0, pos0 + 1024)
     const int j0 = pos0 + tid;
-    const int alive = (j0 < n && !s_removed[j0]) ? 1 : 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
-    __syncthreads();
-    if (warp == 0) {   // exclusive prefix over the 32 warp counts
-      const int c = s_wcnt[lane];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      s_wcnt[lane] = incl - c;
-      if (lane == 31) s_found = incl;
-    }
-    __syncthreads();
-    const int found = s_found;
+    const int alive = (j0 < n && state[j0] == kAlive) ? 1 : 0;
+    int found;
+    const int rank = block_rank(alive, s_wcnt[par], found);
+    par ^= 1;                                            // the next scan must not overwrite counts still being read
     if (found == 0) { pos0 += kNmsThreads; continue; }   // uniform
-    const int rank = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
     if (alive && rank < kChunk) {
       c_pos[rank] = j0;
-      c_box[rank] = sbox[j0];
-      c_cls[rank] = (int)(keys[j0] >> 56);
+      c_box[rank] = box[j0];
+      c_cls[rank] = fits ? (int)s_cls[j0] : (int)(keys[j0] >> 56);
       c_mask[rank] = 0ull;
       if (rank == kChunk - 1) s_next = j0 + 1;   // the next round resumes right after the 64th alive entry
     }
@@ -240,49 +320,73 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
       }
     }
     __syncthreads();
-    // (3) serial resolution (one thread, bit tricks, shared memory only)
-    if (tid == 0) {
+    // (3) serial resolution by warp 0: the 64 masks sit in registers (two per lane) and are broadcast by
+    //     shuffles that do not depend on `keep`, so the dependent chain is one AND/OR per candidate
+    if (tid < 32) {
+      const unsigned long long m0 = c_mask[tid], m1 = c_mask[tid + 32];
       unsigned long long keep = 0ull;
-      for (int j = 0; j < cn; ++j)
-        if (!(c_mask[j] & keep)) keep |= 1ull << j;
-      s_keep = keep;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const unsigned long long mj = __shfl_sync(0xffffffffu, m0, j);
+        if (j < cn && !(mj & keep)) keep |= 1ull << j;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const unsigned long long mj = __shfl_sync(0xffffffffu, m1, j);
+        if (j + 32 < cn && !(mj & keep)) keep |= 1ull << (j + 32);
+      }
+      if (tid == 0) s_keep = keep;
     }
     __syncthreads();
     const unsigned long long keep64 = s_keep;
     const int kc = __popcll(keep64);
-    const int base = s_total;           // read before thread 0 updates it below (separated by the next barrier)
     if (tid < cn) {
-      if ((keep64 >> tid) & 1ull) {     // kept entries write themselves out in parallel, in order
+      const bool kept = (keep64 >> tid) & 1ull;
+      if (kept) {
         const int r = __popcll(keep64 & ((1ull << tid) - 1ull));
         k_box[r] = c_box[tid];
         k_cls[r] = c_cls[tid];
-        const int a = (int)(keys[c_pos[tid]] & 0xFFFFFFull);
-        const int pos = base + r;
-        float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
-        const float4 bx = c_box[tid];
-        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-        o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + c_cls[tid]];
-        o[5] = (float)c_cls[tid];
-        p.out_idx[(int64_t)b * p.A + pos] = a;
       }
-      s_removed[c_pos[tid]] = 1;        // every entry of the chunk is now decided
+      state[c_pos[tid]] = kept ? kKept : kGone;   // every entry of the chunk is now decided
     }
     __syncthreads();
-    if (tid == 0) s_total = base + kc;
     // (4) the boxes kept in this round suppress the later candidates
     for (int j = next + tid; j < n; j += kNmsThreads) {
-      if (s_removed[j]) continue;
-      const float4 bj = sbox[j];
-      const int cj = (int)(keys[j] >> 56);
+      if (state[j] != kAlive) continue;
+      const float4 bj = box[j];
+      const int cj = fits ? (int)s_cls[j] : (int)(keys[j] >> 56);
       for (int k = 0; k < kc; ++k) {
-        if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { s_removed[j] = 1; break; }
+        if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { state[j] = kGone; break; }
       }
     }
     __syncthreads();
     pos0 = next;
   }
+
+  // (5) kept candidates write themselves out, in sorted order (ordered compaction of the kKept states)
+  int total = 0;
+  for (int w0 = 0; w0 < n; w0 += kNmsThreads) {
+    const int j = w0 + tid;
+    const int kept = (j < n && state[j] == kKept) ? 1 : 0;
+    int found;
+    const int rank = block_rank(kept, s_wcnt[par], found);
+    par ^= 1;
+    if (kept) {
+      const uint64_t key = keys[j];
+      const int a = (int)(key & 0xFFFFFFull);
+      const int cls = (int)(key >> 56);
+      const int pos = total + rank;
+      float* o = p.out_det + ((int64_t)b * p.A + pos) * 6;
+      const float4 bx = box[j];
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+      o[4] = pred[(int64_t)a * (4 + p.nc) + 4 + cls];
+      o[5] = (float)cls;
+      p.out_idx[(int64_t)b * p.A + pos] = a;
+    }
+    total += found;
+  }
   if (tid == 0) {
-    p.out_cnt[b] = s_total;
+    p.out_cnt[b] = total;
     if (p.out_cand) p.out_cand[b] = n;
   }
 }
@@ -330,28 +434,51 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
   DCFA_CHECK_LAUNCH("nms_prepare_kernel");
 
   SortArgs sa{keys, cand, Apad};
-  const size_t sort_smem = (size_t)(Apad < kSmemSortMax ? Apad : kSmemSortMax) * 8;
-  static bool attr_sort = false, attr_g0 = false, attr_g1 = false;
-  if (!attr_sort) {
-    cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSortMax * 8);
-    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(sort): %s", cudaGetErrorString(e));
-    attr_sort = true;
+  {
+    // E keys per thread: the smallest of 1,2,4,8,16 with 1024*E >= min(Apad, 16384)
+    int E = 1;
+    while (E < 16 && kNmsThreads * E < Apad) E <<= 1;
+    const size_t sort_smem = (size_t)(kNmsThreads * E + kNmsThreads * E / 16) * 8;
+    static bool attr_sort = false;
+    if (!attr_sort) {
+      cudaError_t e1 = cudaFuncSetAttribute(nms_sort_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 8 * 8 / 16);
+      cudaError_t e2 = cudaFuncSetAttribute(nms_sort_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 16 * 8 / 16);
+      if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(sort): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      attr_sort = true;
+    }
+    switch (E) {
+      case 1: nms_sort_kernel<1><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
+      case 2: nms_sort_kernel<2><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
+      case 4: nms_sort_kernel<4><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
+      case 8: nms_sort_kernel<8><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
+      default: nms_sort_kernel<16><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
+    }
+    DCFA_CHECK_LAUNCH("nms_sort_kernel");
+    if (Apad > kSmemSortMax) {
+      nms_sort_global_kernel<<<(unsigned)B, kNmsThreads, 0, st>>>(sa);
+      DCFA_CHECK_LAUNCH("nms_sort_global_kernel");
+    }
   }
-  nms_sort_kernel<<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa);
-  DCFA_CHECK_LAUNCH("nms_sort_kernel");
 
-  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, (float)nms_thres, nms_thres};
-  const size_t g_smem = (size_t)((A + 15) / 16) * 16;
+  // shared-memory carve-out of the greedy kernel: state[A16] + 17 bytes per resident candidate
+  const int A16 = (A + 15) / 16 * 16;
+  const int kGreedySmemMax = 200 * 1024;
+  int cap = (kGreedySmemMax - A16) / 17;
+  cap = cap >= A16 ? A16 : cap / 16 * 16;
+  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, cap, (float)nms_thres, nms_thres};
+  const size_t g_smem = (size_t)A16 + (size_t)cap * 17;
+  static bool attr_g0 = false, attr_g1 = false;
   if (iou_mode == DCFA_IOU_TV_CUDA) {
     if (!attr_g1) {
-      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16);
+      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
       if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
       attr_g1 = true;
     }
     nms_greedy_kernel<DCFA_IOU_TV_CUDA><<<(unsigned)B, kNmsThreads, g_smem, st>>>(ga);
   } else {
     if (!attr_g0) {
-      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16);
+      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
       if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
       attr_g0 = true;
     }

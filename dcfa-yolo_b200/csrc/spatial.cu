@@ -4,6 +4,8 @@
 //   (nets/yolo_mul.py:426, :433), optionally summing two inputs first (feat3_rgb + feat3_nir, :421) and
 //   writing straight into a channel slot of the BiFPN concat buffer (:428, :435).
 // Both are bandwidth-bound gathers on bf16 NHWC with 128-bit channel vectors.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dcfa {
@@ -13,36 +15,60 @@ struct PoolArgs5 {
   View<const __nv_bfloat16> x;
   View<__nv_bfloat16> y;
   int n_img, H, W, C;
-  int64_t total;
+  int strip;  // output rows per thread
 };
 
+struct Max8 {
+  __nv_bfloat162 m[4];
+  __device__ __forceinline__ void fill(float v) { m[0] = m[1] = m[2] = m[3] = __float2bfloat162_rn(v); }
+  __device__ __forceinline__ void take(const uint4& v) {
+    m[0] = __hmax2(m[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    m[1] = __hmax2(m[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    m[2] = __hmax2(m[2], *reinterpret_cast<const __nv_bfloat162*>(&v.z));
+    m[3] = __hmax2(m[3], *reinterpret_cast<const __nv_bfloat162*>(&v.w));
+  }
+  __device__ __forceinline__ void take(const Max8& o) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], o.m[i]);
+  }
+};
+
+// Separable 5x5 max: a thread owns one (column, 8-channel chunk) and walks down a strip of rows keeping the
+// horizontal 5-max of the last five input rows in registers -- 5 loads per input row instead of 25 per output.
+// grid = (ceil(W * C/8 / 256), strips, images)
 __global__ void __launch_bounds__(256) maxpool5_kernel(const PoolArgs5 p) {
   const int c8n = p.C >> 3;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
-    const int c8 = (int)(t % c8n); t /= c8n;
-    const int x = (int)(t % p.W); t /= p.W;
-    const int y = (int)(t % p.H);
-    const int n = (int)(t / p.H);
-    const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + c8 * 8;
-    const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
-    __nv_bfloat162 m[4] = {ninf, ninf, ninf, ninf};
-    const int y_lo = max(y - 2, 0), y_hi = min(y + 2, p.H - 1);
-    const int x_lo = max(x - 2, 0), x_hi = min(x + 2, p.W - 1);
-    for (int iy = y_lo; iy <= y_hi; ++iy)
-      for (int ix = x_lo; ix <= x_hi; ++ix) {
-        const uint4 v = ldg128(xin + (int64_t)(iy * p.W + ix) * p.x.ld);
-        m[0] = __hmax2(m[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x));
-        m[1] = __hmax2(m[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y));
-        m[2] = __hmax2(m[2], *reinterpret_cast<const __nv_bfloat162*>(&v.z));
-        m[3] = __hmax2(m[3], *reinterpret_cast<const __nv_bfloat162*>(&v.w));
-      }
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&m[0]);
-    o.y = *reinterpret_cast<uint32_t*>(&m[1]);
-    o.z = *reinterpret_cast<uint32_t*>(&m[2]);
-    o.w = *reinterpret_cast<uint32_t*>(&m[3]);
-    stg128(p.y.p + p.y.img_off(n) + (int64_t)(y * p.W + x) * p.y.ld + c8 * 8, o);
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.W * c8n) return;
+  const int x = idx / c8n, c8 = idx - x * c8n;
+  const int n = blockIdx.z;
+  const int ys = blockIdx.y * p.strip, ye = min(p.H, ys + p.strip);
+  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + c8 * 8;
+  __nv_bfloat16* yout = p.y.p + p.y.img_off(n) + c8 * 8;
+  const int x_lo = max(x - 2, 0), x_hi = min(x + 2, p.W - 1);
+  Max8 w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i].fill(-INFINITY);
+  for (int iy = ys - 2; iy < ye + 2; ++iy) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = w[i + 1];
+    w[4].fill(-INFINITY);
+    if (iy >= 0 && iy < p.H) {
+      const __nv_bfloat16* row = xin + (int64_t)iy * p.W * p.x.ld;
+      for (int ix = x_lo; ix <= x_hi; ++ix) w[4].take(ldg128(row + (int64_t)ix * p.x.ld));
+    }
+    const int oy = iy - 2;
+    if (oy >= ys) {
+      Max8 o = w[0];
+#pragma unroll
+      for (int i = 1; i < 5; ++i) o.take(w[i]);
+      uint4 v;
+      v.x = *reinterpret_cast<uint32_t*>(&o.m[0]);
+      v.y = *reinterpret_cast<uint32_t*>(&o.m[1]);
+      v.z = *reinterpret_cast<uint32_t*>(&o.m[2]);
+      v.w = *reinterpret_cast<uint32_t*>(&o.m[3]);
+      stg128(yout + (int64_t)(oy * p.W + x) * p.y.ld, v);
+    }
   }
 }
 
@@ -52,45 +78,46 @@ struct UpArgs {
   View<__nv_bfloat16> y;
   int n_img, Hi, Wi, Ho, Wo, C;
   float sy, sx;  // (in-1)/(out-1)
-  int64_t total;
 };
 
-__device__ __forceinline__ void load_sum8(const UpArgs& p, int64_t offa, int64_t offb, float* v) {
-  unpack8(ldg128(p.a.p + offa), v);
-  if (p.b.p) {
+template <bool TWO>
+__device__ __forceinline__ void load_sum8(const __nv_bfloat16* a, const __nv_bfloat16* b, float* v) {
+  unpack8(ldg128(a), v);
+  if (TWO) {
     float w[8];
-    unpack8(ldg128(p.b.p + offb), w);
+    unpack8(ldg128(b), w);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] += w[e];
   }
 }
 
+// grid = (ceil(Wo * C/8 / 256), Ho, images): the row terms are per-CTA constants, the column terms cost one
+// 32-bit division per thread.
+template <bool TWO>
 __global__ void __launch_bounds__(256) upsample_kernel(const UpArgs p) {
   const int c8n = p.C >> 3;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
-    const int c8 = (int)(t % c8n); t /= c8n;
-    const int ox = (int)(t % p.Wo); t /= p.Wo;
-    const int oy = (int)(t % p.Ho);
-    const int n = (int)(t / p.Ho);
-    // ATen upsample_bilinear2d, align_corners=True: src = scale * dst, scale = (in-1)/(out-1)
-    const float fy = p.sy * (float)oy, fx = p.sx * (float)ox;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.0f - ly, hx = 1.0f - lx;
-    const int64_t ba = p.a.img_off(n) + c8 * 8;
-    const int64_t bb = p.b.p ? p.b.img_off(n) + c8 * 8 : 0;
-    float v00[8], v01[8], v10[8], v11[8];
-    load_sum8(p, ba + (int64_t)(y0 * p.Wi + x0) * p.a.ld, bb + (int64_t)(y0 * p.Wi + x0) * p.b.ld, v00);
-    load_sum8(p, ba + (int64_t)(y0 * p.Wi + x1) * p.a.ld, bb + (int64_t)(y0 * p.Wi + x1) * p.b.ld, v01);
-    load_sum8(p, ba + (int64_t)(y1 * p.Wi + x0) * p.a.ld, bb + (int64_t)(y1 * p.Wi + x0) * p.b.ld, v10);
-    load_sum8(p, ba + (int64_t)(y1 * p.Wi + x1) * p.a.ld, bb + (int64_t)(y1 * p.Wi + x1) * p.b.ld, v11);
-    float o[8];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.Wo * c8n) return;
+  const int ox = idx / c8n, c8 = idx - ox * c8n;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  // ATen upsample_bilinear2d, align_corners=True: src = scale * dst, scale = (in-1)/(out-1)
+  const float fy = p.sy * (float)oy, fx = p.sx * (float)ox;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  const __nv_bfloat16* pa = p.a.p + p.a.img_off(n) + c8 * 8;
+  const __nv_bfloat16* pb = TWO ? p.b.p + p.b.img_off(n) + c8 * 8 : nullptr;
+  const int i00 = y0 * p.Wi + x0, i01 = y0 * p.Wi + x1, i10 = y1 * p.Wi + x0, i11 = y1 * p.Wi + x1;
+  float v00[8], v01[8], v10[8], v11[8];
+  load_sum8<TWO>(pa + (int64_t)i00 * p.a.ld, pb + (int64_t)i00 * p.b.ld, v00);
+  load_sum8<TWO>(pa + (int64_t)i01 * p.a.ld, pb + (int64_t)i01 * p.b.ld, v01);
+  load_sum8<TWO>(pa + (int64_t)i10 * p.a.ld, pb + (int64_t)i10 * p.b.ld, v10);
+  load_sum8<TWO>(pa + (int64_t)i11 * p.a.ld, pb + (int64_t)i11 * p.b.ld, v11);
+  float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
-    stg128(p.y.p + p.y.img_off(n) + (int64_t)(oy * p.Wo + ox) * p.y.ld + c8 * 8, pack8(o));
-  }
+  for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+  stg128(p.y.p + p.y.img_off(n) + (int64_t)(oy * p.Wo + ox) * p.y.ld + c8 * 8, pack8(o));
 }
 
 inline bool aligned(const void* ptr, int ld, int64_t img_stride, int64_t gstride) {
@@ -108,11 +135,14 @@ int launch_maxpool5(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(a.C > 0 && a.C % 8 == 0, "maxpool5: C %d unsupported", a.C);
   DCFA_REQUIRE(aligned(a.x.p, a.x.ld, a.x.img_stride, a.x.gstride) && aligned(a.y.p, a.y.ld, a.y.img_stride, a.y.gstride),
                "maxpool5: views must be 16-byte aligned");
-  a.total = (int64_t)a.n_img * a.H * a.W * (a.C >> 3);
-  int64_t blocks = (a.total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  maxpool5_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DCFA_REQUIRE(a.n_img <= 65535, "maxpool5: n_img %d too large", a.n_img);
+  // strips tall enough to amortise the 4 halo rows, short enough to fill the SMs
+  const int bx = ceil_div(a.W * (a.C >> 3), 256);
+  int strips = ceil_div(sm_count() * 4, bx * a.n_img);
+  strips = std::max(1, std::min(strips, ceil_div(a.H, 4)));
+  a.strip = ceil_div(a.H, strips);
+  strips = ceil_div(a.H, a.strip);
+  maxpool5_kernel<<<dim3((unsigned)bx, (unsigned)strips, (unsigned)a.n_img), 256, 0, st>>>(a);
   DCFA_CHECK_LAUNCH("maxpool5_kernel");
   return DCFA_OK;
 }
@@ -131,11 +161,10 @@ int launch_upsample(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
                "upsample: views must be 16-byte aligned");
   a.sy = a.Ho > 1 ? (float)(a.Hi - 1) / (float)(a.Ho - 1) : 0.0f;
   a.sx = a.Wo > 1 ? (float)(a.Wi - 1) / (float)(a.Wo - 1) : 0.0f;
-  a.total = (int64_t)a.n_img * a.Ho * a.Wo * (a.C >> 3);
-  int64_t blocks = (a.total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  upsample_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DCFA_REQUIRE(a.n_img <= 65535 && a.Ho <= 65535, "upsample: grid too large");
+  const dim3 grid((unsigned)ceil_div(a.Wo * (a.C >> 3), 256), (unsigned)a.Ho, (unsigned)a.n_img);
+  if (a.b.p) upsample_kernel<true><<<grid, 256, 0, st>>>(a);
+  else upsample_kernel<false><<<grid, 256, 0, st>>>(a);
   DCFA_CHECK_LAUNCH("upsample_kernel");
   return DCFA_OK;
 }

@@ -83,7 +83,11 @@ CASES = [
     (2, 500, 2, "degenerate", 0.5, 0.4),
     (1, 1, 1, "random", 0.0, 0.5),
     (2, 37, 1, "random", 2.0, 0.5),       # nothing passes the confidence filter
-    (1, 20000, 1, "random", 0.9, 0.5),    # > 16384 keys: global-memory sort path
+    (1, 20000, 1, "random", 0.9, 0.5),    # 16 keys per thread in the register/shuffle sort
+    (1, 33600, 1, "random", 0.99, 0.5),   # 1280x1280 anchors, few candidates: shared-memory boxes with cap < A
+    (1, 33600, 1, "random", 0.05, 0.6),   # > 16384 candidates: global-memory sort + global-scratch greedy paths
+    (2, 1500, 2, "random", 0.2, 0.5),     # 2 keys per thread
+    (1, 4000, 1, "clustered", 0.125, 0.5),  # 4 keys per thread, many score ties
 ]
 
 

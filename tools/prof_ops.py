@@ -37,6 +37,7 @@ def main():
     torch.cuda.synchronize()
     st = torch.cuda.current_stream(dev)
     want = a.ops.split(",")
+    torch.cuda.profiler.start()   # ncu --profile-from-start off: only the selected ops are captured
     for name in want:
         idx = [i for i, n in enumerate(eng.plan.op_names) if n == name]
         if not idx:
@@ -53,6 +54,7 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         print("%-16s %s ms" % (name, ["%.4f" % t for t in ts]))
+    torch.cuda.profiler.stop()
 
 
 if __name__ == "__main__":
