@@ -93,9 +93,16 @@ __global__ void __launch_bounds__(256) cbam_mlp_kernel(const MlpArgs p) {
   const int g = n / p.group_imgs;
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     float ss = 0.0f, mm = -INFINITY;
-    for (int q = 0; q < p.parts; ++q) {
-      ss += p.psum[((int64_t)n * p.parts + q) * p.C + c];
-      mm = fmaxf(mm, p.pmax[((int64_t)n * p.parts + q) * p.C + c]);
+    const float* ps = p.psum + (int64_t)n * p.parts * p.C + c;
+    const float* pm = p.pmax + (int64_t)n * p.parts * p.C + c;
+    for (int q0 = 0; q0 < p.parts; q0 += 8) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (q0 + u < p.parts) { a[u] = __ldg(ps + (int64_t)(q0 + u) * p.C); b[u] = __ldg(pm + (int64_t)(q0 + u) * p.C); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (q0 + u < p.parts) { ss += a[u]; mm = fmaxf(mm, b[u]); }
     }
     s_avg[c] = ss * p.inv_hw;
     s_max[c] = mm;
@@ -105,10 +112,17 @@ __global__ void __launch_bounds__(256) cbam_mlp_kernel(const MlpArgs p) {
   for (int h = warp; h < p.hidden; h += nwarps) {
     const float* w1 = p.fc1 + ((int64_t)g * p.hidden + h) * p.C;
     float da = 0.0f, dm = 0.0f;
-    for (int c = lane; c < p.C; c += 32) {
-      const float w = __ldg(w1 + c);
-      da = fmaf(w, s_avg[c], da);
-      dm = fmaf(w, s_max[c], dm);
+    for (int c0 = lane; c0 < p.C; c0 += 32 * 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u * 32 < p.C) w[u] = __ldg(w1 + c0 + u * 32);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u * 32 < p.C) {
+          da = fmaf(w[u], s_avg[c0 + u * 32], da);
+          dm = fmaf(w[u], s_max[c0 + u * 32], dm);
+        }
     }
     da = warp_sum(da);
     dm = warp_sum(dm);
@@ -119,7 +133,24 @@ __global__ void __launch_bounds__(256) cbam_mlp_kernel(const MlpArgs p) {
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     const float* w2 = p.fc2 + ((int64_t)g * p.C + c) * p.hidden;
     float o = 0.0f;
-    for (int h = 0; h < p.hidden; ++h) o = fmaf(__ldg(w2 + h), s_hid[h], o);
+    if ((p.hidden & 3) == 0 && ((uintptr_t)p.fc2 & 15) == 0) {
+      // the row is read as independent 128-bit loads (one L2 round trip, not `hidden` of them); same add order
+      const float4* w4 = reinterpret_cast<const float4*>(w2);
+      for (int h0 = 0; h0 < p.hidden; h0 += 16) {
+        float4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (h0 + u * 4 < p.hidden) r[u] = __ldg(w4 + (h0 >> 2) + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (h0 + u * 4 < p.hidden) {
+            const float* sh = s_hid + h0 + u * 4;
+            o = fmaf(r[u].x, sh[0], o); o = fmaf(r[u].y, sh[1], o); o = fmaf(r[u].z, sh[2], o); o = fmaf(r[u].w, sh[3], o);
+          }
+      }
+    } else {
+      for (int h = 0; h < p.hidden; ++h) o = fmaf(__ldg(w2 + h), s_hid[h], o);
+    }
     p.gate[(int64_t)n * p.C + c] = 1.0f / (1.0f + expf(-o));
   }
 }

@@ -17,7 +17,14 @@
 //   DCFA_IOU_TV_CUDA  Sa + Sb evaluated as fma(wb, hb, Sa), iou > (float)thr (SASS of torchvision 0.26.0+cu128
 //                     nms_kernel_impl<float> for sm_100: FMUL, FFMA, FADD, IEEE divide, FSETP.GT on F2F.F32.F64(thr))
 // All box arithmetic uses _rn intrinsics so nvcc cannot contract anything else.
+#include <cooperative_groups.h>
+#include <cstdio>
+
+#include <algorithm>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dcfa {
 namespace {
@@ -108,45 +115,61 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sort_global_kernel(const Sort
   }
 }
 
-// One CTA per image, bitonic sort of up to 1024*E keys.  Thread t owns the E consecutive keys t*E .. t*E+E-1 in
-// registers, so compare-exchange distances below E are register moves, distances below 32*E are warp shuffles,
-// and only the larger ones go through (padded, conflict-free) shared memory: 15 block-wide passes for 8192 keys
-// instead of 91.  Stages beyond next_pow2(n) only see sentinels and are skipped.
+// Cluster-wide bitonic sort of up to CS * 1024 * E keys (CS = CTAs of the image's cluster).  CTA `rank` owns the
+// keys [rank * 1024E, (rank + 1) * 1024E); thread t owns E consecutive ones in registers.  Compare-exchange
+// distances below E are register moves, below 32E warp shuffles, below 1024E passes over the CTA's (padded,
+// conflict-free) shared memory, and the remaining log2(CS) distances read the partner CTA's shared memory
+// through DSMEM -- each side keeps its min or max, so nothing is written remotely.
+// Stages beyond next_pow2(n) only see sentinels and are skipped.
 __device__ __forceinline__ int sort_pad(int i) { return i + (i >> 4); }
 
 template <int E>
-__global__ void __launch_bounds__(kNmsThreads) nms_sort_kernel(const SortArgs p) {
-  extern __shared__ uint64_t s_keys[];      // sort_pad(1024*E) entries
-  uint64_t* g = p.keys + (int64_t)blockIdx.x * p.Apad;
-  const int n = p.cand[blockIdx.x];
-  constexpr int N = kNmsThreads * E;
-  if (n <= 1 || n > N) return;
+__device__ __forceinline__ void cluster_sort(uint64_t* g, int n, uint64_t* s_keys, cg::cluster_group& cluster) {
+  constexpr int Nloc = kNmsThreads * E;
+  const int rank = (int)cluster.block_rank();
   int Neff = 2;
   while (Neff < n) Neff <<= 1;
   const int t = threadIdx.x, lane = t & 31;
-  const int base = t * E;
+  const int lbase = t * E;                  // index inside the CTA
+  const int base = rank * Nloc + lbase;     // index inside the image
   uint64_t v[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) v[e] = base + e < n ? g[base + e] : kSentinel;
 
   for (int kk = 2; kk <= Neff; kk <<= 1) {
     int j = kk >> 1;
+    for (; j >= Nloc; j >>= 1) {            // partner key lives in CTA rank ^ (j / Nloc), same local index
+#pragma unroll
+      for (int e = 0; e < E; ++e) s_keys[sort_pad(lbase + e)] = v[e];
+      cluster.sync();
+      const int d = j / Nloc;
+      const uint64_t* remote = cluster.map_shared_rank(s_keys, rank ^ d);
+      const bool lower = (rank & d) == 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint64_t o = remote[sort_pad(lbase + e)];
+        const bool asc = ((base + e) & kk) == 0;
+        const uint64_t lo = v[e] < o ? v[e] : o, hi = v[e] < o ? o : v[e];
+        v[e] = (lower == asc) ? lo : hi;
+      }
+      cluster.sync();                        // the partner has read before anybody overwrites
+    }
     if (j >= 32 * E) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) s_keys[sort_pad(base + e)] = v[e];
+      for (int e = 0; e < E; ++e) s_keys[sort_pad(lbase + e)] = v[e];
       __syncthreads();
       for (; j >= 32 * E; j >>= 1) {
-        for (int c = t; c < N / 2; c += kNmsThreads) {
-          const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));   // c-th index with bit j clear
+        for (int c = t; c < Nloc / 2; c += kNmsThreads) {
+          const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));   // c-th local index with bit j clear
           const int pi = sort_pad(i), pj = sort_pad(i | j);
           const uint64_t a = s_keys[pi], b = s_keys[pj];
-          const bool asc = (i & kk) == 0;
+          const bool asc = ((rank * Nloc + i) & kk) == 0;
           if ((a > b) == asc) { s_keys[pi] = b; s_keys[pj] = a; }
         }
         __syncthreads();
       }
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = s_keys[sort_pad(base + e)];
+      for (int e = 0; e < E; ++e) v[e] = s_keys[sort_pad(lbase + e)];
     }
     // distances E .. 16E: the partner key sits in lane ^ (j / E)
 #pragma unroll
@@ -206,7 +229,7 @@ __device__ __forceinline__ bool suppresses(const float4& a, const float4& b, flo
 
 struct GreedyArgs {
   const float* pred;     // xyxy already
-  const uint64_t* keys;  // sorted
+  uint64_t* keys;        // [B][Apad] compacted candidate keys, sorted in place
   float4* sbox;          // [B][A] scratch: boxes in sorted order (used only when an image has more than `cap` candidates)
   float* out_det;
   int32_t* out_idx;
@@ -218,6 +241,14 @@ struct GreedyArgs {
   float thr_f;
   double thr_d;
 };
+
+#ifdef DCFA_NMS_TIMING
+#define NT_DECL long long nt_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long nt_last = clock64(); int nt_rounds = 0;
+#define NT(i) { const long long nt_now = clock64(); nt_t[i] += nt_now - nt_last; nt_last = nt_now; }
+#else
+#define NT_DECL
+#define NT(i)
+#endif
 
 // state of a sorted candidate
 constexpr uint8_t kAlive = 0, kGone = 1, kKept = 2;
@@ -241,9 +272,21 @@ __device__ __forceinline__ int block_rank(int flag, int* s_wcnt, int& found) {
   return wbase + __popc(bal & ((1u << lane) - 1u));
 }
 
+// One cluster of CS CTAs per image: sort, then the greedy rounds.
+//
+// Every CTA holds the whole image's sorted boxes, classes and alive/gone/kept states, and runs steps (1)-(3) of a
+// round redundantly (identical inputs, identical results, no communication).  Only step (4) -- the kept boxes of
+// the round against every later candidate, the bulk of the arithmetic -- is split: CTA r tests the positions
+// next + r*1024 + tid (+ CS*1024 ...) and stores each "gone" into the state array of EVERY CTA through DSMEM;
+// one cluster barrier closes the round.
+// A CTA that has passed the barrier may start storing round k+1's "gone" marks while a slower CTA still scans the
+// window of round k+1 in step (1): those marks only touch positions behind the 64th alive entry of the window
+// (or behind the window when it holds fewer than 64), so the chunk, `next` and `found >= 64` come out the same
+// in every CTA.
 template <int MODE>
-__global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArgs p) {
-  // dynamic shared memory: float4 box[cap] | uint8 state[A16] | uint8 cls[cap]
+__global__ void __launch_bounds__(kNmsThreads) nms_cluster_kernel(const GreedyArgs p) {
+  // dynamic shared memory, greedy phase: float4 box[cap] | uint8 state[A16] | uint8 cls[cap]
+  //                        sort phase  : uint64 keys[sort_pad(1024 * E)]
   extern __shared__ __align__(16) uint8_t g_smem[];
   __shared__ float4 c_box[kChunk];
   __shared__ int c_cls[kChunk];
@@ -255,15 +298,33 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   __shared__ int s_next;
   __shared__ unsigned long long s_keep;
 
-  const int b = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
   const int tid = threadIdx.x;
-  const uint64_t* keys = p.keys + (int64_t)b * p.Apad;
+  uint64_t* keys = p.keys + (int64_t)b * p.Apad;
   const float* pred = p.pred + (int64_t)b * p.A * (4 + p.nc);
   const int n = p.cand[b];
+  NT_DECL
 
-  // Boxes and classes of the sorted candidates live in shared memory when they fit (the common case: the round
-  // loop below is a chain of dependent steps, so its latency -- not its arithmetic -- is the cost); otherwise in
-  // the global scratch, read back through L2.
+  // ---- sort (images with more than 16384 candidates were sorted by nms_sort_global_kernel)
+  if (n > 1 && n <= kSmemSortMax) {
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(g_smem);
+    const int per_cta = (n + CS - 1) / CS;
+    if (per_cta <= 1024) cluster_sort<1>(keys, n, s_keys, cluster);
+    else if (per_cta <= 2048) cluster_sort<2>(keys, n, s_keys, cluster);
+    else if (per_cta <= 4096) cluster_sort<4>(keys, n, s_keys, cluster);
+    else if (per_cta <= 8192) cluster_sort<8>(keys, n, s_keys, cluster);
+    else cluster_sort<16>(keys, n, s_keys, cluster);
+    __threadfence();
+    cluster.sync();   // every CTA's slice of the sorted keys is in global memory; the sort buffer is free
+  }
+
+  NT(0)
+  // ---- greedy rounds
+  // Boxes and classes of the sorted candidates live in shared memory when they fit (the round loop is a chain of
+  // dependent steps: its latency is the cost); otherwise in the global scratch, read back through L2.
   const bool fits = n <= p.cap;
   float4* s_box = reinterpret_cast<float4*>(g_smem);
   uint8_t* state = g_smem + (size_t)p.cap * 16;
@@ -271,15 +332,18 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
   float4* box = fits ? s_box : p.sbox + (int64_t)b * p.A;
 
   for (int j = tid; j < n; j += kNmsThreads) {
-    const uint64_t key = keys[j];
+    const uint64_t key = __ldcg(keys + j);
     const int a = (int)(key & 0xFFFFFFull);
     const float* row = pred + (int64_t)a * (4 + p.nc);
-    box[j] = make_float4(row[0], row[1], row[2], row[3]);
-    if (fits) s_cls[j] = (uint8_t)(key >> 56);
+    const float4 bx = make_float4(row[0], row[1], row[2], row[3]);
+    if (fits) { s_box[j] = bx; s_cls[j] = (uint8_t)(key >> 56); }
+    else if (crank == 0) box[j] = bx;     // one writer for the shared global scratch
     state[j] = kAlive;
   }
-  __syncthreads();
+  if (!fits) __threadfence();
+  cluster.sync();     // also: nobody stores a remote "gone" before every CTA has initialised its states
 
+  NT(1)
   // Each round takes the next (up to) 64 ALIVE candidates in sorted order -- found by an ordered block-wide
   // compaction over a window of 1024 positions -- so the number of rounds scales with the candidates that
   // survive the boxes kept so far, not with the number of candidates.
@@ -291,49 +355,61 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
     int found;
     const int rank = block_rank(alive, s_wcnt[par], found);
     par ^= 1;                                            // the next scan must not overwrite counts still being read
-    if (found == 0) { pos0 += kNmsThreads; continue; }   // uniform
+    if (found == 0) { pos0 += kNmsThreads; continue; }   // uniform over the cluster
     if (alive && rank < kChunk) {
       c_pos[rank] = j0;
       c_box[rank] = box[j0];
-      c_cls[rank] = fits ? (int)s_cls[j0] : (int)(keys[j0] >> 56);
-      c_mask[rank] = 0ull;
+      c_cls[rank] = fits ? (int)s_cls[j0] : (int)(__ldcg(keys + j0) >> 56);
       if (rank == kChunk - 1) s_next = j0 + 1;   // the next round resumes right after the 64th alive entry
     }
     if (tid == 0 && found < kChunk) s_next = pos0 + kNmsThreads;
     __syncthreads();
     const int cn = min(found, kChunk);
     const int next = s_next;
-    // (2) suppression bits inside the chunk, 4 pairs per thread: bit i of c_mask[j] <=> box i suppresses box j
+    NT(2)
+    // (2) suppression bits inside the chunk: bit i of c_mask[j] <=> box i (< j) suppresses box j.  The 2016
+    //     pairs are spread evenly by folding the triangle: warp w owns rows w and 63 - w (63 pairs, two per lane);
+    //     the lanes' bits are OR-reduced with redux.sync, so every row is written exactly once, without atomics.
     {
-      const int j = tid >> 4;           // 0..63
-      const int i0 = (tid & 15) << 2;   // 0,4,..,60
-      if (j < cn) {
-        unsigned long long bits = 0ull;
-        const float4 bj = c_box[j];
-        const int cj = c_cls[j];
+      const int w = tid >> 5, lane = tid & 31;
+      unsigned a_lo = 0u, a_hi = 0u, b_lo = 0u, b_hi = 0u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = i0 + q;
-          if (i < j && c_cls[i] == cj && suppresses<MODE>(c_box[i], bj, p.thr_f, p.thr_d)) bits |= 1ull << i;
+      for (int q = 0; q < 2; ++q) {
+        const int k = lane + 32 * q;
+        if (k < 63) {
+          const bool first = k < w;
+          const int j = first ? w : 63 - w;
+          const int i = first ? k : k - w;
+          if (j < cn && c_cls[i] == c_cls[j] && suppresses<MODE>(c_box[i], c_box[j], p.thr_f, p.thr_d)) {
+            const unsigned bit = 1u << (i & 31);
+            if (first) { if (i < 32) a_lo |= bit; else a_hi |= bit; }
+            else { if (i < 32) b_lo |= bit; else b_hi |= bit; }
+          }
         }
-        if (bits) atomicOr(&c_mask[j], bits);
+      }
+      a_lo = __reduce_or_sync(0xffffffffu, a_lo); a_hi = __reduce_or_sync(0xffffffffu, a_hi);
+      b_lo = __reduce_or_sync(0xffffffffu, b_lo); b_hi = __reduce_or_sync(0xffffffffu, b_hi);
+      if (lane == 0) {
+        c_mask[w] = ((unsigned long long)a_hi << 32) | a_lo;
+        c_mask[63 - w] = ((unsigned long long)b_hi << 32) | b_lo;
       }
     }
     __syncthreads();
-    // (3) serial resolution by warp 0: the 64 masks sit in registers (two per lane) and are broadcast by
-    //     shuffles that do not depend on `keep`, so the dependent chain is one AND/OR per candidate
+    NT(3)
+    // (3) resolution by warp 0, lane l holding candidates l and l + 32: a candidate is dead once a kept box
+    //     suppresses it and kept once all its suppressors are dead; every pass decides at least the first
+    //     undecided candidate, in practice a handful of passes decide all 64.
     if (tid < 32) {
-      const unsigned long long m0 = c_mask[tid], m1 = c_mask[tid + 32];
-      unsigned long long keep = 0ull;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const unsigned long long mj = __shfl_sync(0xffffffffu, m0, j);
-        if (j < cn && !(mj & keep)) keep |= 1ull << j;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const unsigned long long mj = __shfl_sync(0xffffffffu, m1, j);
-        if (j + 32 < cn && !(mj & keep)) keep |= 1ull << (j + 32);
+      const unsigned long long mA = c_mask[tid], mB = c_mask[tid + 32];
+      bool uA = tid < cn, uB = tid + 32 < cn;
+      unsigned long long keep = 0ull, dead = 0ull;
+      while (__any_sync(0xffffffffu, uA || uB)) {
+        const bool dA = uA && (mA & keep) != 0ull, dB = uB && (mB & keep) != 0ull;
+        const bool kA = uA && !dA && (mA & ~dead) == 0ull, kB = uB && !dB && (mB & ~dead) == 0ull;
+        keep |= (unsigned long long)__ballot_sync(0xffffffffu, kA) | ((unsigned long long)__ballot_sync(0xffffffffu, kB) << 32);
+        dead |= (unsigned long long)__ballot_sync(0xffffffffu, dA) | ((unsigned long long)__ballot_sync(0xffffffffu, dB) << 32);
+        uA = uA && !dA && !kA;
+        uB = uB && !dB && !kB;
       }
       if (tid == 0) s_keep = keep;
     }
@@ -347,21 +423,37 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
         k_box[r] = c_box[tid];
         k_cls[r] = c_cls[tid];
       }
-      state[c_pos[tid]] = kept ? kKept : kGone;   // every entry of the chunk is now decided
+      state[c_pos[tid]] = kept ? kKept : kGone;   // every entry of the chunk is now decided (same in every CTA)
     }
     __syncthreads();
-    // (4) the boxes kept in this round suppress the later candidates
-    for (int j = next + tid; j < n; j += kNmsThreads) {
+    NT(4)
+    // (4) the boxes kept in this round suppress the later candidates; this CTA's share of the positions
+    //     (warp-interleaved, so that every CTA sees the same mix of early and late positions)
+    for (int j = next + ((tid >> 5) * CS + crank) * 32 + (tid & 31); j < n; j += CS * kNmsThreads) {
       if (state[j] != kAlive) continue;
       const float4 bj = box[j];
-      const int cj = fits ? (int)s_cls[j] : (int)(keys[j] >> 56);
+      const int cj = fits ? (int)s_cls[j] : (int)(__ldcg(keys + j) >> 56);
       for (int k = 0; k < kc; ++k) {
-        if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) { state[j] = kGone; break; }
+        if (k_cls[k] == cj && suppresses<MODE>(k_box[k], bj, p.thr_f, p.thr_d)) {
+          for (int r = 0; r < CS; ++r) cluster.map_shared_rank(state, r)[j] = kGone;
+          break;
+        }
       }
     }
-    __syncthreads();
+    NT(5)
+    cluster.sync();
+    NT(6)
     pos0 = next;
+#ifdef DCFA_NMS_TIMING
+    ++nt_rounds;
+#endif
   }
+#ifdef DCFA_NMS_TIMING
+  if (b == 0 && (tid == 0 || tid == 1023))
+    printf("nms timing cta %d tid %d rounds %d: sort %lld init %lld | step1 %lld step2 %lld step3 %lld step4 %lld csync %lld\n", crank, tid,
+           nt_rounds, nt_t[0], nt_t[1], nt_t[2], nt_t[3], nt_t[4], nt_t[5], nt_t[6]);
+#endif
+  if (crank != 0) return;
 
   // (5) kept candidates write themselves out, in sorted order (ordered compaction of the kKept states)
   int total = 0;
@@ -372,7 +464,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const GreedyArg
     const int rank = block_rank(kept, s_wcnt[par], found);
     par ^= 1;
     if (kept) {
-      const uint64_t key = keys[j];
+      const uint64_t key = __ldcg(keys + j);
       const int a = (int)(key & 0xFFFFFFull);
       const int cls = (int)(key >> 56);
       const int pos = total + rank;
@@ -433,57 +525,52 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
   nms_prepare_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pa);
   DCFA_CHECK_LAUNCH("nms_prepare_kernel");
 
-  SortArgs sa{keys, cand, Apad};
-  {
-    // E keys per thread: the smallest of 1,2,4,8,16 with 1024*E >= min(Apad, 16384)
-    int E = 1;
-    while (E < 16 && kNmsThreads * E < Apad) E <<= 1;
-    const size_t sort_smem = (size_t)(kNmsThreads * E + kNmsThreads * E / 16) * 8;
-    static bool attr_sort = false;
-    if (!attr_sort) {
-      cudaError_t e1 = cudaFuncSetAttribute(nms_sort_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 8 * 8 / 16);
-      cudaError_t e2 = cudaFuncSetAttribute(nms_sort_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 16 * 8 / 16);
-      if (e1 != cudaSuccess || e2 != cudaSuccess)
-        return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(sort): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-      attr_sort = true;
-    }
-    switch (E) {
-      case 1: nms_sort_kernel<1><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
-      case 2: nms_sort_kernel<2><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
-      case 4: nms_sort_kernel<4><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
-      case 8: nms_sort_kernel<8><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
-      default: nms_sort_kernel<16><<<(unsigned)B, kNmsThreads, sort_smem, st>>>(sa); break;
-    }
-    DCFA_CHECK_LAUNCH("nms_sort_kernel");
-    if (Apad > kSmemSortMax) {
-      nms_sort_global_kernel<<<(unsigned)B, kNmsThreads, 0, st>>>(sa);
-      DCFA_CHECK_LAUNCH("nms_sort_global_kernel");
-    }
+  if (Apad > kSmemSortMax) {
+    SortArgs sa{keys, cand, Apad};
+    nms_sort_global_kernel<<<(unsigned)B, kNmsThreads, 0, st>>>(sa);
+    DCFA_CHECK_LAUNCH("nms_sort_global_kernel");
   }
 
-  // shared-memory carve-out of the greedy kernel: state[A16] + 17 bytes per resident candidate
+  // cluster size: the largest power of two <= 8 that still gives every image its own SMs
+  int CS = 8;
+  while (CS > 1 && (int64_t)B * CS > sm_count()) CS >>= 1;
+  // shared-memory carve-out: greedy phase state[A16] + 17 bytes per resident candidate; sort phase up to
+  // 16384 / CS (rounded up to a power of two >= 1024) padded keys
   const int A16 = (A + 15) / 16 * 16;
-  const int kGreedySmemMax = 200 * 1024;
-  int cap = (kGreedySmemMax - A16) / 17;
+  const int kNmsSmemMax = 200 * 1024;
+  int cap = (kNmsSmemMax - A16) / 17;
   cap = cap >= A16 ? A16 : cap / 16 * 16;
-  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, cap, (float)nms_thres, nms_thres};
-  const size_t g_smem = (size_t)A16 + (size_t)cap * 17;
-  static bool attr_g0 = false, attr_g1 = false;
-  if (iou_mode == DCFA_IOU_TV_CUDA) {
-    if (!attr_g1) {
-      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
-      if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
-      attr_g1 = true;
-    }
-    nms_greedy_kernel<DCFA_IOU_TV_CUDA><<<(unsigned)B, kNmsThreads, g_smem, st>>>(ga);
-  } else {
-    if (!attr_g0) {
-      cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
-      if (e != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute(greedy): %s", cudaGetErrorString(e));
-      attr_g0 = true;
-    }
-    nms_greedy_kernel<DCFA_IOU_TV_CPU><<<(unsigned)B, kNmsThreads, g_smem, st>>>(ga);
+  size_t smem = (size_t)A16 + (size_t)cap * 17;
+  {
+    int per_cta = (std::min(Apad, kSmemSortMax) + CS - 1) / CS;
+    int nloc = 1024;
+    while (nloc < per_cta) nloc <<= 1;
+    smem = std::max(smem, (size_t)(nloc + nloc / 16) * 8);
   }
-  DCFA_CHECK_LAUNCH("nms_greedy_kernel");
+  GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, cap, (float)nms_thres, nms_thres};
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(nms_cluster_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemMax);
+    cudaError_t e2 = cudaFuncSetAttribute(nms_cluster_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemMax);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CS));
+  cfg.blockDim = dim3(kNmsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = iou_mode == DCFA_IOU_TV_CUDA ? cudaLaunchKernelEx(&cfg, nms_cluster_kernel<DCFA_IOU_TV_CUDA>, ga)
+                                                : cudaLaunchKernelEx(&cfg, nms_cluster_kernel<DCFA_IOU_TV_CPU>, ga);
+  if (le != cudaSuccess) return fail(DCFA_E_CUDA, "nms: cluster launch (B=%d, cluster %d): %s", B, CS, cudaGetErrorString(le));
+  count_launch();
   return DCFA_OK;
 }

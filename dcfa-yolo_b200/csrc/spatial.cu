@@ -45,17 +45,33 @@ __global__ void __launch_bounds__(256) maxpool5_kernel(const PoolArgs5 p) {
   const int ys = blockIdx.y * p.strip, ye = min(p.H, ys + p.strip);
   const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + c8 * 8;
   __nv_bfloat16* yout = p.y.p + p.y.img_off(n) + c8 * 8;
-  const int x_lo = max(x - 2, 0), x_hi = min(x + 2, p.W - 1);
+  // the five column taps, clamped into the image (a duplicate tap does not change a max)
+  int64_t xo[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) xo[k] = (int64_t)min(max(x + k - 2, 0), p.W - 1) * p.x.ld;
   Max8 w[5];
 #pragma unroll
   for (int i = 0; i < 5; ++i) w[i].fill(-INFINITY);
+  // rows are software-pipelined: the loads of row iy + 1 are in flight while row iy is reduced
+  const int r_lo = max(ys - 2, 0), r_hi = min(ye + 2, p.H);   // input rows [r_lo, r_hi)
+  uint4 nxt[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) nxt[k] = ldg128(xin + (int64_t)r_lo * p.W * p.x.ld + xo[k]);
   for (int iy = ys - 2; iy < ye + 2; ++iy) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[i] = w[i + 1];
     w[4].fill(-INFINITY);
-    if (iy >= 0 && iy < p.H) {
-      const __nv_bfloat16* row = xin + (int64_t)iy * p.W * p.x.ld;
-      for (int ix = x_lo; ix <= x_hi; ++ix) w[4].take(ldg128(row + (int64_t)ix * p.x.ld));
+    if (iy >= r_lo && iy < r_hi) {
+      uint4 cur[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cur[k] = nxt[k];
+      if (iy + 1 < r_hi) {
+        const __nv_bfloat16* row = xin + (int64_t)(iy + 1) * p.W * p.x.ld;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) nxt[k] = ldg128(row + xo[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) w[4].take(cur[k]);
     }
     const int oy = iy - 2;
     if (oy >= ys) {
@@ -91,33 +107,46 @@ __device__ __forceinline__ void load_sum8(const __nv_bfloat16* a, const __nv_bfl
   }
 }
 
-// grid = (ceil(Wo * C/8 / 256), Ho, images): the row terms are per-CTA constants, the column terms cost one
-// 32-bit division per thread.
+// grid = (ceil(Wo * C/8 / 256), ceil(Ho / kUpRows), images): a thread produces kUpRows vertically adjacent
+// outputs of one (column, 8-channel chunk), so the column terms (one 32-bit division) are paid once and
+// 4 * kUpRows loads are in flight.
+constexpr int kUpRows = 4;
+
 template <bool TWO>
 __global__ void __launch_bounds__(256) upsample_kernel(const UpArgs p) {
   const int c8n = p.C >> 3;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= p.Wo * c8n) return;
   const int ox = idx / c8n, c8 = idx - ox * c8n;
-  const int oy = blockIdx.y, n = blockIdx.z;
+  const int n = blockIdx.z;
   // ATen upsample_bilinear2d, align_corners=True: src = scale * dst, scale = (in-1)/(out-1)
-  const float fy = p.sy * (float)oy, fx = p.sx * (float)ox;
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
-  const float ly = fy - (float)y0, lx = fx - (float)x0;
-  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  const float fx = p.sx * (float)ox;
+  const int x0 = (int)fx;
+  const int x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+  const float lx = fx - (float)x0, hx = 1.0f - lx;
   const __nv_bfloat16* pa = p.a.p + p.a.img_off(n) + c8 * 8;
   const __nv_bfloat16* pb = TWO ? p.b.p + p.b.img_off(n) + c8 * 8 : nullptr;
-  const int i00 = y0 * p.Wi + x0, i01 = y0 * p.Wi + x1, i10 = y1 * p.Wi + x0, i11 = y1 * p.Wi + x1;
-  float v00[8], v01[8], v10[8], v11[8];
-  load_sum8<TWO>(pa + (int64_t)i00 * p.a.ld, pb + (int64_t)i00 * p.b.ld, v00);
-  load_sum8<TWO>(pa + (int64_t)i01 * p.a.ld, pb + (int64_t)i01 * p.b.ld, v01);
-  load_sum8<TWO>(pa + (int64_t)i10 * p.a.ld, pb + (int64_t)i10 * p.b.ld, v10);
-  load_sum8<TWO>(pa + (int64_t)i11 * p.a.ld, pb + (int64_t)i11 * p.b.ld, v11);
-  float o[8];
+  __nv_bfloat16* py = p.y.p + p.y.img_off(n) + (int64_t)ox * p.y.ld + c8 * 8;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
-  stg128(p.y.p + p.y.img_off(n) + (int64_t)(oy * p.Wo + ox) * p.y.ld + c8 * 8, pack8(o));
+  for (int r = 0; r < kUpRows; ++r) {
+    const int oy = blockIdx.y * kUpRows + r;
+    if (oy < p.Ho) {
+      const float fy = p.sy * (float)oy;
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0);
+      const float ly = fy - (float)y0, hy = 1.0f - ly;
+      const int i00 = y0 * p.Wi + x0, i01 = y0 * p.Wi + x1, i10 = y1 * p.Wi + x0, i11 = y1 * p.Wi + x1;
+      float v00[8], v01[8], v10[8], v11[8];
+      load_sum8<TWO>(pa + (int64_t)i00 * p.a.ld, pb + (int64_t)i00 * p.b.ld, v00);
+      load_sum8<TWO>(pa + (int64_t)i01 * p.a.ld, pb + (int64_t)i01 * p.b.ld, v01);
+      load_sum8<TWO>(pa + (int64_t)i10 * p.a.ld, pb + (int64_t)i10 * p.b.ld, v10);
+      load_sum8<TWO>(pa + (int64_t)i11 * p.a.ld, pb + (int64_t)i11 * p.b.ld, v11);
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+      stg128(py + (int64_t)oy * p.Wo * p.y.ld, pack8(o));
+    }
+  }
 }
 
 inline bool aligned(const void* ptr, int ld, int64_t img_stride, int64_t gstride) {
@@ -162,7 +191,7 @@ int launch_upsample(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.sy = a.Ho > 1 ? (float)(a.Hi - 1) / (float)(a.Ho - 1) : 0.0f;
   a.sx = a.Wo > 1 ? (float)(a.Wi - 1) / (float)(a.Wo - 1) : 0.0f;
   DCFA_REQUIRE(a.n_img <= 65535 && a.Ho <= 65535, "upsample: grid too large");
-  const dim3 grid((unsigned)ceil_div(a.Wo * (a.C >> 3), 256), (unsigned)a.Ho, (unsigned)a.n_img);
+  const dim3 grid((unsigned)ceil_div(a.Wo * (a.C >> 3), 256), (unsigned)ceil_div(a.Ho, kUpRows), (unsigned)a.n_img);
   if (a.b.p) upsample_kernel<true><<<grid, 256, 0, st>>>(a);
   else upsample_kernel<false><<<grid, 256, 0, st>>>(a);
   DCFA_CHECK_LAUNCH("upsample_kernel");
