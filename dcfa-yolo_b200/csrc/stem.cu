@@ -57,8 +57,22 @@ constexpr int B_BYTES = (TPW == 16 ? 256 : 128) * KROW;   // im2col tile
 constexpr int A_BYTES = 128 * KROW;           // replicated weight tile
 constexpr uint32_t kTmemCols = TPW == 16 ? 256 : 128;
 
+// uint8 NHWC input (DCFA_STEM_FLAG_U8): the raw patch is 9 rows of RAWB bytes starting 16 pixels (48 bytes, a
+// 16-byte multiple as the TMA box start requires) left of the tile's first conv column; bytes [32, 160) of each
+// row are converted once per tile to bf16 (exact: 0..255 are bf16 integers; the 1/255 of preprocess_input,
+// utils/utils.py:76-79, is folded into the BN scale) at U8_PITCH values per row.
+constexpr int RAWB = (3 * (16 + CW + 2) + 15) / 16 * 16;   // 160 for TPW 16
+constexpr int RAW_BYTES = RAWB * PH;                        // 1440
+constexpr int U8_SKIP = 32;                                 // first converted byte of a row
+constexpr int U8_CVT = RAWB - U8_SKIP;                      // 128 bytes converted per row
+constexpr int U8_PITCH = U8_CVT + 8;                        // converted row pitch in bf16 values: 68 words, so that the
+                                                            // 7 rows x 5 columns a warp touches spread over the banks
+constexpr int U8_CVT_OFF = (RAW_BYTES + 127) / 128 * 128;   // converted patch offset inside the ring slot
+static_assert(U8_CVT_OFF + PH * U8_PITCH * 2 <= PATCH_BUF, "u8 patch does not fit the ring slot");
+static_assert(U8_CVT % 16 == 0 && U8_PITCH % 8 == 0 && RAWB <= 256, "u8 patch geometry");
+
 struct StemArgs {
-  const float* x[2];
+  const void* x[2];        // fp32 NCHW, or uint8 NHWC
   const __nv_bfloat16* w;  // [G][128*32] swizzled (SWIZZLE_64B) replicated weight tile
   const float* scale;      // [G][C0pad]  (>= 0, sign folded into the weights)
   const float* bias;       // [G][C0pad]
@@ -67,6 +81,13 @@ struct StemArgs {
   int tiles_x, tiles_y, tiles_per_group, total_tiles;
   int use_tma;
 };
+
+__device__ __forceinline__ void tma_load_patch_u8(uint32_t dst, const CUtensorMap* map, int xb, int y, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(xb), "r"(y), "r"(n), "r"(bar)
+      : "memory");
+}
 
 __device__ __forceinline__ void tma_load_patch(uint32_t dst, const CUtensorMap* map, int x, int y, int n, uint32_t bar) {
   asm volatile(
@@ -100,6 +121,7 @@ struct TileIter {
   }
 };
 
+template <bool U8>
 __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(const __grid_constant__ CUtensorMap map0,
                                                                const __grid_constant__ CUtensorMap map1,
                                                                const StemArgs p) {
@@ -175,11 +197,19 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
     const uint32_t bar = bar_patch + 8u * slot;
     const uint32_t dst = s_patch + (uint32_t)slot * (uint32_t)PATCH_BUF;
     const int g = tc.n >= p.group_imgs ? 1 : 0;
-    const int x = 2 * tc.tx * TPW - 2 - XOFF, y = 2 * tc.ty * TPH - 2;
-    ptx::mbar_arrive_expect_tx(bar, PATCH_BYTES);
+    const int y = 2 * tc.ty * TPH - 2;
     // (no pointer select between the two maps: that would copy a __grid_constant__ parameter to local memory)
-    if (g == 0) tma_load_patch(dst, &map0, x, y, tc.n, bar);
-    else tma_load_patch(dst, &map1, x, y, tc.n - p.group_imgs, bar);
+    if (U8) {
+      const int xb = 3 * (2 * tc.tx * TPW - 16);
+      ptx::mbar_arrive_expect_tx(bar, RAW_BYTES);
+      if (g == 0) tma_load_patch_u8(dst, &map0, xb, y, tc.n, bar);
+      else tma_load_patch_u8(dst, &map1, xb, y, tc.n - p.group_imgs, bar);
+    } else {
+      const int x = 2 * tc.tx * TPW - 2 - XOFF;
+      ptx::mbar_arrive_expect_tx(bar, PATCH_BYTES);
+      if (g == 0) tma_load_patch(dst, &map0, x, y, tc.n, bar);
+      else tma_load_patch(dst, &map1, x, y, tc.n - p.group_imgs, bar);
+    }
   };
   if (p.use_tma && tid == 32) {   // prologue: request the first NBUF-1 patches
     for (int d = 0; d < NBUF - 1; ++d) {
@@ -197,7 +227,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
     float* s_in = patch_ptr + buf * (PATCH_BUF / 4);   // [3][PH][PWB]
 
     if (g != cur_group) {  // (re)load this modality's weight tile and this thread's scale/bias
-      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)g * 128 * 32);
+      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)g * 128 * 32);   // packing matches the input type
       uint4* dst = reinterpret_cast<uint4*>(gbase + B_BYTES);
       for (int i = tid; i < A_BYTES / 16; i += kStemThreads) dst[i] = __ldg(src + i);
       sc = __ldg(p.scale + (int64_t)g * p.C0pad + ch);
@@ -206,8 +236,18 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
     }
     if (p.use_tma) {
       ptx::mbar_wait(bar_patch + 8u * buf, (it / NBUF) & 1u);
+    } else if (U8) {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * p.Hi * p.Wi * 3;
+      uint8_t* raw = reinterpret_cast<uint8_t*>(s_in);
+      const int xb0 = 3 * (2 * px0 - 16), rowb = 3 * p.Wi;
+      for (int i = tid; i < RAW_BYTES; i += kStemThreads) {
+        const int r = i / RAWB, q = i - r * RAWB;
+        const int iy = cy0 - 1 + r, xb = xb0 + q;
+        raw[i] = (iy >= 0 && iy < p.Hi && xb >= 0 && xb < rowb) ? __ldg(img + (int64_t)iy * rowb + xb) : (uint8_t)0;
+      }
+      __syncthreads();
     } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
-      const float* img = (g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
+      const float* img = reinterpret_cast<const float*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
       constexpr int PC = CW + 2;   // patch columns actually used
       for (int i = tid; i < 3 * PH * PC; i += kStemThreads) {
         const int c = i / (PH * PC);
@@ -221,8 +261,51 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
       __syncthreads();
     }
 
-    // ---- im2col: one conv pixel per thread, K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes
-    if (tid < NPIX) {
+    if (U8) {
+      // ---- uint8 -> bf16, once per patch byte (each byte feeds up to 9 taps of ~2 conv pixels)
+      constexpr int CHUNKS = PH * (U8_CVT / 16);
+      if (tid < CHUNKS) {
+        const int r = tid / (U8_CVT / 16), c = tid - r * (U8_CVT / 16);
+        const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s_in) + r * RAWB + U8_SKIP + c * 16);
+        const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o[2 * k] = pack_bf16x2((float)(w[k] & 0xffu), (float)((w[k] >> 8) & 0xffu));
+          o[2 * k + 1] = pack_bf16x2((float)((w[k] >> 16) & 0xffu), (float)(w[k] >> 24));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(s_in) + U8_CVT_OFF + (r * U8_PITCH + c * 16) * 2);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      __syncthreads();
+      // ---- im2col: K index = ky*10 + kx*3 + ci (slots 9, 19, 29 carry a neighbouring value under a zero weight;
+      //      30, 31 are zero).  The 9 taps of one kernel row are 9 consecutive bf16 of the converted patch row,
+      //      starting at value 10 + 3*cx: five words, shifted by half a word when cx is odd.
+      if (tid < NPIX) {
+        const uint32_t* prow = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(s_in) + U8_CVT_OFF) +
+                               icy * (U8_PITCH / 2) + 5 + ((3 * icx) >> 1);
+        const uint32_t sh = (uint32_t)(icx & 1) * 16u;
+        uint32_t pk[16];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          uint32_t w[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) w[k] = prow[ky * (U8_PITCH / 2) + k];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) pk[ky * 5 + k] = __funnelshift_r(w[k], w[k + 1], sh);
+        }
+        pk[15] = 0u;
+        const uint32_t rowb = s_b + (uint32_t)tid * KROW;
+        const uint32_t xr = (uint32_t)((tid >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
+                       "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                       : "memory");
+      }
+    } else if (tid < NPIX) {
+      // ---- im2col: one conv pixel per thread, K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes
       const float* pin = s_in + icy * PWB + icx + XOFF;
       uint32_t pk[16];
 #pragma unroll
@@ -362,8 +445,9 @@ EncodeTiledFn stem_encode_fn() {
 
 int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   StemArgs a;
-  a.x[0] = resolve_ptr<const float>(op.x, bufs);
-  a.x[1] = resolve_ptr<const float>(op.x2, bufs);
+  const bool u8 = (op.flags & DCFA_STEM_FLAG_U8) != 0;
+  a.x[0] = resolve_ptr<const uint8_t>(op.x, bufs);
+  a.x[1] = resolve_ptr<const uint8_t>(op.x2, bufs);
   a.w = resolve_ptr<const __nv_bfloat16>(op.w, bufs);
   a.scale = resolve_ptr<const float>(op.scale, bufs);
   a.bias = resolve_ptr<const float>(op.bias, bufs);
@@ -390,34 +474,48 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.tiles_per_group = (int)per_group;
   a.total_tiles = (int)total;
 
-  // ---- tensor maps over the fp32 NCHW inputs: dims (W, H, C, N), box (36, 9, 3, 1), zero fill outside
+  // ---- tensor maps, zero fill outside the image:
+  //      fp32 NCHW : dims (W, H, C, N), box (PWB, 9, 3, 1)          uint8 NHWC : dims (3W bytes, H, N), box (RAWB, 9, 1)
   alignas(64) CUtensorMap maps[2];
   memset(maps, 0, sizeof(maps));
-  a.use_tma = (a.Wi % 4 == 0 && ((uintptr_t)a.x[0] % 16) == 0 && (groups == 1 || ((uintptr_t)a.x[1] % 16) == 0)) ? 1 : 0;
+  const bool ptr_ok = ((uintptr_t)a.x[0] % 16) == 0 && (groups == 1 || ((uintptr_t)a.x[1] % 16) == 0);
+  a.use_tma = (ptr_ok && (u8 ? (3 * a.Wi) % 16 == 0 : a.Wi % 4 == 0)) ? 1 : 0;
   if (a.use_tma) {
     EncodeTiledFn enc = stem_encode_fn();
     DCFA_REQUIRE(enc != nullptr, "stem: cuTensorMapEncodeTiled entry point unavailable");
     for (int g = 0; g < groups; ++g) {
-      const cuuint64_t gdim[4] = {(cuuint64_t)a.Wi, (cuuint64_t)a.Hi, 3, (cuuint64_t)a.group_imgs};
-      const cuuint64_t gstr[3] = {(cuuint64_t)a.Wi * 4, (cuuint64_t)a.Wi * a.Hi * 4, (cuuint64_t)a.Wi * a.Hi * 12};
-      const cuuint32_t box[4] = {(cuuint32_t)PWB, (cuuint32_t)PH, 3u, 1u};
       const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
-      CUresult cr = enc(&maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x[g]), gdim, gstr, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult cr;
+      if (u8) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)a.Wi * 3, (cuuint64_t)a.Hi, (cuuint64_t)a.group_imgs};
+        const cuuint64_t gstr[2] = {(cuuint64_t)a.Wi * 3, (cuuint64_t)a.Wi * a.Hi * 3};
+        const cuuint32_t box[3] = {(cuuint32_t)RAWB, (cuuint32_t)PH, 1u};
+        cr = enc(&maps[g], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(a.x[g]), gdim, gstr, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        const cuuint64_t gdim[4] = {(cuuint64_t)a.Wi, (cuuint64_t)a.Hi, 3, (cuuint64_t)a.group_imgs};
+        const cuuint64_t gstr[3] = {(cuuint64_t)a.Wi * 4, (cuuint64_t)a.Wi * a.Hi * 4, (cuuint64_t)a.Wi * a.Hi * 12};
+        const cuuint32_t box[4] = {(cuuint32_t)PWB, (cuuint32_t)PH, 3u, 1u};
+        cr = enc(&maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(a.x[g]), gdim, gstr, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
       if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled failed with %d", (int)cr);
     }
   }
   const size_t smem = 1024 + B_BYTES + A_BYTES + NBUF * PATCH_BUF + (size_t)TPH * TPW * 128 * 2 + 128;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "stem: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   int64_t grid = (int64_t)sm_count() * kStemCtasPerSm;   // CTAs per SM bounded by TMEM columns (512 / kTmemCols)
   if (grid > total) grid = total;
-  stem_kernel<<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
+  if (u8) stem_kernel<true><<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
+  else stem_kernel<false><<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
   DCFA_CHECK_LAUNCH("stem_kernel");
   return DCFA_OK;
 }

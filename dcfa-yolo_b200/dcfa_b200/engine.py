@@ -12,12 +12,13 @@ from . import plan as P
 class Engine:
     """One (batch, H, W) instance of the forward pass on one device."""
 
-    def __init__(self, state_dict, phi, num_classes, batch, height, width, device):
+    def __init__(self, state_dict, phi, num_classes, batch, height, width, device, input_u8=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("dcfa_b200 has no CPU path: the engine needs a CUDA (sm_100a) device")
         _lib.check(_lib.lib.dcfa_device_check(self.device.index if self.device.index is not None else torch.cuda.current_device()))
-        self.plan = P.Plan(state_dict, phi, num_classes, batch, height, width)
+        self.input_u8 = bool(input_u8)
+        self.plan = P.Plan(state_dict, phi, num_classes, batch, height, width, input_u8=self.input_u8)
         self.B, self.H, self.W, self.nc, self.no, self.A = batch, height, width, self.plan.nc, self.plan.no, self.plan.A
         self.level_shapes = list(self.plan.level_shapes)
         self.blob = self.plan.blob_tensor.to(self.device)
@@ -47,12 +48,14 @@ class Engine:
         return dbox, cls, x
 
     def run(self, rgb, nir, outputs=None, stream=None):
-        """rgb, nir: contiguous float32 CUDA tensors [B,3,H,W].  Enqueues the whole forward; returns (dbox, cls, x)."""
-        shp = (self.B, 3, self.H, self.W)
+        """rgb, nir: contiguous CUDA tensors, float32 [B,3,H,W] (or uint8 [B,H,W,3] for an input_u8 engine).
+        Enqueues the whole forward; returns (dbox, cls, x)."""
+        shp = (self.B, self.H, self.W, 3) if self.input_u8 else (self.B, 3, self.H, self.W)
+        dt = torch.uint8 if self.input_u8 else torch.float32
         for t in (rgb, nir):
-            if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
-                raise ValueError("engine.run: expected contiguous float32 %s on %s, got %s %s on %s" % (
-                    shp, self.device, tuple(t.shape), t.dtype, t.device))
+            if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("engine.run: expected contiguous %s %s on %s, got %s %s on %s" % (
+                    dt, shp, self.device, tuple(t.shape), t.dtype, t.device))
         dbox, cls, x = outputs if outputs is not None else self.new_outputs()
         b = self._bufs
         b[P.BUF_RGB], b[P.BUF_NIR] = rgb.data_ptr(), nir.data_ptr()

@@ -68,8 +68,12 @@ def pack_conv_weight(w, bk=None):
     return packed, meta
 
 
-def pack_stem(w, scale, bias):
+def pack_stem(w, scale, bias, u8=False):
     """Stem conv [C0,3,3,3] + folded BN -> (weight tile bf16 [128*32], scale [C0pad], bias [C0pad], C0pad).
+
+    u8=True packs for uint8 NHWC inputs (DCFA_STEM_FLAG_U8): K = ky*10 + kx*3 + ci, so that the nine taps of one
+    kernel row are nine consecutive values of an NHWC image row (slots 9, 19, 29, 30, 31 are zero), and the scale
+    carries preprocess_input's 1/255 (utils/utils.py:76-79) -- the kernel multiplies exact integer pixels.
 
     The stem GEMM puts CHANNELS on the 128 MMA rows (replicated C0pad-periodically so every TMEM lane quarter holds
     a copy) and pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative
@@ -78,13 +82,21 @@ def pack_stem(w, scale, bias):
     c0pad = 32 if c0 <= 32 else (64 if c0 <= 64 else 128)
     sgn = torch.where(scale < 0, -torch.ones_like(scale), torch.ones_like(scale))
     wk = (w * sgn.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(c0, 27)     # K = (ky*3 + kx)*3 + ci
+    if u8:
+        wk10 = torch.zeros(c0, 32, dtype=wk.dtype)
+        for ky in range(3):
+            wk10[:, ky * 10: ky * 10 + 9] = wk[:, ky * 9: ky * 9 + 9]
+        wk, nk = wk10, 32
+    else:
+        nk = 27
     tile = torch.zeros(128, 32, dtype=torch.float32)
     for m in range(128):
         c = m % c0pad
         if c < c0:
-            tile[m, :27] = wk[c]
+            tile[m, :nk] = wk[c]
     packed = swizzle_tile(tile.to(torch.bfloat16)).reshape(-1)
-    return packed, pad_channels(scale.abs(), c0pad), pad_channels(bias, c0pad), c0pad
+    sc = scale.abs() / 255.0 if u8 else scale.abs()
+    return packed, pad_channels(sc, c0pad), pad_channels(bias, c0pad), c0pad
 
 
 def pad_channels(v, n, fill=0.0):

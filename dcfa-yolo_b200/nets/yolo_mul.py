@@ -174,12 +174,12 @@ class YoloBody(nn.Module):
             self.invalidate_plan()
         return out
 
-    def _engine(self, batch, height, width, device):
+    def _engine(self, batch, height, width, device, input_u8=False):
         from dcfa_b200.engine import Engine
-        key = (batch, height, width, str(device))
+        key = (batch, height, width, str(device), bool(input_u8))
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self.state_dict(), self.phi, self.num_classes, batch, height, width, device)
+            eng = Engine(self.state_dict(), self.phi, self.num_classes, batch, height, width, device, input_u8=input_u8)
             self._engines[key] = eng
         return eng
 
@@ -189,6 +189,19 @@ class YoloBody(nn.Module):
                                       "(training-mode BatchNorm / backward are out of scope)")
         if not (torch.is_tensor(rgb) and torch.is_tensor(nir) and rgb.is_cuda and nir.is_cuda):
             raise RuntimeError("dcfa_b200 has no CPU path: YoloBody.forward needs CUDA tensors on an sm_100a device")
+        if rgb.dtype == torch.uint8 or nir.dtype == torch.uint8:
+            # Extension of the reference signature: raw uint8 images [B,H,W,3] (what cvtColor/resize_image produce,
+            # utils/utils.py:9-37).  preprocess_input's /255 and the HWC->CHW transpose (yolo_mul.py:76) happen
+            # inside the stem kernel; the upload is 4x smaller than the fp32 tensor.
+            if rgb.dtype != nir.dtype or rgb.shape != nir.shape or rgb.dim() != 4 or rgb.shape[3] != 3:
+                raise ValueError("expected two uint8 (B,H,W,3) tensors, got %s %s and %s %s" % (
+                    rgb.dtype, tuple(rgb.shape), nir.dtype, tuple(nir.shape)))
+            b, h, w, _ = rgb.shape
+            eng = self._engine(b, h, w, rgb.device, input_u8=True)
+            with torch.no_grad():
+                dbox, cls, x = eng.run(rgb.detach().contiguous(), nir.detach().contiguous())
+            self.anchors, self.strides, self.shape = eng.anchors, eng.strides, (b, x[0].shape[1], x[0].shape[2], x[0].shape[3])
+            return dbox, cls, x, eng.anchors, eng.strides
         if rgb.shape != nir.shape or rgb.dim() != 4 or rgb.shape[1] != 3:
             raise ValueError("expected two (B,3,H,W) tensors, got %s and %s" % (tuple(rgb.shape), tuple(nir.shape)))
         b, _, h, w = rgb.shape

@@ -70,6 +70,10 @@ enum {
 /* activation applied in conv / depthwise epilogues */
 enum { DCFA_ACT_NONE = 0, DCFA_ACT_RELU = 1, DCFA_ACT_SILU = 2 };
 
+/* DCFA_OP_STEM flags: the inputs are uint8 NHWC images [group_imgs,Hi,Wi,3] (the output of cvtColor/resize_image,
+ * utils/utils.py:9-37, before preprocess_input's /255, which the caller folds into `scale`) instead of fp32 NCHW */
+enum { DCFA_STEM_FLAG_U8 = 0x100 };
+
 /* DCFA_OP_CONV output modes */
 enum { DCFA_OUT_BF16_NHWC = 0, DCFA_OUT_F32_NCHW = 1 };
 
@@ -100,6 +104,8 @@ typedef struct dcfa_view {
  *        K-major tile per group whose 128 rows are the Cout channels repeated with period BN (= Cout rounded up
  *        to 32/64/128), K = (ky*3+kx)*3+ci padded to 32, rows of channels with a negative BN scale negated;
  *        scale (>= 0), bias = fp32 [G][BN]; y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
+ *        With flags & DCFA_STEM_FLAG_U8: x,x2 = uint8 NHWC [group_imgs,Hi,Wi,3], K = ky*10+kx*3+ci (slots 9,19,29
+ *        and 30,31 zero), scale already divided by 255.
  * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed
  *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
  *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added

@@ -87,8 +87,14 @@ def run_ops(ops, bufs):
             outs = []
             for g in range(G):
                 src = bufs[op.x.buf] if g == 0 else bufs[op.x2.buf]
-                x = src.view(torch.float32).view(gi, 3, op.Hi, op.Wi).to(torch.bfloat16).float()
-                wt = wall[g, :c0, :27].view(c0, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                if op.flags & 0x100:   # uint8 NHWC pixels, K = ky*10 + kx*3 + ci, scale already / 255
+                    x = src.view(gi, op.Hi, op.Wi, 3).permute(0, 3, 1, 2).float()
+                    wk = torch.cat([wall[g, :c0, ky * 10: ky * 10 + 9] for ky in range(3)], 1)
+                    assert float(wall[g, :, [9, 19, 29, 30, 31]].abs().max()) == 0.0
+                else:
+                    x = src.view(torch.float32).view(gi, 3, op.Hi, op.Wi).to(torch.bfloat16).float()
+                    wk = wall[g, :c0, :27]
+                wt = wk.reshape(c0, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
                 y = F.conv2d(x, wt, None, 1, 1) * sc[g, :c0].view(1, -1, 1, 1) + bi[g, :c0].view(1, -1, 1, 1)
                 y = F.max_pool2d(F.relu(y), 3, 2, 1)
                 outs.append(y.permute(0, 2, 3, 1))
@@ -199,7 +205,8 @@ def run_ops(ops, bufs):
 
 
 def run_plan(plan, rgb, nir):
-    """Execute a dcfa_b200.plan.Plan on CPU.  rgb, nir: float32 [B,3,H,W].  -> (dbox, cls, [x0,x1,x2])."""
+    """Execute a dcfa_b200.plan.Plan on CPU.  rgb, nir: float32 [B,3,H,W] (uint8 [B,H,W,3] for an input_u8 plan).
+    -> (dbox, cls, [x0,x1,x2])."""
     from dcfa_b200 import plan as P
     b, no = plan.B, plan.no
     f32 = lambda numel: torch.zeros(numel * 4, dtype=torch.uint8)

@@ -109,6 +109,27 @@ def test_full_pipeline_vs_oracle_and_shard_invariance(cuda):
     assert len(res) == 4
 
 
+def test_uint8_nhwc_inputs_match_oracle_on_preprocessed_pixels(cuda):
+    """net(uint8 [B,H,W,3]) == oracle(preprocess_input(pixels) as NCHW): the /255 and the transpose of
+    yolo_mul.py:76 run inside the stem kernel."""
+    from oracle import forward as O
+    z, meta, keys = load_golden("s128_stress")
+    sd = golden_state_dict(meta, keys)
+    net = build_model(meta, sd, cuda)
+    g = torch.Generator().manual_seed(11)
+    rgb8 = torch.randint(0, 256, (3, 128, 128, 3), generator=g, dtype=torch.uint8)
+    nir8 = torch.randint(0, 256, (3, 128, 128, 3), generator=g, dtype=torch.uint8)
+    out = net(rgb8.to(cuda), nir8.to(cuda))
+    ref = O.yolo_forward(sd, "s", rgb8.permute(0, 3, 1, 2).float() / 255.0, nir8.permute(0, 3, 1, 2).float() / 255.0, 1)
+    np.testing.assert_allclose(out[0].cpu().numpy(), ref[0].numpy(), atol=2e-2, rtol=1e-2)
+    np.testing.assert_allclose(out[1].cpu().numpy(), ref[1].numpy(), atol=2e-2, rtol=1e-2)
+    # and it agrees with the fp32 entry point fed the same pixels (only the input rounding differs)
+    out_f = net((rgb8.permute(0, 3, 1, 2).float() / 255.0).to(cuda), (nir8.permute(0, 3, 1, 2).float() / 255.0).to(cuda))
+    np.testing.assert_allclose(out[0].cpu().numpy(), out_f[0].cpu().numpy(), atol=4e-2, rtol=2e-2)
+    with pytest.raises(ValueError):
+        net(rgb8.permute(0, 3, 1, 2).contiguous().to(cuda), nir8.permute(0, 3, 1, 2).contiguous().to(cuda))
+
+
 def test_no_cpu_fallback_and_training_mode(cuda):
     from nets.yolo_mul import YoloBody
     from utils.utils_bbox import DecodeBox

@@ -152,6 +152,36 @@ def test_stem(cuda, b, h, w, c0, groups):
     _bf16_close(y.cpu(), ref.permute(0, 2, 3, 1), "stem")
 
 
+@pytest.mark.parametrize("b,h,w,c0,groups", [(1, 32, 64, 16, 1), (2, 40, 80, 32, 2), (1, 70, 130, 32, 1), (3, 33, 47, 48, 2),
+                                            (2, 96, 128, 64, 2), (1, 640, 640, 32, 1)])
+def test_stem_uint8_nhwc(cuda, b, h, w, c0, groups):
+    """DCFA_STEM_FLAG_U8: raw uint8 NHWC pixels; the kernel folds preprocess_input's /255 (utils/utils.py:76-79).
+    Widths whose rows are 16-byte multiples take the TMA path, the others the plain-load path."""
+    from dcfa_b200 import abi, pack
+    g = torch.Generator().manual_seed(6)
+    xs = [torch.randint(0, 256, (b, h, w, 3), generator=g, dtype=torch.uint8) for _ in range(groups)]
+    ws = [bf16_round(torch.randn(c0, 3, 3, 3, generator=g) * 0.3) for _ in range(groups)]
+    bs = [torch.randn(c0, generator=g) * 0.2 for _ in range(groups)]
+    scs = [torch.rand(c0, generator=g) - 0.3 for _ in range(groups)]
+    packed, sks, bks, c0pad = [], [], [], 32
+    for i in range(groups):
+        pk, sca, bia, c0pad = pack.pack_stem(ws[i], scs[i], bs[i], u8=True)
+        packed.append(pk); sks.append(sca); bks.append(bia)
+    wk, sk, bk = torch.stack(packed).to(cuda), torch.stack(sks).to(cuda), torch.stack(bks).to(cuda)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.zeros(groups * b, ho, wo, c0, dtype=torch.bfloat16, device=cuda)
+    xg = [t.to(cuda) for t in xs]
+    bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
+    op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
+                    bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad,
+                    flags=abi.STEM_FLAG_U8)
+    _run([op], bufs)
+    ref = torch.cat([F.max_pool2d(F.relu(F.conv2d(xs[i].permute(0, 3, 1, 2).float() / 255.0, ws[i], None, 1, 1)
+                                         * scs[i].view(1, -1, 1, 1) + bs[i].view(1, -1, 1, 1)), 3, 2, 1) for i in range(groups)])
+    _bf16_close(y.cpu(), ref.permute(0, 2, 3, 1), "stem_u8")
+
+
 @pytest.mark.parametrize("n,h,w,c,act,groups,use_res", [(2, 9, 11, 16, 0, 1, False), (4, 20, 20, 64, 2, 2, True),
                                                       (2, 13, 6, 128, 2, 1, True), (2, 40, 40, 32, 0, 2, False),
                                                       (3, 33, 50, 256, 2, 1, True), (2, 160, 160, 32, 0, 2, False),

@@ -34,3 +34,22 @@ def test_plan_flop_count_matches_survey():
     sd = O.synth_state_dict({k: torch.empty(tuple(s), device="meta") for k, s in keys.items()}, 1, "default")
     plan = Plan(sd, "n", 1, 1, 640, 640)
     assert abs(plan.conv_flops / 7.361e9 - 1.0) < 0.01, plan.conv_flops
+
+
+def test_plan_uint8_input_matches_oracle_on_preprocessed_pixels():
+    """input_u8 plans (uint8 NHWC images, /255 folded into the stem) vs the fp32 oracle fed preprocess_input's
+    output (utils/utils.py:76-79 + the HWC->CHW transpose of yolo_mul.py:76)."""
+    from dcfa_b200.plan import Plan
+    from oracle import forward as O
+    from oracle import plan_interp
+    z, meta, keys = load_golden("s128_stress")
+    sd = golden_state_dict(meta, keys)
+    g = torch.Generator().manual_seed(3)
+    rgb8 = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    nir8 = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    plan = Plan(sd, meta["phi"], meta["nc"], 2, 128, 128, input_u8=True)
+    dbox, cls, x = plan_interp.run_plan(plan, rgb8, nir8)
+    ref = O.yolo_forward(sd, meta["phi"], rgb8.permute(0, 3, 1, 2).float() / 255.0, nir8.permute(0, 3, 1, 2).float() / 255.0,
+                         meta["nc"])
+    np.testing.assert_allclose(dbox.numpy(), ref[0].numpy(), atol=2e-2, rtol=1e-2)
+    np.testing.assert_allclose(cls.numpy(), ref[1].numpy(), atol=2e-2, rtol=1e-2)

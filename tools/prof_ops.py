@@ -27,12 +27,17 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--u8", action="store_true", help="uint8 NHWC inputs (DCFA_STEM_FLAG_U8)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     net = bench.build_model(a.phi, a.size, dev)
-    eng = net._engine(a.batch, a.size, a.size, dev)
-    rgb = torch.rand(a.batch, 3, a.size, a.size, device=dev)
-    nir = torch.rand(a.batch, 3, a.size, a.size, device=dev)
+    eng = net._engine(a.batch, a.size, a.size, dev, input_u8=a.u8)
+    if a.u8:
+        rgb = torch.randint(0, 256, (a.batch, a.size, a.size, 3), dtype=torch.uint8, device=dev)
+        nir = torch.randint(0, 256, (a.batch, a.size, a.size, 3), dtype=torch.uint8, device=dev)
+    else:
+        rgb = torch.rand(a.batch, 3, a.size, a.size, device=dev)
+        nir = torch.rand(a.batch, 3, a.size, a.size, device=dev)
     eng.run(rgb, nir)
     torch.cuda.synchronize()
     st = torch.cuda.current_stream(dev)
