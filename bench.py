@@ -414,8 +414,17 @@ def run_ours(args):
     if args.profile_ops:
         with open(args.profile_ops, "w") as f:
             json.dump({"batch": B, "size": S, "phi": args.phi, "ms_by_kind": by_kind, "ops": rows}, f, indent=1)
+    traffic = None
+    try:   # DRAM bytes of the same 47 launches from the committed ncu --set full capture (same workload only)
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1f_conv_traffic.json")))
+        if (tj["phi"], tj["batch"], tj["size"]) == (args.phi, B, S):
+            traffic = tj["dram_bytes_read_per_step"] + tj["dram_bytes_write_per_step"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "tensor", "kernel": "conv_tma_kernel", "achieved": round(achieved, 2), "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["src"],
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic,
+                "traffic_note": "DRAM read+write bytes summed over the step's conv launches (ncu, cold caches); achieved = "
+                                "algorithmic conv FLOPs of the step / summed conv launch time", "peak_source": peaks["src"],
                 "launches_per_step": len(conv), "kernel_ms_per_step": round(conv_ms, 4),
                 "share_of_forward": round(conv_ms / all_ms, 3), "ms_by_kind": {k: round(v, 4) for k, v in by_kind.items()}}
     flops_pair = eng.plan.conv_flops / B

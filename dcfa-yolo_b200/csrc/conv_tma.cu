@@ -75,6 +75,7 @@ struct TmaConvArgs {
   int cbox;               // channels per store slab (64 / 32 / 16)
   uint32_t out_stage_bytes;  // 128 rows * cbox * 2
   uint32_t tmem_cols;
+  uint32_t acc_stages;   // TMEM accumulator stages (2 or 4): the MMA issuer runs this many tiles ahead of the epilogues
 };
 
 #ifdef DCFA_TIMELINE
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t bar_full = bars;
   const uint32_t bar_empty = bars + 8u * kMaxStages;
   const uint32_t bar_tfull = bars + 16u * kMaxStages;
-  const uint32_t bar_tempty = bar_tfull + 16u;
-  const uint32_t tmem_slot = bar_tempty + 16u;
+  const uint32_t bar_tempty = bar_tfull + 32u;
+  const uint32_t tmem_slot = bar_tempty + 32u;
   const uint32_t sb_base = (tmem_slot + 4u + 15u) & ~15u;  // 2 groups x (256 scale + 256 bias) floats
   const uint32_t stage_out = (sb_base + 4096u + 1023u) & ~1023u;  // [group][2] output staging tiles (TMA store)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         ptx::mbar_init(bar_full + 8u * s, 1);   // one arrive.expect_tx; A and W complete through tx bytes
         ptx::mbar_init(bar_empty + 8u * s, 1);  // one tcgen05.commit
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < (int)p.acc_stages; ++a) {
         ptx::mbar_init(bar_tfull + 8u * a, 1);
         ptx::mbar_init(bar_tempty + 8u * a, 4);  // the four warps of the stage's epilogue group
       }
@@ -238,8 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           }
         }
         ptx::umma_commit(bar_tfull + 8u * as);
-        as ^= 1u;
-        if (as == 0u) aph ^= 1u;
+        if (++as == p.acc_stages) { as = 0u; aph ^= 1u; }
       }
     }
   } else {
@@ -255,12 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     // shared memory there is no L1 left, so __ldg would pay an L2 round trip per 16-channel chunk
     float* sb = reinterpret_cast<float*>(smem_raw + (sb_base - ptx::smem_u32(smem_raw))) + group * 512;
     int sb_key = -1;
-    uint32_t aph = 0;
+    const uint32_t acc_shift = p.acc_stages == 4u ? 2u : 1u;
     uint32_t slab = 0;   // store slabs issued by this group (selects the staging buffer)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       if ((int)(tcount & 1u) != group) continue;
-      const uint32_t as = (uint32_t)group;
+      const uint32_t as = tcount & (p.acc_stages - 1u);   // accumulator stage; its parity is the group's
+      const uint32_t aph = (tcount >> acc_shift) & 1u;     // the stage's use count, mod 2
       const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
       const int nt = tile - (int)rest * p.n_tiles;
       const int n = (int)p.div_tiles_img.div(rest);
@@ -293,7 +294,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       }
       const int cvalid = min(p.BN, p.Cout - nt * p.BN);  // valid channels of this n-tile
       ptx::mbar_wait(bar_tfull + 8u * as, aph);
-      aph ^= 1u;
       ptx::tc_fence_after();
       if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 1);
       const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         }
         if (p.act == DCFA_ACT_SILU) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = v[e] * sigmoid_fast(v[e]);
+          for (int e = 0; e < 16; ++e) v[e] = silu_fast(v[e]);
         } else if (p.act == DCFA_ACT_RELU) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
@@ -326,12 +326,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         }
         if (p.tma_store) {
           // ---- stage 16 channels of this row into the swizzled slab; a full slab leaves with one TMA store
-          const int cs = c0 % p.cbox;            // channel offset inside the slab
+          const int cs = c0 & (p.cbox - 1);      // channel offset inside the slab (cbox is 16, 32 or 64)
+          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 0);
           if (cs == 0) {
             // the slab buffer about to be overwritten was read by the TMA store issued two slabs ago
             if (gtid == 0) bulk_wait_read<1>();
             ptx::named_bar_sync(1 + group, 128);
           }
+          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 1);
           const uint32_t pitch = (uint32_t)p.cbox * 2u;
           const uint32_t rowb = stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes + (uint32_t)r * pitch;
           // Swizzle<B,4,3>: 16-byte chunk index XOR (row bits above the 128-byte line)
@@ -344,14 +346,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (((ch + 1u) ^ xr) << 4)), "r"(hi.x),
                        "r"(hi.y), "r"(hi.z), "r"(hi.w)
                        : "memory");
+          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 2);
           if (cs + 16 == p.cbox) {   // slab complete
             ptx::fence_proxy_async_smem();
+            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 3);
             ptx::named_bar_sync(1 + group, 128);
+            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 4);
             if (gtid == 0 && nt * p.BN + c0 + 16 - p.cbox < p.Cout) {
               tma_store_4d(&tmap_y, stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes,
                            nt * p.BN + c0 + 16 - p.cbox, tx * p.tw, ty * p.th, n);
             }
             if (gtid == 0) bulk_commit();
+            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 5);
             ++slab;
           }
         } else if (rvalid && c0 < cvalid) {
@@ -378,11 +384,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       ptx::tmem_ld_x16(taddr0, accA);
       for (int j = 0; j < nchunks; j += 2) {
         ptx::tmem_ld_wait();
+        if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 6);
         if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), accB);  // prefetch the next chunk
         process(accA, j);
         __syncwarp();
         if (j + 1 < nchunks) {
           ptx::tmem_ld_wait();
+          if (group == 0 && gtid == 0 && j + 1 < 2) TL(6, 16 * (tcount >> 1) + 8 * (j + 1) + 6);
           if (j + 2 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2) * 16), accA);
           process(accB, j + 1);
           __syncwarp();
@@ -531,8 +539,9 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(stages >= 2, "conv(tma): not enough shared memory");
   a.stages = stages;
   const int smem = fixed + stages * stage_bytes;
+  a.acc_stages = 4 * a.BN <= 512 ? 4u : 2u;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
+  while (cols < a.acc_stages * (uint32_t)a.BN) cols <<= 1;
   a.tmem_cols = cols;
 
   // ---- tensor map over the input view: dims (C, W, H, N), innermost first

@@ -118,7 +118,7 @@ __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_
     const int pp = (oy0 + o) * TW + col;
     if (p.act == DCFA_ACT_SILU) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[o][e] = acc[o][e] * sigmoid_fast(acc[o][e]);
+      for (int e = 0; e < 8; ++e) acc[o][e] = silu_fast(acc[o][e]);
     } else if (p.act == DCFA_ACT_RELU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[o][e] = fmaxf(acc[o][e], 0.0f);

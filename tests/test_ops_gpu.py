@@ -47,6 +47,8 @@ CONV_CASES = [
     (2, 160, 160, 32, 64, 3, 2, 2, 1),  # backbone-like: 64-byte swizzle, stride 2, wide tiles
     (1, 21, 37, 64, 64, 3, 2, 2, 1),    # odd input size with stride 2
     (2, 20, 20, 512, 256, 1, 1, 2, 1),  # 20x20 maps: partial spatial tiles
+    (2, 40, 40, 128, 128, 3, 2, 2, 2),  # stride 2, two k-blocks per tap, two groups
+    (1, 22, 38, 64, 32, 3, 2, 0, 1),    # stride 2, even width, partial tiles on the right / bottom edge
 ]
 
 
@@ -96,6 +98,24 @@ def test_conv_views_residual_postscale(cuda):
     r = (r * torch.sigmoid(r)) * 0.5 + res[..., 16:16 + cout].permute(0, 3, 1, 2)
     _bf16_close(y[..., 40:72].cpu(), r.permute(0, 2, 3, 1), "conv view")
     assert (y[..., :40] == 3.0).all() and (y[..., 72:] == 3.0).all(), "conv wrote outside its channel slot"
+
+
+def test_conv_stride2_on_channel_subview(cuda):
+    """stride-2 3x3 conv reading a channel sub-view (Cin < ld): the element-strided tensor map must step over the
+    neighbouring channels (down1/down2 read P3/P4 out of wider buffers)."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(17)
+    n, h, w, ctot, c_off, cin, cout = 2, 24, 36, 160, 64, 64, 96
+    x = bf16_round(torch.randn(n, h, w, ctot, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / 24)
+    sc, bi = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    y = torch.full((n, h // 2, w // 2, cout), 3.0, dtype=torch.bfloat16, device=cuda)
+    op, bufs = conv_op(x.to(torch.bfloat16).to(cuda), [wt], [sc], [bi], y, ksize=3, stride=2, act=abi.ACT_SILU, cin=cin,
+                       c_off_in=c_off)
+    assert op.flags != 0
+    _run([op], bufs)
+    r = F.conv2d(x[..., c_off:c_off + cin].permute(0, 3, 1, 2), wt, None, 2, 1) * sc[None, :, None, None] + bi[None, :, None, None]
+    _bf16_close(y.cpu(), (r * torch.sigmoid(r)).permute(0, 2, 3, 1), "conv s2 sub-view")
 
 
 def test_conv_f32_nchw_out(cuda):
