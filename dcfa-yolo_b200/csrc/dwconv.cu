@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,7 +31,8 @@ constexpr int kDwThreads = 256;
 constexpr int IN_BYTES = HH * HW * CB * 2;     // 23040
 constexpr int IN_BUF = (IN_BYTES + 1023) / 1024 * 1024;
 constexpr int OUT_BYTES = TH * TW * CB * 2;    // 16384
-constexpr int NIN = 2;                         // input ring: the next tile's box loads while this one computes
+constexpr int kMaxNin = 4;                     // input ring depth limit.  Round 1: with one box in flight per CTA the kernel
+                                               // spent 26 % of its samples waiting for the TMA load (profiles/)
                                                // (~98 KB per CTA -> two CTAs per SM)
 
 struct DwTmaArgs {
@@ -41,6 +44,10 @@ struct DwTmaArgs {
   int tiles_x, tiles_y;
   int total_tiles;
   int has_res;
+  int nin;            // input ring depth (2..kMaxNin): loads run nin-1 tiles ahead
+  int in_buf;         // bytes reserved per input ring slot (1024-byte multiple)
+  int out_buf;        // bytes per staging / residual tile buffer (1024-byte multiple)
+  int res_slots;      // residual buffers: nin (ringed with the inputs), 1 (loads then run one tile ahead only) or 0
 };
 
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
@@ -140,14 +147,19 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: in[NIN] | res (one tile, optional) | out[2] | w (9*64 fp32) | bias (64 fp32) | barriers
+  // layout: in[nin] | res[nin] (only with a residual) | out[2] | w (9*64 fp32) | bias (64 fp32) | barriers; buffer
+  // sizes follow the channel block (p.in_buf, p.out_buf), so that narrow layers get a deeper ring at two CTAs per SM
+  const int NIN = p.nin;
+  const uint32_t IN_BUF = (uint32_t)p.in_buf, OUT_BUF = (uint32_t)p.out_buf;
+  const uint32_t res_ring = p.res_slots > 1 ? OUT_BUF : 0u;   // residual slot pitch (0: one shared buffer)
+  const uint32_t res_total = (uint32_t)p.res_slots * OUT_BUF;
   const uint32_t s_in = base;
   const uint32_t s_res = s_in + NIN * IN_BUF;
-  const uint32_t s_out = s_res + OUT_BYTES;
-  float* w_s = reinterpret_cast<float*>(gbase + NIN * IN_BUF + 3 * OUT_BYTES);
+  const uint32_t s_out = s_res + res_total;
+  float* w_s = reinterpret_cast<float*>(gbase + NIN * IN_BUF + res_total + 2 * OUT_BUF);
   float* b_s = w_s + 9 * CB;
-  const uint32_t bars = s_out + 2 * OUT_BYTES + (9 * CB + CB) * 4;
-  const uint32_t bar_in = bars;               // NIN barriers (input box [+ residual box] landed)
+  const uint32_t bars = s_out + 2 * OUT_BUF + (9 * CB + CB) * 4;
+  const uint32_t bar_in = bars;               // nin barriers (input box [+ residual box] landed)
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -165,11 +177,11 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
     const uint32_t bar = bar_in + 8u * slot;
     ptx::mbar_arrive_expect_tx(bar, in_bytes + (p.has_res ? out_bytes : 0u));
     tma_load_box(s_in + (uint32_t)slot * IN_BUF, &map_x, t.cbi * p.cb, t.tx * TW - 1, t.ty * TH - 1, t.n, bar);
-    if (p.has_res) tma_load_box(s_res + 0u, &map_r, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n, bar);
+    if (p.has_res) tma_load_box(s_res + (uint32_t)slot * res_ring, &map_r, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n, bar);
   };
-  // NOTE: the residual buffer is single: the residual box of tile i+k must not land before tile i consumed its
-  // own, so with a residual the ring runs one tile ahead only (handled below by `ahead`).
-  const int ahead = p.has_res ? 1 : NIN - 1;
+  // with a single residual buffer the residual box of tile i+2 must not land before tile i+1 consumed its own:
+  // the ring then runs one tile ahead only
+  const int ahead = (p.has_res && p.res_slots == 1) ? 1 : NIN - 1;
   int tile = blockIdx.x;
   if (tid == 32) {
     for (int d = 0; d < ahead; ++d)
@@ -181,7 +193,8 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
   int cur_key = -1;
   uint32_t it = 0;
   int slot = 0;
-  for (; tile < p.total_tiles; tile += gridDim.x, ++it, slot = (slot + 1 == NIN ? 0 : slot + 1)) {
+  uint32_t ring_ph = 0;                        // parity of the ring pass `slot` is in
+  for (; tile < p.total_tiles; tile += gridDim.x, ++it) {
     const DwTile t = dw_decode(p, tile);
     const int g = t.n / p.group_imgs;
     const int key = g * p.cblocks + t.cbi;
@@ -195,10 +208,10 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
       cur_key = key;
       __syncthreads();
     }
-    ptx::mbar_wait(bar_in + 8u * slot, (it / NIN) & 1u);
+    ptx::mbar_wait(bar_in + 8u * slot, ring_ph);
     const uint8_t* in = gbase + slot * IN_BUF;
-    const uint8_t* res = gbase + NIN * IN_BUF;
-    uint8_t* out = gbase + NIN * IN_BUF + OUT_BYTES + (it & 1u) * OUT_BYTES;
+    const uint8_t* res = gbase + NIN * IN_BUF + slot * res_ring;
+    uint8_t* out = gbase + NIN * IN_BUF + res_total + (it & 1u) * OUT_BUF;
 
     // the staging buffer (it & 1) was last read by the TMA store issued two tiles ago
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -211,12 +224,13 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
     __syncthreads();                 // input slot and residual buffer consumed, staging complete
     if (tid == 32) {                 // refill the ring (this thread owns all bulk loads)
       const int nxt = tile + ahead * (int)gridDim.x;
-      if (nxt < p.total_tiles) issue(nxt, (slot + ahead) % NIN);
+      if (nxt < p.total_tiles) issue(nxt, slot + ahead >= NIN ? slot + ahead - NIN : slot + ahead);
     }
     if (tid == 0) {                  // this thread owns all bulk stores
-      tma_store_box(&map_y, s_out + (it & 1u) * OUT_BYTES, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n);
+      tma_store_box(&map_y, s_out + (it & 1u) * OUT_BUF, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (++slot == NIN) { slot = 0; ring_ph ^= 1u; }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -393,10 +407,23 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
       rc = make_map(&mr, a.res.p, a.C, a.W, a.H, a.n_img, a.res.ld, a.res.img_stride, t.cb, TW, TH);
       if (rc) return rc;
     }
-    const size_t smem = 1024 + NIN * IN_BUF + 3 * OUT_BYTES + (9 * CB + CB) * 4 + 64;
+    // ring depth: as deep as two CTAs per SM allow (about 110 KB each), at most kMaxNin
+    t.in_buf = (HH * HW * t.cb * 2 + 1023) / 1024 * 1024;
+    t.out_buf = (TH * TW * t.cb * 2 + 1023) / 1024 * 1024;
+    const int budget = 112 * 1024;   // two CTAs per SM
+    const int fixed = 1024 + 2 * t.out_buf + (9 * CB + CB) * 4 + 64;
+    const int per_slot = t.in_buf + (t.has_res ? t.out_buf : 0);
+    t.nin = std::min(kMaxNin, (budget - fixed) / per_slot);
+    t.res_slots = t.has_res ? t.nin : 0;
+    if (t.nin < 2) {                 // wide channel block with a residual: one residual buffer, inputs double-buffered
+      t.nin = 2;
+      t.res_slots = 1;
+    }
+    const size_t smem = (size_t)fixed + (size_t)t.nin * t.in_buf + (size_t)t.res_slots * t.out_buf;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * CB + CB) * 4 + 64);
       if (e != cudaSuccess) return fail(DCFA_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set = true;
     }
