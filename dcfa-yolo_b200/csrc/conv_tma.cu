@@ -72,6 +72,8 @@ struct TmaConvArgs {
   uint32_t sbo;           // 8 rows * row pitch
   FastDiv div_tw, div_tiles_img, div_tiles_x, div_ntiles;
   int tma_store;          // bf16 NHWC output written with TMA stores from a swizzled smem staging tile
+  int st256;              // bf16 NHWC output written with one 256-bit store per thread and 16-channel chunk: a whole
+                          // 32-byte sector per instruction, no staging, no barriers inside the epilogue group
   int cbox;               // channels per store slab (64 / 32 / 16)
   uint32_t out_stage_bytes;  // 128 rows * cbox * 2
   uint32_t tmem_cols;
@@ -324,7 +326,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] *= p.post_scale;
         }
-        if (p.tma_store) {
+        if (p.st256) {
+          if (rvalid && c0 < cvalid) {
+            uint4 lo, hi;
+            if (rb) {
+              uint32_t q[8];
+              asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                           : "l"(rb + c0));
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float2 f = unpack_bf16x2(q[e]);
+                v[2 * e] += f.x;
+                v[2 * e + 1] += f.y;
+              }
+            }
+            lo = pack8(v);
+            hi = pack8(v + 8);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yb + c0), "r"(lo.x), "r"(lo.y),
+                         "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                         : "memory");
+          }
+        } else if (p.tma_store) {
           // ---- stage 16 channels of this row into the swizzled slab; a full slab leaves with one TMA store
           const int cs = c0 & (p.cbox - 1);      // channel offset inside the slab (cbox is 16, 32 or 64)
           if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 0);
@@ -528,7 +551,18 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.a_tx_bytes = (uint32_t)(a.tw * a.th) * pitch;
   const int stage_bytes = (int)(a.a_stage_bytes + a.b_stage_bytes);
   const int max_smem = 227 * 1024;
-  a.tma_store = (a.out_mode == DCFA_OUT_BF16_NHWC && !a.res.p && a.y.gi <= 0) ? 1 : 0;
+  // epilogue store path for bf16 NHWC outputs
+  a.st256 = 0;
+  {
+    const char* e = getenv("DCFA_ST256");   // debug: DCFA_ST256=0 forces the TMA-store / 128-bit paths
+    const bool want = !(e && atoi(e) == 0);
+    const bool ok = a.out_mode == DCFA_OUT_BF16_NHWC && a.Cout % 16 == 0 && ((uintptr_t)a.y.p % 32) == 0 && a.y.ld % 16 == 0 &&
+                    a.y.img_stride % 16 == 0 && a.y.gstride % 16 == 0 &&
+                    (!a.res.p || (((uintptr_t)a.res.p % 32) == 0 && a.res.ld % 16 == 0 && a.res.img_stride % 16 == 0 &&
+                                  a.res.gstride % 16 == 0));
+    if (want && ok) a.st256 = 1;
+  }
+  a.tma_store = (!a.st256 && a.out_mode == DCFA_OUT_BF16_NHWC && !a.res.p && a.y.gi <= 0) ? 1 : 0;
   a.cbox = a.BN >= 64 ? 64 : a.BN;   // BN is 16, 32, 48 or a multiple of 64 below
   if (a.tma_store && (a.BN % a.cbox != 0 || (a.cbox != 64 && a.cbox != 32 && a.cbox != 16))) a.tma_store = 0;
   a.out_stage_bytes = 128u * (uint32_t)a.cbox * 2u;
