@@ -4,6 +4,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dcfa {
@@ -20,6 +22,15 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DCFA_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcfa {
 namespace {
@@ -28,6 +29,8 @@ constexpr int kU = 4;  // independent 128-bit loads in flight per thread in the 
 // threads; a thread keeps ONE 8-channel chunk for its whole life (its gate values stay in registers) and walks
 // pixels plane, plane + planes, ...   (c8n <= 256; threads beyond planes * c8n idle when 256 % c8n != 0)
 __global__ void __launch_bounds__(256) cbam_pool_kernel(const PoolArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float s_red[];  // [planes][2][C]
   const int c8n = p.C >> 3;          // <= 256 (C <= 2048)
   const int planes = 256 / c8n;
@@ -85,6 +88,8 @@ struct MlpArgs {
 };
 
 __global__ void __launch_bounds__(256) cbam_mlp_kernel(const MlpArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float s_mlp[];  // avg[C], max[C], hid[hidden]
   float* s_avg = s_mlp;
   float* s_max = s_mlp + p.C;
@@ -168,6 +173,8 @@ struct StatsArgs {
 // partials of one round of planes * kU pixels meet in shared memory ([pixel][c8n + 1] float2, double buffered:
 // one barrier per round) and one thread per pixel adds them up in channel order.
 __global__ void __launch_bounds__(256) cbam_stats_kernel(const StatsArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float2 s_part[];  // [2][planes * kU][c8n + 1]
   const int c8n = p.C >> 3;
   const int planes = 256 / c8n;
@@ -242,6 +249,8 @@ struct ApplyArgs {
 };
 
 __global__ void __launch_bounds__(256) cbam_apply_kernel(const ApplyArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float s_ap[];
   const int SW = p.W + 6;
   float* s_st = s_ap;                        // [RB+6][SW][2]
@@ -330,7 +339,7 @@ int launch_cbam_pool(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   const int planes = 256 / (a.C >> 3);
   const size_t smem = (size_t)planes * 2 * a.C * sizeof(float);
   DCFA_REQUIRE(smem <= 48 * 1024, "cbam_pool: shared memory %zu too large", smem);
-  cbam_pool_kernel<<<(unsigned)(a.n_img * a.parts), 256, smem, st>>>(a);
+  launch_pdl(cbam_pool_kernel, dim3((unsigned)(a.n_img * a.parts)), dim3(256), smem, st, a);
   DCFA_CHECK_LAUNCH("cbam_pool_kernel");
   return DCFA_OK;
 }
@@ -349,7 +358,7 @@ int launch_cbam_mlp(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(a.psum && a.pmax && a.fc1 && a.fc2 && a.gate, "cbam_mlp: missing tensor");
   DCFA_REQUIRE(a.hidden >= 1 && a.C >= 1, "cbam_mlp: bad sizes");
   const size_t smem = (size_t)(2 * a.C + a.hidden) * sizeof(float);
-  cbam_mlp_kernel<<<(unsigned)a.n_img, 256, smem, st>>>(a);
+  launch_pdl(cbam_mlp_kernel, dim3((unsigned)a.n_img), dim3(256), smem, st, a);
   DCFA_CHECK_LAUNCH("cbam_mlp_kernel");
   return DCFA_OK;
 }
@@ -375,7 +384,7 @@ int launch_cbam_stats(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.chunk = ceil_div(ceil_div(a.HW, chunks), round_px) * round_px;
   chunks = ceil_div(a.HW, a.chunk);
   const size_t smem = (size_t)2 * round_px * (c8n + 1) * sizeof(float2);
-  cbam_stats_kernel<<<dim3((unsigned)chunks, (unsigned)a.n_img), 256, smem, st>>>(a);
+  launch_pdl(cbam_stats_kernel, dim3((unsigned)chunks, (unsigned)a.n_img), dim3(256), smem, st, a);
   DCFA_CHECK_LAUNCH("cbam_stats_kernel");
   return DCFA_OK;
 }
@@ -399,7 +408,7 @@ int launch_cbam_apply(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.bands = ceil_div(a.H, RB);
   const size_t smem = (size_t)((RB + 6) * (a.W + 6) * 2 + RB * a.W + 98) * sizeof(float);
   DCFA_REQUIRE(smem <= 48 * 1024, "cbam_apply: image width %d too large", a.W);
-  cbam_apply_kernel<<<(unsigned)(a.n_img * a.bands), 256, smem, st>>>(a);
+  launch_pdl(cbam_apply_kernel, dim3((unsigned)(a.n_img * a.bands)), dim3(256), smem, st, a);
   DCFA_CHECK_LAUNCH("cbam_apply_kernel");
   return DCFA_OK;
 }

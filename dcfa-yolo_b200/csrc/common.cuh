@@ -3,6 +3,8 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <utility>
 #include <stdint.h>
 
 #include "../../include/dcfa_b200.h"
@@ -125,6 +127,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Kernel launch with the programmatic-dependent-launch attribute (see ptx::pdl_wait): EVERY kernel launched through
+// this helper executes griddepcontrol.wait before its first global access that depends on earlier work.
+// DCFA_PDL=0 in the environment falls back to plain stream-ordered launches (debugging).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // launchers implemented in the individual .cu files (host side; bufs already resolved by the caller)
 int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st);

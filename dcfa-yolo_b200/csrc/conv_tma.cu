@@ -162,10 +162,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   if (warp == kTmaWarp && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
   }
+  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -618,7 +620,7 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
   }
-  conv_tma_kernel<<<grid, kThreads, smem, st>>>(tmap, tmap_y, a);
+  launch_pdl(conv_tma_kernel, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
   DCFA_CHECK_LAUNCH("conv_tma_kernel");
   return DCFA_OK;
 }

@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
   const uint32_t bar_in = bars;               // nin barriers (input box [+ residual box] landed)
 
   const int tid = threadIdx.x;
+  ptx::pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < NIN; ++i) ptx::mbar_init(bar_in + 8u * i, 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
+  ptx::pdl_wait();
 
   const int row_bytes = p.cb * 2;             // bytes per pixel row in shared memory (dense, no swizzle)
   const uint32_t in_bytes = (uint32_t)(HH * HW) * row_bytes;
@@ -429,7 +431,7 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     }
     int64_t grid = (int64_t)sm_count() * 2;
     if (grid > total) grid = total;
-    dwconv_tma_kernel<<<(unsigned)grid, kDwThreads, smem, st>>>(mx, my, mr, t);
+    launch_pdl(dwconv_tma_kernel, dim3((unsigned)grid), dim3(kDwThreads), smem, st, mx, my, mr, t);
     DCFA_CHECK_LAUNCH("dwconv_tma_kernel");
     return DCFA_OK;
   }

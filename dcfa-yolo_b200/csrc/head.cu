@@ -5,6 +5,7 @@
 // Single pass, one thread per (image, anchor); every access is coalesced along the anchor axis.  fp32
 // throughout, exponentials with expf (not the fast intrinsic): the spec for this stage is 1e-5.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcfa {
 namespace {
@@ -18,6 +19,8 @@ struct DflArgs {
 };
 
 __global__ void __launch_bounds__(256) dfl_kernel(const DflArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)p.B * p.A) return;
   const int b = (int)(i / p.A);
@@ -103,7 +106,7 @@ int launch_dfl(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(tot == a.A, "dfl: anchors %d != level sizes %d", a.A, tot);
   DCFA_REQUIRE(a.nc >= 1, "dfl: nc must be >= 1");
   const int64_t total = (int64_t)a.B * a.A;
-  dfl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  launch_pdl(dfl_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a);
   DCFA_CHECK_LAUNCH("dfl_kernel");
   return DCFA_OK;
 }

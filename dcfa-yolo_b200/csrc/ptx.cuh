@@ -162,5 +162,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-serialization attribute may be
+// scheduled while its predecessor in the stream is still running: everything before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace ptx
+
 }  // namespace dcfa

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcfa {
 namespace {
@@ -37,6 +38,8 @@ struct Max8 {
 // horizontal 5-max of the last five input rows in registers -- 5 loads per input row instead of 25 per output.
 // grid = (ceil(W * C/8 / 256), strips, images)
 __global__ void __launch_bounds__(256) maxpool5_kernel(const PoolArgs5 p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int c8n = p.C >> 3;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= p.W * c8n) return;
@@ -114,6 +117,8 @@ constexpr int kUpRows = 4;
 
 template <bool TWO>
 __global__ void __launch_bounds__(256) upsample_kernel(const UpArgs p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int c8n = p.C >> 3;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= p.Wo * c8n) return;
@@ -171,7 +176,7 @@ int launch_maxpool5(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   strips = std::max(1, std::min(strips, ceil_div(a.H, 4)));
   a.strip = ceil_div(a.H, strips);
   strips = ceil_div(a.H, a.strip);
-  maxpool5_kernel<<<dim3((unsigned)bx, (unsigned)strips, (unsigned)a.n_img), 256, 0, st>>>(a);
+  launch_pdl(maxpool5_kernel, dim3((unsigned)bx, (unsigned)strips, (unsigned)a.n_img), dim3(256), 0, st, a);
   DCFA_CHECK_LAUNCH("maxpool5_kernel");
   return DCFA_OK;
 }
@@ -192,8 +197,8 @@ int launch_upsample(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.sx = a.Wo > 1 ? (float)(a.Wi - 1) / (float)(a.Wo - 1) : 0.0f;
   DCFA_REQUIRE(a.n_img <= 65535 && a.Ho <= 65535, "upsample: grid too large");
   const dim3 grid((unsigned)ceil_div(a.Wo * (a.C >> 3), 256), (unsigned)ceil_div(a.Ho, kUpRows), (unsigned)a.n_img);
-  if (a.b.p) upsample_kernel<true><<<grid, 256, 0, st>>>(a);
-  else upsample_kernel<false><<<grid, 256, 0, st>>>(a);
+  if (a.b.p) launch_pdl(upsample_kernel<true>, grid, dim3(256), 0, st, a);
+  else launch_pdl(upsample_kernel<false>, grid, dim3(256), 0, st, a);
   DCFA_CHECK_LAUNCH("upsample_kernel");
   return DCFA_OK;
 }

@@ -151,11 +151,13 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
+  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t idesc = ptx::make_idesc_bf16_f32(128, UMMA_N);
+  ptx::pdl_wait();
 
   // ---- static per-thread roles
   // im2col: thread m < NPIX builds GEMM column (row of the K-major B tile) m = cx*CH + cy
@@ -514,8 +516,8 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   }
   int64_t grid = (int64_t)sm_count() * kStemCtasPerSm;   // CTAs per SM bounded by TMEM columns (512 / kTmemCols)
   if (grid > total) grid = total;
-  if (u8) stem_kernel<true><<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
-  else stem_kernel<false><<<(unsigned)grid, kStemThreads, smem, st>>>(maps[0], maps[1], a);
+  if (u8) launch_pdl(stem_kernel<true>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], a);
+  else launch_pdl(stem_kernel<false>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], a);
   DCFA_CHECK_LAUNCH("stem_kernel");
   return DCFA_OK;
 }
