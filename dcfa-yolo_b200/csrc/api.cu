@@ -78,6 +78,26 @@ int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, vo
         return fail(DCFA_E_INVALID, "run_ops: op %d (kind %d) view %d references buffer %d (nbufs %d)", i, op.kind, k,
                     vs[k]->buf, nbufs);
     int rc;
+    // peephole: the four records of one CBAM run as a single cluster launch when the shape allows
+    if (op.kind == DCFA_OP_CBAM_POOL && i + 3 < n_ops && ops[i + 1].kind == DCFA_OP_CBAM_MLP &&
+        ops[i + 2].kind == DCFA_OP_CBAM_STATS && ops[i + 3].kind == DCFA_OP_CBAM_APPLY) {
+      bool ok = true;
+      for (int j = 1; j <= 3 && ok; ++j) {
+        const dcfa_op& o = ops[i + j];
+        const dcfa_view* ws[9] = {&o.x, &o.x2, &o.y, &o.w, &o.scale, &o.bias, &o.a0, &o.a1, &o.a2};
+        for (int k = 0; k < 9; ++k)
+          if (ws[k]->buf >= nbufs || (ws[k]->buf >= 0 && bufs[ws[k]->buf] == nullptr)) ok = false;
+      }
+      if (ok) {
+        rc = launch_cbam_fused(op, ops[i + 1], ops[i + 2], ops[i + 3], bufs, st);
+        if (rc < 0) {
+          char tmp[400];
+          snprintf(tmp, sizeof(tmp), "%s", dcfa_last_error());
+          return fail(rc, "op %d (fused cbam): %s", i, tmp);
+        }
+        if (rc == 1) { i += 3; continue; }
+      }
+    }
     switch (op.kind) {
       case DCFA_OP_STEM: rc = launch_stem(op, bufs, st); break;
       case DCFA_OP_CONV: rc = launch_conv(op, bufs, st); break;

@@ -7,6 +7,9 @@
 // Used at the six fusion sites (:346-353, :403-415) and inside SPPF_CBAM (:18-31, hidden width 1).
 // All channel accesses are 128-bit (8 x bf16); reductions are warp shuffles / fixed-order loops, so the
 // result is deterministic.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -222,16 +225,15 @@ __global__ void __launch_bounds__(256) cbam_stats_kernel(const StatsArgs p) {
       }
     }
     __syncthreads();
-    const int px = base + (int)threadIdx.x;
-    if ((int)threadIdx.x < round_px && px < q1) {
-      const float2* row = part + threadIdx.x * pitch;
+    for (int t = threadIdx.x; t < round_px && base + t < q1; t += 256) {
+      const float2* row = part + t * pitch;
       float sm = 0.0f, mx = -INFINITY;
       for (int k = 0; k < c8n; ++k) {
-        const float2 t = row[k];
-        sm += t.x;
-        mx = fmaxf(mx, t.y);
+        const float2 v = row[k];
+        sm += v.x;
+        mx = fmaxf(mx, v.y);
       }
-      *reinterpret_cast<float2*>(p.stats + ((int64_t)n * p.HW + px) * 2) = make_float2(sm * inv_c, mx);
+      *reinterpret_cast<float2*>(p.stats + ((int64_t)n * p.HW + base + t) * 2) = make_float2(sm * inv_c, mx);
     }
   }
 }
@@ -313,6 +315,268 @@ __global__ void __launch_bounds__(256) cbam_apply_kernel(const ApplyArgs p) {
         const float sp = s_s[lp];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= gt8[e] * sp;
+        stg128(yout + (int64_t)lp * p.y.ld, pack8(v));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fused CBAM
+// One thread-block CLUSTER per image runs the whole CBAM (pool -> MLP -> stats -> 7x7 -> apply) in one launch; the
+// four kernels above stay as the path for shapes it does not take.  CTA r of the cluster owns a band of image rows.
+//   A  channel sums / maxima of the band, combined across the cluster through DSMEM (fixed order: deterministic);
+//   B  the MLP, recomputed by every CTA (weights are L2-resident, C*hidden*2 floats);
+//   C  per-pixel mean/max over channels of x*gate for the band, into a zero-bordered stats tile in shared memory;
+//      the 3 halo rows on each side are read from the neighbouring CTAs' tiles through DSMEM;
+//   D  7x7 conv + sigmoid for the band's pixels;   E  y = x * gate * s  (x read a third time: L2).
+// The launch count of a forward drops by 21, and the per-launch fill/drain of three kernels per CBAM disappears.
+constexpr int kFusedThreads = 512;
+
+struct FusedArgs {
+  View<const __nv_bfloat16> x;
+  View<__nv_bfloat16> y;
+  const float* fc1;   // [G][hidden][C]
+  const float* fc2;   // [G][C][hidden]
+  const float* w7;    // [G][2][7][7]
+  int n_img, group_imgs, H, W, C, hidden;
+  int rows_per;       // image rows per CTA
+};
+
+__global__ void __launch_bounds__(kFusedThreads) cbam_fused_kernel(const FusedArgs p) {
+  extern __shared__ __align__(16) float s_f[];
+  namespace cg = cooperative_groups;
+  ptx::pdl_launch_dependents();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CS;
+  const int g = n / p.group_imgs;
+  const int tid = threadIdx.x;
+  const int C = p.C, W = p.W;
+  const int c8n = C >> 3;
+  const int planes = kFusedThreads / c8n;
+  const int c8 = tid % c8n, plane = tid / c8n;
+  const bool active = plane < planes;
+  const int y0 = min(p.H, crank * p.rows_per), y1 = min(p.H, y0 + p.rows_per);
+  const int npix = (y1 - y0) * W;
+  const int SW = W + 6, SR = p.rows_per + 6;
+  const int round_px = planes * kU;
+
+  // shared memory (floats)
+  float* part_sum = s_f;                       // [C]   this CTA's band
+  float* part_max = part_sum + C;              // [C]
+  float* s_avg = part_max + C;                 // [C]
+  float* s_max = s_avg + C;                    // [C]
+  float* s_gate = s_max + C;                   // [C]
+  float* s_hid = s_gate + C;                   // [hidden] (padded to a multiple of 4)
+  float* s_w = s_hid + ((p.hidden + 3) & ~3);  // [100]
+  float* s_st = s_w + 100;                     // [SR][SW][2] stats tile, zero border
+  float* s_sig = s_st + SR * SW * 2;           // [rows_per * W]
+  float* scratch = s_sig + ((p.rows_per * W + 3) & ~3);   // max(planes*2*C floats, 2*round_px*(c8n+1) float2)
+
+  ptx::pdl_wait();
+  const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + (int64_t)y0 * W * p.x.ld + c8 * 8;
+
+  // ---- A: channel sums / maxima of the band
+  {
+    float sm[8], mx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sm[e] = 0.0f; mx[e] = -INFINITY; }
+    if (active) {
+      for (int px = plane; px < npix; px += planes * kU) {
+        uint4 r[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (px + u * planes < npix) r[u] = ldg128(xin + (int64_t)(px + u * planes) * p.x.ld);
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (px + u * planes < npix) {
+            float v[8];
+            unpack8(r[u], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sm[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
+          }
+      }
+      float4* ds = reinterpret_cast<float4*>(scratch + (plane * 2 + 0) * C + c8 * 8);
+      float4* dm = reinterpret_cast<float4*>(scratch + (plane * 2 + 1) * C + c8 * 8);
+      ds[0] = make_float4(sm[0], sm[1], sm[2], sm[3]); ds[1] = make_float4(sm[4], sm[5], sm[6], sm[7]);
+      dm[0] = make_float4(mx[0], mx[1], mx[2], mx[3]); dm[1] = make_float4(mx[4], mx[5], mx[6], mx[7]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kFusedThreads) {
+      float ss = 0.0f, mm = -INFINITY;
+      for (int q = 0; q < planes; ++q) {
+        ss += scratch[(q * 2 + 0) * C + c];
+        mm = fmaxf(mm, scratch[(q * 2 + 1) * C + c]);
+      }
+      part_sum[c] = ss;
+      part_max[c] = mm;
+    }
+    for (int i = tid; i < 98; i += kFusedThreads) s_w[i] = __ldg(p.w7 + (int64_t)g * 98 + i);
+    for (int i = tid; i < SR * SW * 2; i += kFusedThreads) s_st[i] = 0.0f;
+  }
+  cluster.sync();
+  {
+    const float inv_hw = 1.0f / (float)(p.H * W);
+    for (int c = tid; c < C; c += kFusedThreads) {
+      float ss = 0.0f, mm = -INFINITY;
+      for (int r = 0; r < CS; ++r) {             // fixed order over the cluster: deterministic
+        ss += cluster.map_shared_rank(part_sum, r)[c];
+        mm = fmaxf(mm, cluster.map_shared_rank(part_max, r)[c]);
+      }
+      s_avg[c] = ss * inv_hw;
+      s_max[c] = mm;
+    }
+  }
+  __syncthreads();
+
+  // ---- B: fc1 -> ReLU -> fc2 on both vectors, add, sigmoid (fc2 is linear: one pass over relu(a)+relu(m))
+  {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = kFusedThreads >> 5;
+    for (int h = warp; h < p.hidden; h += nwarps) {
+      const float* w1 = p.fc1 + ((int64_t)g * p.hidden + h) * C;
+      float da = 0.0f, dm = 0.0f;
+      for (int c0 = lane; c0 < C; c0 += 32 * 8) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u * 32 < C) w[u] = __ldg(w1 + c0 + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u * 32 < C) {
+            da = fmaf(w[u], s_avg[c0 + u * 32], da);
+            dm = fmaf(w[u], s_max[c0 + u * 32], dm);
+          }
+      }
+      da = warp_sum(da);
+      dm = warp_sum(dm);
+      if (lane == 0) s_hid[h] = fmaxf(da, 0.0f) + fmaxf(dm, 0.0f);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kFusedThreads) {
+      const float* w2 = p.fc2 + ((int64_t)g * C + c) * p.hidden;
+      float o = 0.0f;
+      if ((p.hidden & 3) == 0 && ((uintptr_t)p.fc2 & 15) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(w2);
+        for (int h0 = 0; h0 < p.hidden; h0 += 16) {
+          float4 r[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (h0 + u * 4 < p.hidden) r[u] = __ldg(w4 + (h0 >> 2) + u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (h0 + u * 4 < p.hidden) {
+              const float* sh = s_hid + h0 + u * 4;
+              o = fmaf(r[u].x, sh[0], o); o = fmaf(r[u].y, sh[1], o); o = fmaf(r[u].z, sh[2], o); o = fmaf(r[u].w, sh[3], o);
+            }
+        }
+      } else {
+        for (int h = 0; h < p.hidden; ++h) o = fmaf(__ldg(w2 + h), s_hid[h], o);
+      }
+      s_gate[c] = 1.0f / (1.0f + expf(-o));
+    }
+  }
+  __syncthreads();
+
+  float g8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) g8[e] = s_gate[c8 * 8 + e];
+
+  // ---- C: per-pixel mean / max over channels of x * gate for the band -> interior of the stats tile
+  {
+    float2* part = reinterpret_cast<float2*>(scratch);
+    const int pitch = c8n + 1;
+    const float inv_c = 1.0f / (float)C;
+    int buf = 0;
+    for (int base = 0; base < npix; base += round_px, buf ^= 1) {
+      float2* pb = part + buf * round_px * pitch;
+      if (active) {
+        uint4 r[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int px = base + u * planes + plane;
+          if (px < npix) r[u] = ldg128(xin + (int64_t)px * p.x.ld);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int px = base + u * planes + plane;
+          if (px < npix) {
+            float v[8];
+            unpack8(r[u], v);
+            float sm = 0.0f, mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = v[e] * g8[e];
+              sm += t;
+              mx = fmaxf(mx, t);
+            }
+            pb[(u * planes + plane) * pitch + c8] = make_float2(sm, mx);
+          }
+        }
+      }
+      __syncthreads();
+      for (int t = tid; t < round_px && base + t < npix; t += kFusedThreads) {
+        const float2* row = pb + t * pitch;
+        float sm = 0.0f, mx = -INFINITY;
+        for (int k = 0; k < c8n; ++k) {
+          const float2 v = row[k];
+          sm += v.x;
+          mx = fmaxf(mx, v.y);
+        }
+        const int px = base + t;
+        const int ry = px / W, rx = px - ry * W;
+        *reinterpret_cast<float2*>(s_st + ((ry + 3) * SW + rx + 3) * 2) = make_float2(sm * inv_c, mx);
+      }
+    }
+  }
+  cluster.sync();
+  // halo rows: the last 3 rows of the band above, the first 3 rows of the band below (zero outside the image)
+  for (int i = tid; i < 6 * W; i += kFusedThreads) {
+    const int hr = i / W, rx = i - hr * W;               // hr 0..2 above, 3..5 below
+    const int gy = hr < 3 ? y0 - 3 + hr : y1 + hr - 3;   // image row
+    if (gy >= 0 && gy < p.H && y1 > y0) {
+      const int owner = gy / p.rows_per;
+      const int ly = gy - owner * p.rows_per;
+      const float2 v = *reinterpret_cast<const float2*>(cluster.map_shared_rank(s_st, owner) + ((ly + 3) * SW + rx + 3) * 2);
+      const int dr = hr < 3 ? hr : (y1 - y0) + hr;       // tile row
+      *reinterpret_cast<float2*>(s_st + (dr * SW + rx + 3) * 2) = v;
+    }
+  }
+  cluster.sync();   // no remote access to this CTA's shared memory after this point
+
+  // ---- D: 7x7 conv over (mean, max), sigmoid
+  for (int i = tid; i < npix; i += kFusedThreads) {
+    const int r = i / W, q = i - r * W;
+    float acc = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float2 sp = *reinterpret_cast<const float2*>(s_st + ((r + ky) * SW + q + kx) * 2);
+        acc = fmaf(s_w[ky * 7 + kx], sp.x, acc);
+        acc = fmaf(s_w[49 + ky * 7 + kx], sp.y, acc);
+      }
+    s_sig[i] = 1.0f / (1.0f + __expf(-acc));
+  }
+  __syncthreads();
+
+  // ---- E: y = x * gate * s
+  if (!active) return;
+  __nv_bfloat16* yout = p.y.p + p.y.img_off(n) + (int64_t)y0 * W * p.y.ld + c8 * 8;
+  for (int lp0 = plane; lp0 < npix; lp0 += planes * kU) {
+    uint4 r[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lp0 + u * planes < npix) r[u] = ldg128(xin + (int64_t)(lp0 + u * planes) * p.x.ld);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int lp = lp0 + u * planes;
+      if (lp < npix) {
+        float v[8];
+        unpack8(r[u], v);
+        const float sp = s_sig[lp];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= g8[e] * sp;
         stg128(yout + (int64_t)lp * p.y.ld, pack8(v));
       }
     }
@@ -411,6 +675,71 @@ int launch_cbam_apply(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   launch_pdl(cbam_apply_kernel, dim3((unsigned)(a.n_img * a.bands)), dim3(256), smem, st, a);
   DCFA_CHECK_LAUNCH("cbam_apply_kernel");
   return DCFA_OK;
+}
+
+// The four ops of one CBAM (consecutive POOL, MLP, STATS, APPLY records of the plan) as ONE cluster launch.
+// Returns 1 if the fused kernel was launched, 0 if the shape is left to the four separate kernels, < 0 on error.
+int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& stats, const dcfa_op& apply, void* const* bufs,
+                      cudaStream_t st) {
+  bool force = false;
+  {
+    const char* e = getenv("DCFA_CBAM_FUSED");   // debug / tests: 0 keeps the four-kernel path, 2 fuses even tiny batches
+    if (e && atoi(e) == 0) return 0;
+    force = e && atoi(e) == 2;
+  }
+  FusedArgs a;
+  a.x = resolve<const __nv_bfloat16>(apply.x, bufs);
+  a.y = resolve<__nv_bfloat16>(apply.y, bufs);
+  a.fc1 = resolve_ptr<const float>(mlp.w, bufs);
+  a.fc2 = resolve_ptr<const float>(mlp.scale, bufs);
+  a.w7 = resolve_ptr<const float>(apply.w, bufs);
+  a.n_img = apply.n_img;
+  a.group_imgs = apply.group_imgs > 0 ? apply.group_imgs : apply.n_img;
+  a.H = apply.Hi; a.W = apply.Wi; a.C = apply.Cin; a.hidden = mlp.hidden;
+  // the four records must describe the same tensor
+  const View<const __nv_bfloat16> xp = resolve<const __nv_bfloat16>(pool.x, bufs), xs = resolve<const __nv_bfloat16>(stats.x, bufs);
+  if (!(a.x.p && a.y.p && a.fc1 && a.fc2 && a.w7) || xp.p != a.x.p || xs.p != a.x.p || pool.n_img != a.n_img ||
+      stats.n_img != a.n_img || mlp.n_img != a.n_img || pool.Cin != a.C || stats.Cin != a.C || mlp.Cin != a.C ||
+      pool.Hi != a.H || pool.Wi != a.W || mlp.Hi != a.H || mlp.Wi != a.W)
+    return 0;
+  if (a.C % 8 != 0 || (a.C >> 3) > kFusedThreads || a.hidden < 1 || a.n_img > 65535) return 0;
+  if (!(view_aligned(a.x.p, a.x.ld, a.x.img_stride, a.x.gstride) && view_aligned(a.y.p, a.y.ld, a.y.img_stride, a.y.gstride)))
+    return 0;
+  // cluster size: as many CTAs per image as keep the whole grid within one wave, bands of at least 3 rows
+  int CS = 8;
+  while (CS > 1 && ((int64_t)a.n_img * CS > sm_count() || ceil_div(a.H, CS) < 3)) CS >>= 1;
+  if (!force && (int64_t)a.n_img * CS < sm_count() / 4) return 0;   // too few CTAs to fill the GPU: keep the wide kernels
+  a.rows_per = ceil_div(a.H, CS);
+  const int c8n = a.C >> 3, planes = kFusedThreads / c8n, round_px = planes * kU;
+  const size_t scratch = std::max((size_t)planes * 2 * a.C, (size_t)2 * round_px * (c8n + 1) * 2);
+  const size_t floats = (size_t)5 * a.C + ((a.hidden + 3) & ~3) + 100 + (size_t)(a.rows_per + 6) * (a.W + 6) * 2 +
+                        ((a.rows_per * a.W + 3) & ~3) + scratch;
+  const size_t smem = floats * sizeof(float);
+  if (smem > 200 * 1024) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(cbam_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.n_img * CS));
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, cbam_fused_kernel, a);
+  if (le != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: launch (cluster %d, smem %zu): %s", CS, smem, cudaGetErrorString(le));
+  count_launch();
+  return 1;
 }
 
 }  // namespace dcfa

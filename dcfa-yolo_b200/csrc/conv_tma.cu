@@ -352,13 +352,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         } else if (p.tma_store) {
           // ---- stage 16 channels of this row into the swizzled slab; a full slab leaves with one TMA store
           const int cs = c0 & (p.cbox - 1);      // channel offset inside the slab (cbox is 16, 32 or 64)
-          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 0);
           if (cs == 0) {
             // the slab buffer about to be overwritten was read by the TMA store issued two slabs ago
             if (gtid == 0) bulk_wait_read<1>();
             ptx::named_bar_sync(1 + group, 128);
           }
-          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 1);
           const uint32_t pitch = (uint32_t)p.cbox * 2u;
           const uint32_t rowb = stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes + (uint32_t)r * pitch;
           // Swizzle<B,4,3>: 16-byte chunk index XOR (row bits above the 128-byte line)
@@ -371,18 +369,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (((ch + 1u) ^ xr) << 4)), "r"(hi.x),
                        "r"(hi.y), "r"(hi.z), "r"(hi.w)
                        : "memory");
-          if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 2);
           if (cs + 16 == p.cbox) {   // slab complete
             ptx::fence_proxy_async_smem();
-            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 3);
             ptx::named_bar_sync(1 + group, 128);
-            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 4);
             if (gtid == 0 && nt * p.BN + c0 + 16 - p.cbox < p.Cout) {
               tma_store_4d(&tmap_y, stage_out + (uint32_t)(group * 2 + (int)(slab & 1u)) * p.out_stage_bytes,
                            nt * p.BN + c0 + 16 - p.cbox, tx * p.tw, ty * p.th, n);
             }
             if (gtid == 0) bulk_commit();
-            if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 5);
             ++slab;
           }
         } else if (rvalid && c0 < cvalid) {
@@ -409,13 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       ptx::tmem_ld_x16(taddr0, accA);
       for (int j = 0; j < nchunks; j += 2) {
         ptx::tmem_ld_wait();
-        if (group == 0 && gtid == 0 && j < 2) TL(6, 16 * (tcount >> 1) + 8 * j + 6);
         if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), accB);  // prefetch the next chunk
         process(accA, j);
         __syncwarp();
         if (j + 1 < nchunks) {
           ptx::tmem_ld_wait();
-          if (group == 0 && gtid == 0 && j + 1 < 2) TL(6, 16 * (tcount >> 1) + 8 * (j + 1) + 6);
           if (j + 2 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2) * 16), accA);
           process(accB, j + 1);
           __syncwarp();

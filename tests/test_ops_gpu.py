@@ -239,10 +239,15 @@ def _cbam_ref(x, fc1, fc2, w7):
     return t * torch.sigmoid(F.conv2d(p, w7, padding=3))
 
 
-@pytest.mark.parametrize("b,h,w,c,hidden,groups", [(2, 20, 20, 128, 1, 2), (1, 80, 80, 64, 8, 2), (2, 12, 28, 256, 32, 1)])
-def test_cbam_chain(cuda, b, h, w, c, hidden, groups):
-    """pool -> mlp -> stats -> apply, two modalities writing adjacent channel slots of one concat buffer."""
+@pytest.mark.parametrize("fused", ["0", "2"])
+@pytest.mark.parametrize("b,h,w,c,hidden,groups", [(2, 20, 20, 128, 1, 2), (1, 80, 80, 64, 8, 2), (2, 12, 28, 256, 32, 1),
+                                                   (3, 20, 20, 512, 32, 2), (1, 7, 9, 32, 2, 1), (24, 40, 40, 128, 8, 2)])
+def test_cbam_chain(cuda, monkeypatch, b, h, w, c, hidden, groups, fused):
+    """pool -> mlp -> stats -> apply, two modalities writing adjacent channel slots of one concat buffer; as four
+    kernels ("0") and as the one-cluster-per-image fused kernel ("2": forced even where the heuristic would not pick it;
+    cluster sizes 8, 4, 2 and 1 occur across the cases)."""
     from dcfa_b200 import abi
+    monkeypatch.setenv("DCFA_CBAM_FUSED", fused)
     g = torch.Generator().manual_seed(21)
     n = b * groups
     x = bf16_round(torch.randn(n, c, h, w, generator=g))

@@ -34,13 +34,6 @@ for name in sys.argv[1:]:
         g, lt = t & 1, t >> 1
         e = b[4 + g, 4 * lt: 4 * lt + 4]
         print("          epi(group %d): start %d tfull_ok %d chunks_done %d end %d  | wait %d work %d" % (g, e[0], e[1], e[2], e[3], e[1] - e[0], e[2] - e[1]))
-    for lt in range(T // 2, T // 2 + 3):
-        f = b[6, 16 * lt: 16 * lt + 16]
-        e0 = b[4, 4 * lt + 1]
-        print("          fine(group 0, tile %d) rel. to tfull_ok: chunk0 ld_wait %d proc_start %d after_waitread+bar %d packed+sts %d fence %d bar %d tma_issued %d"
-              " | chunk1 ld_wait %d proc_start %d bar %d sts %d fence %d bar %d tma %d" % (
-                  2 * lt, f[6] - e0, f[0] - e0, f[1] - e0, f[2] - e0, f[3] - e0, f[4] - e0, f[5] - e0,
-                  f[14] - e0, f[8] - e0, f[9] - e0, f[10] - e0, f[11] - e0, f[12] - e0, f[13] - e0))
     n = min(2048, 46 * kb)
     print(" producer interval/kb: median %d | mma issue interval/kb: median %d | full lag median %d" % (
         np.median(np.diff(b[0, :n])), np.median(np.diff(b[2, :n])), np.median(b[1, :n] - b[0, :n])))
