@@ -66,6 +66,22 @@ __device__ __forceinline__ void tma_store_box(const CUtensorMap* map, uint32_t s
 struct DwTile {
   int cbi, tx, ty, n;
 };
+// Tile coordinates advanced incrementally (tile += gridDim.x): no divisions in the per-tile path.
+struct DwIter {
+  DwTile t, s;   // current tile, and the mixed-radix digits of the step
+  template <typename P>
+  __device__ __forceinline__ void init(const P& p, int tile, int step);
+  template <typename P>
+  __device__ __forceinline__ void advance(const P& p) {
+    t.cbi += s.cbi;
+    if (t.cbi >= p.cblocks) { t.cbi -= p.cblocks; t.tx += 1; }
+    t.tx += s.tx;
+    if (t.tx >= p.tiles_x) { t.tx -= p.tiles_x; t.ty += 1; }
+    t.ty += s.ty;
+    if (t.ty >= p.tiles_y) { t.ty -= p.tiles_y; t.n += 1; }
+    t.n += s.n;
+  }
+};
 __device__ __forceinline__ DwTile dw_decode(const DwTmaArgs& p, int tile) {
   DwTile t;
   t.cbi = tile % p.cblocks; tile /= p.cblocks;
@@ -75,10 +91,37 @@ __device__ __forceinline__ DwTile dw_decode(const DwTmaArgs& p, int tile) {
   return t;
 }
 
+template <typename P>
+__device__ __forceinline__ void DwIter::init(const P& p, int tile, int step) {
+  t = dw_decode(p, tile);
+  s = dw_decode(p, step);
+}
+
 // One thread = one 8-channel chunk (c8) of one tile column, R consecutive output rows (R * c8n * TW * parts == 256 * R
 // covers the TH x TW tile).  Per kernel column q the 3 weight vectors stay in registers while the thread walks
 // down R + 2 input rows, each input vector feeding up to 3 output rows: 3*(R+2) + 9 shared-memory loads for R
 // outputs instead of 27 per output.
+// Packed fp32 pairs: sm_100 executes fma.rn.f32x2 (two IEEE fp32 FMAs, one instruction) -- the depthwise kernel is
+// bound by instruction issue, and 9 of its ~18 instructions per output are FMAs.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_get(const F2& a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ void f2_fma(F2& acc, const F2& a, const F2& b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(b.v));
+}
+// 8 bf16 -> 4 fp32 pairs (element 2i in the low half of word i: shift; element 2i+1: mask)
+__device__ __forceinline__ void unpack8_f2(const uint4& q, F2* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = f2_make(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+
 template <int R>
 __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_t* in, const uint8_t* res, uint8_t* out,
                                                 const float* w_s, const float* b_s, int tid, int row_bytes) {
@@ -86,40 +129,45 @@ __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_
   const int c8 = tid % c8n;
   const int col = (tid / c8n) % TW;
   const int oy0 = (tid / (c8n * TW)) * R;
-  float acc[R][8];
+  F2 acc2[R][4];
   {
     const float4 b0 = *reinterpret_cast<const float4*>(b_s + c8 * 8);
     const float4 b1 = *reinterpret_cast<const float4*>(b_s + c8 * 8 + 4);
 #pragma unroll
     for (int o = 0; o < R; ++o) {
-      acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
-      acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+      acc2[o][0] = f2_make(b0.x, b0.y); acc2[o][1] = f2_make(b0.z, b0.w);
+      acc2[o][2] = f2_make(b1.x, b1.y); acc2[o][3] = f2_make(b1.z, b1.w);
     }
   }
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    float w[3][8];
+    F2 w[3][4];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float4 w0 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8 + 4);
-      w[r][0] = w0.x; w[r][1] = w0.y; w[r][2] = w0.z; w[r][3] = w0.w;
-      w[r][4] = w1.x; w[r][5] = w1.y; w[r][6] = w1.z; w[r][7] = w1.w;
+      w[r][0] = f2_make(w0.x, w0.y); w[r][1] = f2_make(w0.z, w0.w);
+      w[r][2] = f2_make(w1.x, w1.y); w[r][3] = f2_make(w1.z, w1.w);
     }
 #pragma unroll
     for (int ri = 0; ri < R + 2; ++ri) {
-      float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(in + ((oy0 + ri) * HW + col + q) * row_bytes + c8 * 16), v);
+      F2 v[4];
+      unpack8_f2(*reinterpret_cast<const uint4*>(in + ((oy0 + ri) * HW + col + q) * row_bytes + c8 * 16), v);
 #pragma unroll
       for (int o = 0; o < R; ++o) {
         const int r = ri - o;   // kernel row that maps input row ri to output row o (compile-time after unrolling)
         if (r >= 0 && r < 3) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(v[e], w[r][e], acc[o][e]);
+          for (int e = 0; e < 4; ++e) f2_fma(acc2[o][e], v[e], w[r][e]);
         }
       }
     }
   }
+  float acc[R][8];
+#pragma unroll
+  for (int o = 0; o < R; ++o)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f2_get(acc2[o][e], acc[o][2 * e], acc[o][2 * e + 1]);
 #pragma unroll
   for (int o = 0; o < R; ++o) {
     const int pp = (oy0 + o) * TW + col;
@@ -140,7 +188,11 @@ __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_
   }
 }
 
-__global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_x,
+// R = output rows per thread = channel block / 16; the narrower the block, the smaller the register tile and the
+// shared-memory footprint, so more CTAs fit an SM (the kernel is latency-bound: per tile it waits for a box, computes
+// and stores, with block-wide barriers in between).
+template <int R>
+__global__ void __launch_bounds__(kDwThreads, R == 4 ? 2 : (R == 2 ? 3 : 4)) dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                    const __grid_constant__ CUtensorMap map_y,
                                                                    const __grid_constant__ CUtensorMap map_r,
                                                                    const DwTmaArgs p) {
@@ -174,8 +226,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
   const uint32_t in_bytes = (uint32_t)(HH * HW) * row_bytes;
   const uint32_t out_bytes = (uint32_t)(TH * TW) * row_bytes;
 
-  auto issue = [&](int tile, int slot) {      // one thread: input halo box (+ residual box) of `tile`
-    const DwTile t = dw_decode(p, tile);
+  auto issue = [&](const DwTile& t, int slot) {   // one thread: input halo box (+ residual box) of tile t
     const uint32_t bar = bar_in + 8u * slot;
     ptx::mbar_arrive_expect_tx(bar, in_bytes + (p.has_res ? out_bytes : 0u));
     tma_load_box(s_in + (uint32_t)slot * IN_BUF, &map_x, t.cbi * p.cb, t.tx * TW - 1, t.ty * TH - 1, t.n, bar);
@@ -184,21 +235,24 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
   // with a single residual buffer the residual box of tile i+2 must not land before tile i+1 consumed its own:
   // the ring then runs one tile ahead only
   const int ahead = (p.has_res && p.res_slots == 1) ? 1 : NIN - 1;
-  int tile = blockIdx.x;
+  DwIter cur, pre;                             // tile being processed; tile whose box is requested next (thread 32)
+  cur.init(p, blockIdx.x, gridDim.x);
+  pre = cur;
   if (tid == 32) {
-    for (int d = 0; d < ahead; ++d)
-      if (tile + d * (int)gridDim.x < p.total_tiles) issue(tile + d * (int)gridDim.x, d);
+    for (int d = 0; d < ahead; ++d) {
+      if (pre.t.n < p.n_img) issue(pre.t, d);
+      pre.advance(p);
+    }
   }
 
-  // per-thread mapping: 16-byte channel chunk c8 of output pixel (py, px); c8n chunks per pixel
-  const int c8n = p.cb >> 3;
   int cur_key = -1;
   uint32_t it = 0;
   int slot = 0;
   uint32_t ring_ph = 0;                        // parity of the ring pass `slot` is in
-  for (; tile < p.total_tiles; tile += gridDim.x, ++it) {
-    const DwTile t = dw_decode(p, tile);
-    const int g = t.n / p.group_imgs;
+  for (; cur.t.n < p.n_img; cur.advance(p), ++it) {
+    const DwTile t = cur.t;
+    int g = 0;
+    for (int nn = t.n; nn >= p.group_imgs; nn -= p.group_imgs) ++g;   // n / group_imgs without a division (1 or 2 groups)
     const int key = g * p.cblocks + t.cbi;
     if (key != cur_key) {                     // this (group, channel block)'s weights and bias
       __syncthreads();
@@ -219,14 +273,12 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_tma_kernel(const __grid_
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncthreads();
 
-    if (c8n == 8) dw_tile_compute<4>(p, in, res, out, w_s, b_s, tid, row_bytes);
-    else if (c8n == 4) dw_tile_compute<2>(p, in, res, out, w_s, b_s, tid, row_bytes);
-    else dw_tile_compute<1>(p, in, res, out, w_s, b_s, tid, row_bytes);
+    dw_tile_compute<R>(p, in, res, out, w_s, b_s, tid, row_bytes);
     ptx::fence_proxy_async_smem();   // staged tile -> async proxy (TMA store); no bulk loads are owned by these threads
     __syncthreads();                 // input slot and residual buffer consumed, staging complete
     if (tid == 32) {                 // refill the ring (this thread owns all bulk loads)
-      const int nxt = tile + ahead * (int)gridDim.x;
-      if (nxt < p.total_tiles) issue(nxt, slot + ahead >= NIN ? slot + ahead - NIN : slot + ahead);
+      if (pre.t.n < p.n_img) issue(pre.t, slot + ahead >= NIN ? slot + ahead - NIN : slot + ahead);
+      pre.advance(p);
     }
     if (tid == 0) {                  // this thread owns all bulk stores
       tma_store_box(&map_y, s_out + (it & 1u) * OUT_BUF, t.cbi * p.cb, t.tx * TW, t.ty * TH, t.n);
@@ -409,10 +461,11 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
       rc = make_map(&mr, a.res.p, a.C, a.W, a.H, a.n_img, a.res.ld, a.res.img_stride, t.cb, TW, TH);
       if (rc) return rc;
     }
-    // ring depth: as deep as two CTAs per SM allow (about 110 KB each), at most kMaxNin
+    // CTAs per SM by channel block (see the kernel's launch bounds); ring depth: as deep as that leaves room for
+    const int ctas = t.cb == 64 ? 2 : (t.cb == 32 ? 3 : 4);
     t.in_buf = (HH * HW * t.cb * 2 + 1023) / 1024 * 1024;
     t.out_buf = (TH * TW * t.cb * 2 + 1023) / 1024 * 1024;
-    const int budget = 112 * 1024;   // two CTAs per SM
+    const int budget = (227 * 1024) / ctas - 1536;
     const int fixed = 1024 + 2 * t.out_buf + (9 * CB + CB) * 4 + 64;
     const int per_slot = t.in_buf + (t.has_res ? t.out_buf : 0);
     t.nin = std::min(kMaxNin, (budget - fixed) / per_slot);
@@ -424,14 +477,18 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     const size_t smem = (size_t)fixed + (size_t)t.nin * t.in_buf + (size_t)t.res_slots * t.out_buf;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * CB + CB) * 4 + 64);
+      const int mx_smem = 1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * CB + CB) * 4 + 64;
+      cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e != cudaSuccess) return fail(DCFA_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set = true;
     }
-    int64_t grid = (int64_t)sm_count() * 2;
+    int64_t grid = (int64_t)sm_count() * ctas;
     if (grid > total) grid = total;
-    launch_pdl(dwconv_tma_kernel, dim3((unsigned)grid), dim3(kDwThreads), smem, st, mx, my, mr, t);
+    if (t.cb == 64) launch_pdl(dwconv_tma_kernel<4>, dim3((unsigned)grid), dim3(kDwThreads), smem, st, mx, my, mr, t);
+    else if (t.cb == 32) launch_pdl(dwconv_tma_kernel<2>, dim3((unsigned)grid), dim3(kDwThreads), smem, st, mx, my, mr, t);
+    else launch_pdl(dwconv_tma_kernel<1>, dim3((unsigned)grid), dim3(kDwThreads), smem, st, mx, my, mr, t);
     DCFA_CHECK_LAUNCH("dwconv_tma_kernel");
     return DCFA_OK;
   }
