@@ -52,11 +52,16 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("path", ["tma", "gather"])
+@pytest.mark.parametrize("path", ["tma", "tma-staged", "gather"])
 @pytest.mark.parametrize("n,h,w,cin,cout,k,s,act,groups", CONV_CASES)
-def test_conv_bf16_nhwc(cuda, n, h, w, cin, cout, k, s, act, groups, path):
-    """both A-operand paths: TMA box loads (one k-block per tap x channel block) and the cp.async gather (flat K)."""
+def test_conv_bf16_nhwc(cuda, monkeypatch, n, h, w, cin, cout, k, s, act, groups, path):
+    """both A-operand paths: TMA box loads (one k-block per tap x channel block) and the cp.async gather (flat K);
+    and both store paths of the TMA kernel: 256-bit sector stores (default) and the staged tile + TMA store
+    ("tma-staged": DCFA_ST256=0, the path taken by outputs that are not 32-byte aligned)."""
     from dcfa_b200 import abi
+    if path == "tma-staged":
+        monkeypatch.setenv("DCFA_ST256", "0")
+        path = "tma"
     g = torch.Generator().manual_seed(1234 + cin + cout + k + s)
     x = bf16_round(torch.randn(n, cin, h, w, generator=g))
     ws = [bf16_round(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5) for _ in range(groups)]
