@@ -306,25 +306,43 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
                        "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
                        : "memory");
       }
-    } else if (tid < NPIX) {
-      // ---- im2col: one conv pixel per thread, K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes
-      const float* pin = s_in + icy * PWB + icx + XOFF;
-      uint32_t pk[16];
+    } else if (tid < (CW + 1) / 2 * CH) {
+      // ---- im2col: two horizontally adjacent conv pixels per thread (columns 2q, 2q+1 of conv row cy): the 4 floats
+      //      of a (channel, kernel row) feeding both pixels are two aligned 64-bit loads instead of 2 x 3 scalar ones.
+      //      K index = (ky*3 + kx)*3 + ci, 27 taps + 5 zeros -> 4 x 16 bytes per pixel.
+      const int q = tid / CH, cy = tid - q * CH;
+      const int cx = 2 * q;
+      const float* pin = s_in + cy * PWB + cx + XOFF;   // even float index: 8-byte aligned
+      float f[3][3][4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v0 = 0.0f, v1 = 0.0f;
-        const int k0 = 2 * j, k1 = 2 * j + 1;   // compile-time after unrolling
-        if (k0 < 27) v0 = pin[((k0 % 3) * PH + (k0 / 9)) * PWB + ((k0 / 3) % 3)];
-        if (k1 < 27) v1 = pin[((k1 % 3) * PH + (k1 / 9)) * PWB + ((k1 / 3) % 3)];
-        pk[j] = pack_bf16x2(v0, v1);
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float2 a = *reinterpret_cast<const float2*>(pin + (ci * PH + ky) * PWB);
+          const float2 b = *reinterpret_cast<const float2*>(pin + (ci * PH + ky) * PWB + 2);
+          f[ci][ky][0] = a.x; f[ci][ky][1] = a.y; f[ci][ky][2] = b.x; f[ci][ky][3] = b.y;
+        }
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (px == 1 && cx + 1 >= CW) break;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = 0.0f, v1 = 0.0f;
+          const int k0 = 2 * j, k1 = 2 * j + 1;   // compile-time after unrolling
+          if (k0 < 27) v0 = f[k0 % 3][k0 / 9][(k0 / 3) % 3 + px];
+          if (k1 < 27) v1 = f[k1 % 3][k1 / 9][(k1 / 3) % 3 + px];
+          pk[j] = pack_bf16x2(v0, v1);
+        }
+        const int m = (cx + px) * CH + cy;
+        const uint32_t rowb = s_b + (uint32_t)m * KROW;
+        const uint32_t xr = (uint32_t)((m >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
+                       "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                       : "memory");
       }
-      const uint32_t rowb = s_b + (uint32_t)tid * KROW;
-      const uint32_t xr = (uint32_t)((tid >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
-                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                     : "memory");
     }
     __syncthreads();   // B tile (and A tile) written; the patch slot `buf` has been consumed
 
