@@ -51,6 +51,8 @@ FastDiv make_fastdiv(uint32_t d) {
 struct TmaConvArgs {
   View<const __nv_bfloat16> res;
   View<void> y;
+  View<__nv_bfloat16> y2;  // split output: channels >= split go to this view (channel 0 of y2 = channel `split`)
+  int split;               // 0 = single destination
   const __nv_bfloat16* w;
   const float* scale;
   const float* bias;
@@ -286,11 +288,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         ptx::named_bar_sync(1 + group, 128);
       }
       __nv_bfloat16* yb = nullptr;
+      __nv_bfloat16* yb2 = nullptr;   // split output: destination of channel c is yb2 + c for c >= split
       float* yf = nullptr;
       const __nv_bfloat16* rb = nullptr;
       if (rvalid) {
         if (p.out_mode == DCFA_OUT_BF16_NHWC) {
           yb = reinterpret_cast<__nv_bfloat16*>(p.y.p) + p.y.img_off(n) + (int64_t)pix * p.y.ld + nt * p.BN;
+          if (p.split > 0) yb2 = p.y2.p + p.y2.img_off(n) + (int64_t)pix * p.y2.ld + nt * p.BN - p.split;
           if (p.res.p) rb = p.res.p + p.res.img_off(n) + (int64_t)pix * p.res.ld + nt * p.BN;
         } else {
           yf = reinterpret_cast<float*>(p.y.p) + (int64_t)n * p.y.img_stride + (int64_t)(p.out_coff + nt * p.BN) * HoWo + pix;
@@ -345,7 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             }
             lo = pack8(v);
             hi = pack8(v + 8);
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yb + c0), "r"(lo.x), "r"(lo.y),
+            __nv_bfloat16* dst = (p.split > 0 && nt * p.BN + c0 >= p.split) ? yb2 + c0 : yb + c0;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y),
                          "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                          : "memory");
           }
@@ -477,6 +482,8 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   View<const __nv_bfloat16> x = resolve<const __nv_bfloat16>(op.x, bufs);
   a.res = resolve<const __nv_bfloat16>(op.x2, bufs);
   a.y = resolve<void>(op.y, bufs);
+  a.y2 = resolve<__nv_bfloat16>(op.a0, bufs);
+  a.split = op.parts;
   a.w = resolve_ptr<const __nv_bfloat16>(op.w, bufs);
   a.scale = resolve_ptr<const float>(op.scale, bufs);
   a.bias = resolve_ptr<const float>(op.bias, bufs);
@@ -555,6 +562,12 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
                     (!a.res.p || (((uintptr_t)a.res.p % 32) == 0 && a.res.ld % 16 == 0 && a.res.img_stride % 16 == 0 &&
                                   a.res.gstride % 16 == 0));
     if (want && ok) a.st256 = 1;
+  }
+  if (a.split > 0) {
+    DCFA_REQUIRE(a.y2.p && a.split % 16 == 0 && a.split < a.Cout && !a.res.p, "conv(tma): bad split output");
+    DCFA_REQUIRE(((uintptr_t)a.y2.p % 32) == 0 && a.y2.ld % 16 == 0 && a.y2.img_stride % 16 == 0 && a.y2.gstride % 16 == 0,
+                 "conv(tma): split destination must be 32-byte aligned");
+    DCFA_REQUIRE(a.st256, "conv(tma): split output needs the 256-bit store path (aligned bf16 NHWC destinations)");
   }
   a.tma_store = (!a.st256 && a.out_mode == DCFA_OUT_BF16_NHWC && !a.res.p && a.y.gi <= 0) ? 1 : 0;
   a.cbox = a.BN >= 64 ? 64 : a.BN;   // BN is 16, 32, 48 or a multiple of 64 below

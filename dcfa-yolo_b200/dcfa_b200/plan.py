@@ -115,9 +115,10 @@ class Plan:
         out[:, src.perm_tensor()] = w
         return out
 
-    def conv(self, name, src, dst, groups, k, stride, act, res=None, f32_out=None, post_scale=1.0):
+    def conv(self, name, src, dst, groups, k, stride, act, res=None, f32_out=None, post_scale=1.0, split=None):
         """groups: list (1 or 2 entries) of (weight [Cout,Cin,k,k] logical order, scale [Cout], bias [Cout],
-        col_scale or None).  dst: TRef (bf16 NHWC) or None with f32_out = (buf, ctot, coff)."""
+        col_scale or None).  dst: TRef (bf16 NHWC) or None with f32_out = (buf, ctot, coff).
+        split = (c, TRef): output channels from c on go to that second tensor instead of dst[..., c:]."""
         packed, meta = [], None
         scs, bis = [], []
         for (w, sc, bi, col) in groups:
@@ -142,6 +143,11 @@ class Plan:
             assert dst.n == src.n and dst.h == ho and dst.w == wo and dst.c == meta['Cout'], name
             op.out_mode = abi.OUT_BF16_NHWC
             op.y = dst.view()
+            if split is not None:
+                c_split, dst2 = split
+                assert res is None and dst2.c == meta['Cout'] - c_split and dst2.n == dst.n and dst2.h == ho and dst2.w == wo
+                op.parts = c_split
+                op.a0 = dst2.view()
         else:
             buf, ctot, coff = f32_out
             op.out_mode = abi.OUT_F32_NCHW
@@ -209,12 +215,14 @@ class Plan:
         sc, bi = self._bn(prefix + '.bn', eps)
         return (self.sd[prefix + '.conv.weight'], sc, bi, col_scale)
 
-    def _shuffle_unit(self, name, x, prefixes):
-        """ShuffleNetV2 stride-1 unit, in place on x (nets/yolo_mul.py:138-168).  Returns x with the shuffle perm."""
+    def _shuffle_unit(self, name, x, prefixes, x2_src=None):
+        """ShuffleNetV2 stride-1 unit (nets/yolo_mul.py:138-168): branch 2 reads x2_src (or, in place, the second half
+        of x) and writes the second half of x.  Returns x with the shuffle perm."""
         s = self.sd
         c = x.c
         h = c // 2
         x2 = x.sub(h, h)
+        x2_in = x2_src if x2_src is not None else x2
         t1 = self._tensor(x.n, x.h, x.w, h)
         t2 = self._tensor(x.n, x.h, x.w, h)
         g0, gdw, g2 = [], [], []
@@ -226,7 +234,7 @@ class Plan:
             gdw.append((s[b + '.3.weight'] * sc.view(-1, 1, 1, 1), s[b + '.3.bias'] * sc + bi))
             sc, bi = self._bn(b + '.6', 1e-5)
             g2.append((s[b + '.5.weight'], sc, bi, None))
-        self.conv(name + '.pw1', x2, t1, g0, 1, 1, abi.ACT_RELU)
+        self.conv(name + '.pw1', x2_in, t1, g0, 1, 1, abi.ACT_RELU)
         self.dwconv(name + '.dw', t1, t2, gdw, abi.ACT_NONE)
         self.conv(name + '.pw2', t2, x2, g2, 1, 1, abi.ACT_RELU)
         # logical channel l of the shuffled tensor: even -> x1[l/2], odd -> branch2[(l-1)/2]
@@ -297,9 +305,18 @@ class Plan:
         # ---- dark2..dark5 (nets/yolo_mul.py:258-277)
         feats = {}
         for stage, cout in (('dark2', 2 * bc), ('dark3', c3), ('dark4', c4), ('dark5', c5)):
+            # The stage conv writes its first half straight into the unit's output tensor and its second half (the
+            # unit's branch-2 input) into a separate tensor: the fused unit kernel reads halo pixels of its input
+            # while neighbouring tiles already write their outputs, so input and output must not alias.
             y = self._tensor(N2, down2(x.h), down2(x.w), cout)
-            self.conv(stage + '.0', x, y, [self._conv_group('%s.%s.0' % (m, stage), 1e-3) for m in mods], 3, 2, abi.ACT_SILU)
-            x = self._shuffle_unit(stage + '.1', y, ['%s.%s.1' % (m, stage) for m in mods])
+            y2 = self._tensor(N2, down2(x.h), down2(x.w), cout // 2)
+            groups = [self._conv_group('%s.%s.0' % (m, stage), 1e-3) for m in mods]
+            if (cout // 2) % 16 == 0:
+                self.conv(stage + '.0', x, y, groups, 3, 2, abi.ACT_SILU, split=(cout // 2, y2))
+            else:   # 16-channel granularity of the split store: narrow models copy through the unfused path
+                self.conv(stage + '.0', x, y, groups, 3, 2, abi.ACT_SILU)
+                y2 = None
+            x = self._shuffle_unit(stage + '.1', y, ['%s.%s.1' % (m, stage) for m in mods], y2)
             feats[stage] = x
         feat1, feat2 = feats['dark3'], feats['dark4']
 

@@ -110,6 +110,8 @@ typedef struct dcfa_view {
  *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
  *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added
  *        after the activation; y = output (out_mode).  f0 = post-activation scale (1.0 = none).
+ *        parts > 0 (bf16 NHWC, TMA path only): SPLIT output -- channels [0, parts) go to y, channels [parts, Cout) to
+ *        the view a0 (whose channel 0 is channel `parts`); parts % 16 == 0.
  * DWCONV x -> y depthwise 3x3 s1 p1, w = fp32 [G][9][Cin] (BN folded), bias = fp32 [G][Cin], act,
  *        x2 = optional residual (added after activation).
  * CBAM_POOL   x -> a0 = fp32 [n_img][parts][Cin] sums, a1 = same shape maxima; parts pixel chunks.

@@ -116,7 +116,11 @@ def run_ops(ops, bufs):
                 y = y.permute(0, 2, 3, 1)
                 if op.x2.buf >= 0:
                     y = y + read_nhwc(bufs, op.x2, n, op.Ho, op.Wo, op.Cout)
-                write_nhwc(bufs, op.y, y)
+                if op.parts > 0:   # split output: the channels from `parts` on go to the second view
+                    write_nhwc(bufs, op.y, y[..., :op.parts])
+                    write_nhwc(bufs, op.a0, y[..., op.parts:])
+                else:
+                    write_nhwc(bufs, op.y, y)
             else:
                 dst = bufs[op.y.buf].view(torch.float32).view(n, op.out_ctot, op.Ho, op.Wo)
                 dst[:, op.out_coff:op.out_coff + op.Cout] = y
