@@ -98,6 +98,26 @@ int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, vo
         if (rc == 1) { i += 3; continue; }
       }
     }
+    // peephole: 1x1 conv -> depthwise -> 1x1 conv chains the plan marked as private run as one fused kernel
+    if (op.kind == DCFA_OP_CONV && (op.flags & DCFA_CONV_FLAG_CHAIN_HEAD) && i + 2 < n_ops && ops[i + 1].kind == DCFA_OP_DWCONV &&
+        ops[i + 2].kind == DCFA_OP_CONV) {
+      bool ok = true;
+      for (int j = 1; j <= 2 && ok; ++j) {
+        const dcfa_op& o = ops[i + j];
+        const dcfa_view* ws[9] = {&o.x, &o.x2, &o.y, &o.w, &o.scale, &o.bias, &o.a0, &o.a1, &o.a2};
+        for (int k = 0; k < 9; ++k)
+          if (ws[k]->buf >= nbufs || (ws[k]->buf >= 0 && bufs[ws[k]->buf] == nullptr)) ok = false;
+      }
+      if (ok) {
+        rc = launch_chain(op, ops[i + 1], ops[i + 2], bufs, st);
+        if (rc < 0) {
+          char tmp[400];
+          snprintf(tmp, sizeof(tmp), "%s", dcfa_last_error());
+          return fail(rc, "op %d (fused chain): %s", i, tmp);
+        }
+        if (rc == 1) { i += 2; continue; }
+      }
+    }
     switch (op.kind) {
       case DCFA_OP_STEM: rc = launch_stem(op, bufs, st); break;
       case DCFA_OP_CONV: rc = launch_conv(op, bufs, st); break;

@@ -112,6 +112,27 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return v;
 }
 
+// Packed fp32 pairs: sm_100 executes fma.rn.f32x2 (two IEEE fp32 FMAs, one instruction) -- the depthwise kernel is
+// bound by instruction issue, and 9 of its ~18 instructions per output are FMAs.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_get(const F2& a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ void f2_fma(F2& acc, const F2& a, const F2& b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(b.v));
+}
+// 8 bf16 -> 4 fp32 pairs (element 2i in the low half of word i: shift; element 2i+1: mask)
+__device__ __forceinline__ void unpack8_f2(const uint4& q, F2* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = f2_make(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg128(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
@@ -152,6 +173,7 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void* const* bufs, cudaStream_t st);
 int launch_cbam_pool(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_mlp(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_stats(const dcfa_op& op, void* const* bufs, cudaStream_t st);

@@ -101,27 +101,6 @@ __device__ __forceinline__ void DwIter::init(const P& p, int tile, int step) {
 // covers the TH x TW tile).  Per kernel column q the 3 weight vectors stay in registers while the thread walks
 // down R + 2 input rows, each input vector feeding up to 3 output rows: 3*(R+2) + 9 shared-memory loads for R
 // outputs instead of 27 per output.
-// Packed fp32 pairs: sm_100 executes fma.rn.f32x2 (two IEEE fp32 FMAs, one instruction) -- the depthwise kernel is
-// bound by instruction issue, and 9 of its ~18 instructions per output are FMAs.
-struct F2 {
-  unsigned long long v;
-};
-__device__ __forceinline__ F2 f2_make(float lo, float hi) {
-  F2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_get(const F2& a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-__device__ __forceinline__ void f2_fma(F2& acc, const F2& a, const F2& b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(b.v));
-}
-// 8 bf16 -> 4 fp32 pairs (element 2i in the low half of word i: shift; element 2i+1: mask)
-__device__ __forceinline__ void unpack8_f2(const uint4& q, F2* v) {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = f2_make(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
-}
-
 template <int R>
 __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_t* in, const uint8_t* res, uint8_t* out,
                                                 const float* w_s, const float* b_s, int tid, int row_bytes) {

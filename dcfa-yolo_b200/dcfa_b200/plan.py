@@ -235,6 +235,8 @@ class Plan:
             sc, bi = self._bn(b + '.6', 1e-5)
             g2.append((s[b + '.5.weight'], sc, bi, None))
         self.conv(name + '.pw1', x2_in, t1, g0, 1, 1, abi.ACT_RELU)
+        if x2_src is not None:   # t1, t2 are private and the output does not alias the input: fusable chain
+            self.ops[-1].flags |= abi.CONV_FLAG_CHAIN_HEAD
         self.dwconv(name + '.dw', t1, t2, gdw, abi.ACT_NONE)
         self.conv(name + '.pw2', t2, x2, g2, 1, 1, abi.ACT_RELU)
         # logical channel l of the shuffled tensor: even -> x1[l/2], odd -> branch2[(l-1)/2]

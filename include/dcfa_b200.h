@@ -74,6 +74,11 @@ enum { DCFA_ACT_NONE = 0, DCFA_ACT_RELU = 1, DCFA_ACT_SILU = 2 };
  * utils/utils.py:9-37, before preprocess_input's /255, which the caller folds into `scale`) instead of fp32 NCHW */
 enum { DCFA_STEM_FLAG_U8 = 0x100 };
 
+/* DCFA_OP_CONV flags (above the low 8 bits, which hold the k-block width of the TMA packing): this 1x1 conv, the DWCONV
+ * after it and the 1x1 CONV after that form a chain whose two intermediate tensors nobody else reads and whose output
+ * does not alias its input -- dcfa_run_ops may run the three records as one fused kernel */
+enum { DCFA_CONV_FLAG_CHAIN_HEAD = 0x400 };
+
 /* DCFA_OP_CONV output modes */
 enum { DCFA_OUT_BF16_NHWC = 0, DCFA_OUT_F32_NCHW = 1 };
 

@@ -44,17 +44,21 @@ def main():
     want = a.ops.split(",")
     torch.cuda.profiler.start()   # ncu --profile-from-start off: only the selected ops are captured
     for name in want:
+        count = 1
+        if "+" in name:   # "dark2.1.pw1+3": three consecutive records in one call (lets the dispatcher fuse them)
+            name, cnt = name.split("+")
+            count = int(cnt)
         idx = [i for i, n in enumerate(eng.plan.op_names) if n == name]
         if not idx:
             print("no op named", name, "; have:", eng.plan.op_names)
             continue
         i = idx[0]
-        op1 = (abi.Op * 1)(eng.plan.ops[i])
+        op1 = (abi.Op * count)(*eng.plan.ops[i:i + count])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ts = []
         for _ in range(a.iters):
             e0.record(st)
-            _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+            _lib.check(_lib.lib.dcfa_run_ops(op1, count, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
             e1.record(st)
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
