@@ -80,14 +80,14 @@ __device__ __forceinline__ void chain_tma_load(uint32_t dst, const CUtensorMap* 
 
 // depthwise 3x3 over the GEMM-1 tile for one block of 8*R... see dw_tile_compute in dwconv.cu: one thread = one
 // 8-channel chunk of one tile column, R consecutive output rows; results go into the swizzled A tile of GEMM 2.
-template <int R>
+template <int R, int CT>
 __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, uint32_t s_a2, const float* wd_s, const float* bd_s,
                                          int c8_base, int tid) {
   constexpr int C8N = 2 * R;                 // chunks handled per pass: 4 (R = 2) or 8 (R = 4)
   const int c8 = c8_base + tid % C8N;
   const int col = (tid / C8N) % TW;
   const int oy0 = (tid / (C8N * TW)) * R;
-  const int C = p.C;
+  constexpr int C = CT;
   F2 acc[R][4];
   {
     const float4 b0 = *reinterpret_cast<const float4*>(bd_s + c8 * 8);
@@ -141,13 +141,16 @@ __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, 
   }
 }
 
-__global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_constant__ CUtensorMap map_x, const ChainArgs p) {
+// CT = channel count (compile time: loop bounds, shifts and the register tile follow it); CTAs per SM by CT
+template <int CT>
+__global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 1)) chain_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                                             const ChainArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gb = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t s_xa = base, s_a2 = base + p.off_a2, s_w1 = base + p.off_w1, s_w2 = base + p.off_w2;
   uint8_t* t1 = gb + p.off_t1;
-  const int C = p.C;
+  constexpr int C = CT;
   float* wd_s = reinterpret_cast<float*>(gb + p.off_par);   // [9][C]
   float* bd_s = wd_s + 9 * C;
   float* s1_s = bd_s + C;
@@ -273,9 +276,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
 
     // ---- depthwise 3x3 -> A tile of GEMM 2
     if (C == 32) {
-      chain_dw<2>(p, t1, s_a2, wd_s, bd_s, 0, tid);
+      chain_dw<2, CT>(p, t1, s_a2, wd_s, bd_s, 0, tid);
     } else {
-      for (int cb = 0; cb < (C >> 3); cb += 8) chain_dw<4>(p, t1, s_a2, wd_s, bd_s, cb, tid);
+#pragma unroll
+      for (int cb = 0; cb < (C >> 3); cb += 8) chain_dw<4, CT>(p, t1, s_a2, wd_s, bd_s, cb, tid);
     }
     __syncthreads();
 
@@ -445,14 +449,19 @@ int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int ctas = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+  const int ctas = C == 32 ? 3 : (C == 64 ? 2 : 1);   // matches the kernel's launch bounds; shared memory allows it
   int64_t grid = (int64_t)sm_count() * ctas;
   if (grid > total) grid = total;
-  cudaError_t le = launch_pdl(chain_kernel, dim3((unsigned)grid), dim3(kChainThreads), smem, st, map, a);
+  const dim3 g3((unsigned)grid), b3(kChainThreads);
+  cudaError_t le = C == 32 ? launch_pdl(chain_kernel<32>, g3, b3, smem, st, map, a)
+                           : (C == 64 ? launch_pdl(chain_kernel<64>, g3, b3, smem, st, map, a)
+                                      : launch_pdl(chain_kernel<128>, g3, b3, smem, st, map, a));
   if (le != cudaSuccess) return fail(DCFA_E_CUDA, "chain: launch: %s", cudaGetErrorString(le));
   le = cudaGetLastError();
   if (le != cudaSuccess) return fail(DCFA_E_CUDA, "chain_kernel launch failed: %s", cudaGetErrorString(le));
