@@ -217,26 +217,46 @@ def profile_ops(net, batch, size, device, iters=5):
     nir = torch.rand(batch, 3, size, size, device=device)
     eng.run(rgb, nir)
     torch.cuda.synchronize()
-    n = eng.n_ops
     st = torch.cuda.current_stream(device)
+    # Records the dispatcher runs as ONE kernel are timed together: the four records of a CBAM, and a 1x1 conv ->
+    # depthwise -> 1x1 conv chain the plan marked as private (if the shape falls back to separate kernels the group
+    # is still what one dcfa_run_ops call executes).
+    ops, names = eng.plan.ops, eng.plan.op_names
+    groups, i = [], 0
+    while i < len(ops):
+        k = ops[i].kind
+        if (k == abi.OP_CBAM_POOL and i + 3 < len(ops) and
+                [o.kind for o in ops[i + 1:i + 4]] == [abi.OP_CBAM_MLP, abi.OP_CBAM_STATS, abi.OP_CBAM_APPLY]):
+            groups.append((i, 4, "cbam", names[i].rsplit(".", 1)[0]))
+            i += 4
+        elif (k == abi.OP_CONV and (ops[i].flags & abi.CONV_FLAG_CHAIN_HEAD) and i + 2 < len(ops) and
+              ops[i + 1].kind == abi.OP_DWCONV and ops[i + 2].kind == abi.OP_CONV):
+            groups.append((i, 3, "chain", names[i].rsplit(".", 1)[0]))
+            i += 3
+        else:
+            groups.append((i, 1, abi.OP_NAMES[k], names[i]))
+            i += 1
+    n = len(groups)
+    arrays = [(abi.Op * cnt)(*ops[i0:i0 + cnt]) for (i0, cnt, _, _) in groups]
     tot = np.zeros(n)
     for _ in range(iters):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         evs[0].record(st)
-        for i in range(n):
-            op1 = (abi.Op * 1)(eng.plan.ops[i])
-            _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
-            evs[i + 1].record(st)
+        for gi, (i0, cnt, _, _) in enumerate(groups):
+            _lib.check(_lib.lib.dcfa_run_ops(arrays[gi], cnt, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+            evs[gi + 1].record(st)
         torch.cuda.synchronize()
         tot += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n)])
     ms = tot / iters
     rows = []
-    for i, op in enumerate(eng.plan.ops):
+    for gi, (i0, cnt, kind, name) in enumerate(groups):
+        op = ops[i0]
         flops = 0
-        if op.kind == abi.OP_CONV:
+        if kind == "conv":
             flops = 2 * op.n_img * op.Ho * op.Wo * op.Cout * op.K_real
-        rows.append({"i": i, "name": eng.plan.op_names[i], "kind": abi.OP_NAMES[op.kind], "ms": float(ms[i]), "flops": flops,
+        rows.append({"i": i0, "name": name, "kind": kind, "ms": float(ms[gi]), "flops": flops,
                      "shape": [op.n_img, op.Hi, op.Wi, op.Cin, op.Cout, op.ksize, op.stride]})
+    n = len(ops)
     # decode_box and NMS (outside the op list: separate C-ABI entry points)
     from utils.utils_bbox import DecodeBox
     dec = DecodeBox(1, (size, size))
