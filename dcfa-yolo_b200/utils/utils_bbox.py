@@ -52,18 +52,21 @@ class DecodeBox():
         return _engine.decode_box(dbox, cls, anchors, strides, self.input_shape)
 
     def yolo_correct_boxes(self, box_xy, box_wh, input_shape, image_shape, letterbox_image):
-        """numpy, host side, post-NMS (tiny): undo the letterbox; rows (y1, x1, y2, x2) in original-image pixels."""
+        """numpy, host side, post-NMS (tiny): undo the letterbox; rows (y1, x1, y2, x2) in original-image pixels.
+        image_shape is (2,) or one (h, w) row per box.  The dtype flow is the reference's (:60-85): its in-place
+        `box_hw *= scale` and `boxes *= image_shape` keep the arrays' dtypes, so float32 inputs are rounded to
+        float32 at exactly those two points and the results are bit-identical."""
         yx, hw = box_xy[..., ::-1], box_wh[..., ::-1]
         input_shape, image_shape = np.array(input_shape), np.array(image_shape)
         if letterbox_image:
-            new_shape = np.round(image_shape * np.min(input_shape / image_shape))
+            new_shape = np.round(image_shape * np.min(input_shape / image_shape, axis=-1, keepdims=True))
             offset = (input_shape - new_shape) / 2. / input_shape
             scale = input_shape / new_shape
             yx = (yx - offset) * scale
-            hw = hw * scale
+            hw = (hw * scale).astype(hw.dtype)
         lo, hi = yx - hw / 2., yx + hw / 2.
         boxes = np.concatenate([lo[..., 0:1], lo[..., 1:2], hi[..., 0:1], hi[..., 1:2]], axis=-1)
-        return boxes * np.concatenate([image_shape, image_shape], axis=-1)
+        return (boxes * np.concatenate([image_shape, image_shape], axis=-1)).astype(boxes.dtype)
 
     def nms_device(self, prediction, conf_thres=0.5, nms_thres=0.4):
         """GPU part only: returns the NmsWorkspace (det/idx/cnt on the device, stream-ordered, no host sync)."""
@@ -111,6 +114,10 @@ class DecodeBox():
         head = ws.head_host.numpy()
         counts = head[:, 0].astype(np.int64)
         output = [None for _ in range(b)]
+        shapes = np.asarray(image_shape)
+        per_image = shapes.ndim == 2          # (B, 2): every image has its own original shape (batched facade)
+        if per_image and shapes.shape[0] != b:
+            raise ValueError("image_shape must be (2,) or (%d, 2), got %s" % (b, tuple(shapes.shape)))
         if counts.max(initial=0) <= k:
             # every image's rows arrived with the first copy: un-letterbox all boxes in one numpy pass
             # (elementwise arithmetic, so identical to the reference's per-image calls), then split
@@ -118,7 +125,8 @@ class DecodeBox():
             det = rows[np.arange(k)[None, :] < counts[:, None]]            # (sum n_i, 6), image order, a copy
             if det.shape[0]:
                 box_xy, box_wh = (det[:, 0:2] + det[:, 2:4]) / 2, det[:, 2:4] - det[:, 0:2]
-                det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+                row_shapes = np.repeat(shapes, counts, axis=0) if per_image else shapes
+                det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, row_shapes, letterbox_image)
                 ends = np.cumsum(counts)
                 for i in range(b):
                     if counts[i]:
@@ -130,7 +138,8 @@ class DecodeBox():
                 continue
             det = head[i, 1:1 + n * 6].reshape(n, 6).copy() if n <= k else ws.det[i, :n].cpu().numpy()
             box_xy, box_wh = (det[:, 0:2] + det[:, 2:4]) / 2, det[:, 2:4] - det[:, 0:2]
-            det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+            det[:, :4] = self.yolo_correct_boxes(box_xy, box_wh, input_shape, shapes[i] if per_image else shapes,
+                                                 letterbox_image)
             output[i] = det
         return output
 

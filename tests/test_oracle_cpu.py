@@ -27,7 +27,9 @@ import json
 import os
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
+# model goldens (oracle/make_golden.py); facade_*.npz hold the host-helper goldens of oracle/make_golden_facade.py
+GOLDEN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz"))
+                      if not os.path.basename(p).startswith("facade_"))
 
 
 def load_golden(name):
