@@ -167,6 +167,10 @@ int64_t dcfa_launch_count(void);
 /*
  * Execute `n_ops` ops in order on `stream`.  `ops` is HOST memory (read during
  * the call only).  `bufs[nbufs]` are the device base pointers the views index.
+ * Consecutive records may run as ONE kernel when their shapes allow: CBAM_POOL, CBAM_MLP, CBAM_STATS, CBAM_APPLY of one
+ * tensor (a thread-block cluster per image; the partial-sum / gate / stats scratch views are then not written), and
+ * CONV(1x1) -> DWCONV -> CONV(1x1) chains whose head carries DCFA_CONV_FLAG_CHAIN_HEAD (the two intermediate tensors
+ * are then not written).  Results are the same either way.
  */
 int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, void* stream);
 
