@@ -41,7 +41,7 @@ CONF, IOU = 0.5, 0.3   # reference facade defaults (yolo_mul.py:22-23)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)   # ~0.85 s timed region: several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--phi", default="s")
