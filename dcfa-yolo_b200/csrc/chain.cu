@@ -78,8 +78,9 @@ __device__ __forceinline__ void chain_tma_load(uint32_t dst, const CUtensorMap* 
       : "memory");
 }
 
-// depthwise 3x3 over the GEMM-1 tile for one block of 8*R... see dw_tile_compute in dwconv.cu: one thread = one
-// 8-channel chunk of one tile column, R consecutive output rows; results go into the swizzled A tile of GEMM 2.
+// Depthwise 3x3 over the GEMM-1 tile (same register tiling as dw_tile_compute in dwconv.cu): one thread = one
+// 8-channel chunk of one tile column and R consecutive output rows, for the 2R chunks starting at c8_base; the bf16
+// results go straight into the swizzled K-major A tile of GEMM 2.
 template <int R, int CT>
 __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, uint32_t s_a2, const float* wd_s, const float* bd_s,
                                          int c8_base, int tid) {

@@ -104,7 +104,8 @@ class DecodeBox():
 
     def fetch_detections(self, ws, input_shape, image_shape, letterbox_image):
         """Host half of non_max_suppression: one device->host copy of (count, first rows) per image, then the
-        reference's numpy un-letterbox (:170-173).  Returns list of None | float32 (n_i, 6) rows (y1,x1,y2,x2,conf,cls)."""
+        reference's numpy un-letterbox (:170-173).  image_shape is the original (h, w) of the image, or a (B, 2) array
+        with one shape per image of the batch.  Returns list of None | float32 (n_i, 6) rows (y1,x1,y2,x2,conf,cls)."""
         b, a = ws.b, ws.a
         k = min(a, self.first_fetch)
         if not getattr(ws, 'head_pending', False):
