@@ -160,8 +160,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
   ptx::pdl_wait();
 
   // ---- static per-thread roles
-  // im2col: thread m < NPIX builds GEMM column (row of the K-major B tile) m = cx*CH + cy
-  const int icx = tid / CH, icy = tid - icx * CH;
+  // im2col: GEMM column (row of the K-major B tile) m = cx*CH + cy; one thread builds columns 2q, 2q+1 of a conv row
   // epilogue: TMEM lane = 32*(warp%4) + lane -> MMA row; channel = row % C0pad; replica = row / C0pad
   const int q4 = warp & 3, half = warp >> 2;
   const int mrow = q4 * 32 + lane;
@@ -283,28 +282,36 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
       __syncthreads();
       // ---- im2col: K index = ky*10 + kx*3 + ci (slots 9, 19, 29 carry a neighbouring value under a zero weight;
       //      30, 31 are zero).  The 9 taps of one kernel row are 9 consecutive bf16 of the converted patch row,
-      //      starting at value 10 + 3*cx: five words, shifted by half a word when cx is odd.
-      if (tid < NPIX) {
+      //      starting at value 10 + 3*cx.  One thread builds columns 2q and 2q+1 of conv row cy from seven words per
+      //      kernel row: the even column's five words as they are, the odd column's shifted by a word and a half.
+      if (tid < (CW + 1) / 2 * CH) {
+        const int q = tid / CH, cy = tid - q * CH;
+        const int cx = 2 * q;
         const uint32_t* prow = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(s_in) + U8_CVT_OFF) +
-                               icy * (U8_PITCH / 2) + 5 + ((3 * icx) >> 1);
-        const uint32_t sh = (uint32_t)(icx & 1) * 16u;
-        uint32_t pk[16];
+                               cy * (U8_PITCH / 2) + 5 + 3 * q;
+        uint32_t w[3][7];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          uint32_t w[6];
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int k = 0; k < 6; ++k) w[k] = prow[ky * (U8_PITCH / 2) + k];
+          for (int k = 0; k < 7; ++k) w[ky][k] = prow[ky * (U8_PITCH / 2) + k];
 #pragma unroll
-          for (int k = 0; k < 5; ++k) pk[ky * 5 + k] = __funnelshift_r(w[k], w[k + 1], sh);
+        for (int px = 0; px < 2; ++px) {
+          if (px == 1 && cx + 1 >= CW) break;
+          uint32_t pk[16];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) pk[ky * 5 + k] = px == 0 ? w[ky][k] : __funnelshift_r(w[ky][k + 1], w[ky][k + 2], 16u);
+          pk[15] = 0u;
+          const int m = (cx + px) * CH + cy;
+          const uint32_t rowb = s_b + (uint32_t)m * KROW;
+          const uint32_t xr = (uint32_t)((m >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
         }
-        pk[15] = 0u;
-        const uint32_t rowb = s_b + (uint32_t)tid * KROW;
-        const uint32_t xr = (uint32_t)((tid >> 1) & 3);   // SWIZZLE_64B: chunk ^= (row >> 1) & 3
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c) ^ xr) << 4)), "r"(pk[4 * c]),
-                       "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                       : "memory");
       }
     } else if (tid < (CW + 1) / 2 * CH) {
       // ---- im2col: two horizontally adjacent conv pixels per thread (columns 2q, 2q+1 of conv row cy): the 4 floats
