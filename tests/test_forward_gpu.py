@@ -130,6 +130,58 @@ def test_uint8_nhwc_inputs_match_oracle_on_preprocessed_pixels(cuda):
         net(rgb8.permute(0, 3, 1, 2).contiguous().to(cuda), nir8.permute(0, 3, 1, 2).contiguous().to(cuda))
 
 
+def test_full_size_properties_at_the_bench_workload(cuda):
+    """BASELINE.json configs[1] shape (s, 640x640, constructor-init weights, ~8000 NMS candidates per image), checked
+    through size-independent properties: batch-shard invariance of every output (the multi-GPU path shards the
+    batch), kept rows sorted by descending score per image, NMS idempotence (the kept set is a fixed point), no kept
+    pair above the IoU threshold, and agreement of the uint8 and fp32 entry points on the same pixels."""
+    from nets.yolo_mul import YoloBody
+    from utils.utils_bbox import DecodeBox
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = YoloBody([640, 640], 1, 's').eval().to(cuda)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (2, 6, 640, 640, 3), generator=g, dtype=torch.uint8)
+    rgb = (u8[0].permute(0, 3, 1, 2).float() / 255.0).to(cuda)
+    nir = (u8[1].permute(0, 3, 1, 2).float() / 255.0).to(cuda)
+    full = net(rgb, nir)
+    part = net(rgb[4:], nir[4:])
+    assert torch.equal(full[0][4:], part[0]) and torch.equal(full[1][4:], part[1])
+    for a, b in zip(full[2], part[2]):
+        assert torch.equal(a[4:], b)
+    dec = DecodeBox(1, (640, 640))
+    y = dec.decode_box(full)
+    ws = dec.nms_device(y.clone(), 0.5, 0.3)
+    cnt, cand = ws.cnt.cpu().numpy(), ws.cand.cpu().numpy()
+    assert cand.min() > 1000 and cnt.min() > 0          # the heavy-NMS regime the bench runs in
+    det = ws.det.cpu().numpy()
+    for i in range(6):
+        rows = det[i, :cnt[i]]
+        assert np.all(np.diff(rows[:, 4]) <= 0), "kept rows are not in descending score order"
+        x1, y1, x2, y2 = rows[:, 0:1], rows[:, 1:2], rows[:, 2:3], rows[:, 3:4]
+        iw = np.clip(np.minimum(x2, x2.T) - np.maximum(x1, x1.T), 0, None)
+        ih = np.clip(np.minimum(y2, y2.T) - np.maximum(y1, y1.T), 0, None)
+        area = (x2 - x1) * (y2 - y1)
+        iou = iw * ih / (area + area.T - iw * ih)
+        np.fill_diagonal(iou, 0.0)
+        assert iou.max() <= 0.3 + 1e-6, "two kept boxes overlap above the threshold"
+    # idempotence: feed the kept boxes (as xywh rows with their scores) back in -> all of them are kept again
+    k = int(cnt.max())
+    again = torch.zeros(6, k, 5, device=cuda)
+    for i in range(6):
+        r = ws.det[i, :cnt[i]]
+        again[i, :cnt[i], 0] = (r[:, 0] + r[:, 2]) / 2
+        again[i, :cnt[i], 1] = (r[:, 1] + r[:, 3]) / 2
+        again[i, :cnt[i], 2] = r[:, 2] - r[:, 0]
+        again[i, :cnt[i], 3] = r[:, 3] - r[:, 1]
+        again[i, :cnt[i], 4] = r[:, 4]
+    ws2 = DecodeBox(1, (640, 640)).nms_device(again, 0.5, 0.3)
+    assert np.array_equal(ws2.cnt.cpu().numpy(), cnt)
+    # uint8 entry point on the same pixels
+    out8 = net(u8[0].to(cuda), u8[1].to(cuda))
+    np.testing.assert_allclose(out8[0].cpu().numpy(), full[0].cpu().numpy(), atol=4e-2, rtol=2e-2)
+
+
 def test_no_cpu_fallback_and_training_mode(cuda):
     from nets.yolo_mul import YoloBody
     from utils.utils_bbox import DecodeBox
