@@ -80,6 +80,9 @@ struct TmaConvArgs {
   uint32_t out_stage_bytes;  // 128 rows * cbox * 2
   uint32_t tmem_cols;
   uint32_t acc_stages;   // TMEM accumulator stages (2 or 4): the MMA issuer runs this many tiles ahead of the epilogues
+  int epi_split;         // 1: BOTH epilogue groups work on every tile, each on every other 16-channel chunk (wide
+                         // tiles: halves the epilogue latency of a tile, which is exposed at the tail of every launch
+                         // and is all there is when a CTA gets one tile); 0: the groups alternate tiles
 };
 
 #ifdef DCFA_TIMELINE
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       }
       for (int a = 0; a < (int)p.acc_stages; ++a) {
         ptx::mbar_init(bar_tfull + 8u * a, 1);
-        ptx::mbar_init(bar_tempty + 8u * a, 4);  // the four warps of the stage's epilogue group
+        ptx::mbar_init(bar_tempty + 8u * a, p.epi_split ? 8 : 4);  // the warps of the epilogue group(s) reading the stage
       }
       ptx::fence_mbar_init();
     }
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     uint32_t slab = 0;   // store slabs issued by this group (selects the staging buffer)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      if ((int)(tcount & 1u) != group) continue;
+      if (!p.epi_split && (int)(tcount & 1u) != group) continue;
       const uint32_t as = tcount & (p.acc_stages - 1u);   // accumulator stage; its parity is the group's
       const uint32_t aph = (tcount >> acc_shift) & 1u;     // the stage's use count, mod 2
       const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
@@ -405,16 +408,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           }
         }
       };
-      ptx::tmem_ld_x16(taddr0, accA);
-      for (int j = 0; j < nchunks; j += 2) {
+      // this group's chunks: all of them, or (split) every other one starting at `group`
+      const int jstep = p.epi_split ? 2 : 1, j0 = p.epi_split ? group : 0;
+      ptx::tmem_ld_x16(taddr0 + (uint32_t)(j0 * 16), accA);
+      for (int j = j0; j < nchunks; j += 2 * jstep) {
         ptx::tmem_ld_wait();
-        if (j + 1 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 1) * 16), accB);  // prefetch the next chunk
+        if (j + jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + jstep) * 16), accB);  // prefetch the next chunk
         process(accA, j);
         __syncwarp();
-        if (j + 1 < nchunks) {
+        if (j + jstep < nchunks) {
           ptx::tmem_ld_wait();
-          if (j + 2 < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2) * 16), accA);
-          process(accB, j + 1);
+          if (j + 2 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2 * jstep) * 16), accA);
+          process(accB, j + jstep);
           __syncwarp();
         }
       }
@@ -581,6 +586,10 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.stages = stages;
   const int smem = fixed + stages * stage_bytes;
   a.acc_stages = 4 * a.BN <= 512 ? 4u : 2u;
+  {
+    const char* e = getenv("DCFA_EPI_SPLIT");   // debug: DCFA_EPI_SPLIT=0 keeps the groups on alternating tiles
+    a.epi_split = (a.BN >= 128 && !a.tma_store && !(e && atoi(e) == 0)) ? 1 : 0;
+  }
   uint32_t cols = 32;
   while (cols < a.acc_stages * (uint32_t)a.BN) cols <<= 1;
   a.tmem_cols = cols;
