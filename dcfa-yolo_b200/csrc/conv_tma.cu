@@ -60,6 +60,7 @@ struct TmaConvArgs {
   int64_t sb_gstride;
   int n_img, group_imgs;
   int Ho, Wo, Cout, ksize, stride, pad;
+  int pair;               // DCFA_CONV_FLAG_PAIR: six pixel-pair k-blocks per tile (3x3 stride 2, Cin = 32), see launch_conv_tma
   int BN, n_tiles, k_blocks;
   int bk;                 // channels per k-block (64 / 32 / 16)
   int cblocks;            // Cin / bk
@@ -195,12 +196,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         const int x0 = tx * p.tw * p.stride - p.pad;
         const int y0 = ty * p.th * p.stride - p.pad;
         const __nv_bfloat16* wp = p.w + (int64_t)g * p.w_gstride + (int64_t)nt * p.k_blocks * wstep;
+        // pair mode: per kernel row the k-blocks are pair (ox - 1) and pair ox (x in pair units); else one per (tap, c)
+        const int nx = p.pair ? 2 : p.ksize;
+        const int nc = p.pair ? p.bk : p.cblocks * p.bk;
         for (int dy = 0; dy < p.ksize; ++dy) {
-          for (int dx = 0; dx < p.ksize; ++dx) {
-            for (int c = 0; c < p.cblocks * p.bk; c += p.bk) {
+          for (int dx = 0; dx < nx; ++dx) {
+            for (int c = 0; c < nc; c += p.bk) {
               ptx::mbar_wait(empty, ph ^ 1u);
               ptx::mbar_arrive_expect_tx(full, tx_bytes);
-              tma_load_4d(a_dst, &tmap, c, x0 + dx, y0 + dy, n, full);
+              tma_load_4d(a_dst, &tmap, c, p.pair ? tx * p.tw - 1 + dx : x0 + dx, y0 + dy, n, full);
               ptx::bulk_g2s(b_dst, wp, p.b_tx_bytes, full);
               TL(0, tl_it); ++tl_it;
               wp += wstep;
@@ -501,12 +505,18 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.ksize = op.ksize; a.stride = op.stride; a.pad = op.ksize / 2;
   a.BN = op.BN; a.n_tiles = op.n_tiles; a.k_blocks = op.k_blocks;
   a.bk = op.flags & 0xff;
+  a.pair = (op.flags & DCFA_CONV_FLAG_PAIR) ? 1 : 0;
   a.act = op.act; a.out_mode = op.out_mode; a.out_ctot = op.out_ctot; a.out_coff = op.out_coff;
   a.post_scale = op.f0;
 
   DCFA_REQUIRE(x.p && a.y.p && a.w && a.scale && a.bias, "conv(tma): missing tensor");
   DCFA_REQUIRE(a.bk == 64 || a.bk == 32 || a.bk == 16, "conv(tma): bk %d unsupported", a.bk);
-  DCFA_REQUIRE(Cin % a.bk == 0, "conv(tma): Cin %d not a multiple of bk %d", Cin, a.bk);
+  if (a.pair)
+    DCFA_REQUIRE(a.bk == 64 && Cin == 32 && op.ksize == 3 && op.stride == 2 && op.Wi % 2 == 0 && op.k_blocks == 6 &&
+                     op.K_real == 288,
+                 "conv(tma): pixel-pair packing needs a 3x3 stride-2 conv with Cin = 32 on an even-width input");
+  else
+    DCFA_REQUIRE(Cin % a.bk == 0, "conv(tma): Cin %d not a multiple of bk %d", Cin, a.bk);
   DCFA_REQUIRE(a.n_img > 0 && a.n_img % a.group_imgs == 0, "conv(tma): bad grouping");
   DCFA_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv(tma): ksize %d unsupported", a.ksize);
   DCFA_REQUIRE(a.stride == 1 || a.stride == 2, "conv(tma): stride %d unsupported", a.stride);
@@ -514,8 +524,8 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
                "conv(tma): output size inconsistent");
   DCFA_REQUIRE(a.BN >= 16 && a.BN <= 256 && a.BN % 16 == 0, "conv(tma): BN %d invalid", a.BN);
   DCFA_REQUIRE(a.n_tiles >= 1 && a.n_tiles * a.BN >= a.Cout, "conv(tma): n_tiles*BN < Cout");
-  a.cblocks = Cin / a.bk;
-  DCFA_REQUIRE(a.k_blocks == a.ksize * a.ksize * a.cblocks && op.K_real == a.ksize * a.ksize * Cin,
+  a.cblocks = a.pair ? 1 : Cin / a.bk;
+  DCFA_REQUIRE(a.pair || (a.k_blocks == a.ksize * a.ksize * a.cblocks && op.K_real == a.ksize * a.ksize * Cin),
                "conv(tma): k_blocks %d inconsistent with packing", a.k_blocks);
   DCFA_REQUIRE(x.gi <= 0 || x.gstride == (int64_t)x.gi * x.img_stride, "conv(tma): grouped input views unsupported");
   DCFA_REQUIRE(((uintptr_t)x.p % 16) == 0 && x.ld % 8 == 0 && x.img_stride % 8 == 0, "conv(tma): input must be 16-byte aligned");
@@ -598,10 +608,18 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   EncodeTiledFn enc = encode_tiled_fn();
   DCFA_REQUIRE(enc != nullptr, "conv(tma): cuTensorMapEncodeTiled entry point unavailable");
   alignas(64) CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)a.n_img};
-  const cuuint64_t gstr[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)Wi * x.ld * 2, (cuuint64_t)x.img_stride * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)a.bk, (cuuint32_t)(a.tw * a.stride), (cuuint32_t)(a.th * a.stride), 1u};
-  const cuuint32_t estr[4] = {1u, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1u};
+  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)a.n_img};
+  cuuint64_t gstr[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)Wi * x.ld * 2, (cuuint64_t)x.img_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)a.bk, (cuuint32_t)(a.tw * a.stride), (cuuint32_t)(a.th * a.stride), 1u};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1u};
+  if (a.pair) {   // the W unit is a PAIR of pixels (64 channels, 128 contiguous bytes): dense along x, stride 2 along y only
+    DCFA_REQUIRE(x.ld == Cin, "conv(tma): pixel-pair packing needs a dense input (ld == Cin)");
+    gdim[0] = 2 * (cuuint64_t)Cin;
+    gdim[1] = (cuuint64_t)Wi / 2;
+    gstr[0] = (cuuint64_t)x.ld * 4;
+    box[1] = (cuuint32_t)a.tw;
+    estr[1] = 1u;
+  }
   DCFA_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv(tma): box too large");
   const CUtensorMapSwizzle swz = a.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                             : (a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

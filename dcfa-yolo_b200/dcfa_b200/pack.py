@@ -44,6 +44,25 @@ def swizzle_tile(tile):
     return torch.gather(t, 1, idx[:, :, None].expand(rows, n, 8)).reshape(rows, bk)
 
 
+def pack_conv_weight_pair(w):
+    """3x3 stride-2 conv with Cin = 32 on a dense even-width input (DCFA_CONV_FLAG_PAIR): k-blocks of 64 = one PIXEL PAIR
+    (columns 2p, 2p+1: 128 contiguous bytes).  Output column ox reads input columns 2ox-1, 2ox, 2ox+1 = pair (ox-1).odd,
+    pair ox.even, pair ox.odd, so per kernel row two k-blocks: [0 | w(dy,0)] on pair ox-1 and [w(dy,1) | w(dy,2)] on pair ox
+    -- six 128-byte-row boxes per tile instead of nine 64-byte-row ones (the TMA unit's cost is per box row)."""
+    cout, cin, k, _ = w.shape
+    assert k == 3 and cin == 32
+    bn, n_tiles = conv_tiling(cout)
+    full = torch.zeros(n_tiles * bn, 6 * 64, dtype=torch.float32)
+    for dy in range(3):
+        full[:cout, (2 * dy) * 64 + 32:(2 * dy) * 64 + 64] = w[:, :, dy, 0]
+        full[:cout, (2 * dy + 1) * 64:(2 * dy + 1) * 64 + 32] = w[:, :, dy, 1]
+        full[:cout, (2 * dy + 1) * 64 + 32:(2 * dy + 1) * 64 + 64] = w[:, :, dy, 2]
+    full = full.to(torch.bfloat16)
+    tiles = [swizzle_tile(full[nt * bn:(nt + 1) * bn, kb * 64:(kb + 1) * 64]).reshape(-1) for nt in range(n_tiles) for kb in range(6)]
+    meta = dict(BN=bn, n_tiles=n_tiles, k_blocks=6, K_real=9 * cin, Cout=cout, Cin=cin, ksize=3, bk=64, pair=True)
+    return torch.cat(tiles), meta
+
+
 def pack_conv_weight(w, bk=None):
     """w: [Cout, Cin, k, k] fp32 (input channels already in PHYSICAL order) ->
     (packed bf16 [n_tiles*k_blocks*BN*bk], meta dict).  K index = (ky*k + kx)*Cin + ci.

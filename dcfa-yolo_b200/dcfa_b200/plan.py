@@ -121,9 +121,13 @@ class Plan:
         split = (c, TRef): output channels from c on go to that second tensor instead of dst[..., c:]."""
         packed, meta = [], None
         scs, bis = [], []
+        # pixel-pair k-blocks for 3x3 stride-2 convs on dense 32-channel inputs of even width (see pack_conv_weight_pair)
+        pair = (k == 3 and stride == 2 and src.c == 32 and src.ld == 32 and src.c_off == 0 and src.w % 2 == 0 and
+                res is None and f32_out is None)
         for (w, sc, bi, col) in groups:
             assert w.shape[1] == src.c and w.shape[2] == k, (name, tuple(w.shape), src.c)
-            p, meta = pack.pack_conv_weight(self._permute_in(w, src, col))
+            wp = self._permute_in(w, src, col)
+            p, meta = pack.pack_conv_weight_pair(wp) if pair else pack.pack_conv_weight(wp)
             packed.append(p)
             npad = meta['BN'] * meta['n_tiles']
             scs.append(pack.pad_channels(sc, npad))
@@ -138,7 +142,8 @@ class Plan:
                         bias=_flat(BUF_BLOB, bi_off), n_img=src.n, group_imgs=src.n // g, Hi=src.h, Wi=src.w, Cin=src.c,
                         Ho=ho, Wo=wo, Cout=meta['Cout'], ksize=k, stride=stride, BN=meta['BN'], n_tiles=meta['n_tiles'],
                         k_blocks=meta['k_blocks'], K_real=meta['K_real'], w_gstride=packed[0].numel(),
-                        sb_gstride=meta['BN'] * meta['n_tiles'], f0=post_scale, flags=meta['bk'])
+                        sb_gstride=meta['BN'] * meta['n_tiles'], f0=post_scale,
+                        flags=meta['bk'] | (abi.CONV_FLAG_PAIR if pair else 0))
         if f32_out is None:
             assert dst.n == src.n and dst.h == ho and dst.w == wo and dst.c == meta['Cout'], name
             op.out_mode = abi.OUT_BF16_NHWC

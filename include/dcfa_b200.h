@@ -77,7 +77,12 @@ enum { DCFA_STEM_FLAG_U8 = 0x100 };
 /* DCFA_OP_CONV flags (above the low 8 bits, which hold the k-block width of the TMA packing): this 1x1 conv, the DWCONV
  * after it and the 1x1 CONV after that form a chain whose two intermediate tensors nobody else reads and whose output
  * does not alias its input -- dcfa_run_ops may run the three records as one fused kernel */
-enum { DCFA_CONV_FLAG_CHAIN_HEAD = 0x400 };
+enum {
+  DCFA_CONV_FLAG_CHAIN_HEAD = 0x400,
+  /* 3x3 stride-2 conv, Cin = 32, dense even-width input: w holds SIX k-blocks of 64 per n-tile, one per (kernel row,
+   * pixel pair): [0 | w(dy,0)] applied to input pair ox-1 and [w(dy,1) | w(dy,2)] applied to pair ox */
+  DCFA_CONV_FLAG_PAIR = 0x800
+};
 
 /* DCFA_OP_CONV output modes */
 enum { DCFA_OUT_BF16_NHWC = 0, DCFA_OUT_F32_NCHW = 1 };

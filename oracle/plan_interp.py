@@ -107,7 +107,16 @@ def run_ops(ops, bufs):
             bi = _f32(bufs[op.bias.buf], op.bias.off, G * op.sb_gstride).view(G, -1)[:, :npad]
             outs = []
             for g in range(G):
-                wt = wall[g, :op.Cout, :op.K_real].view(op.Cout, op.ksize, op.ksize, op.Cin).permute(0, 3, 1, 2)
+                if op.flags & 0x800:   # pixel-pair k-blocks: [0 | w(dy,0)], [w(dy,1) | w(dy,2)] per kernel row
+                    wp = wall[g, :op.Cout]
+                    wt = torch.zeros(op.Cout, op.Cin, 3, 3)
+                    for dy in range(3):
+                        assert float(wp[:, (2 * dy) * 64:(2 * dy) * 64 + 32].abs().max()) == 0.0
+                        wt[:, :, dy, 0] = wp[:, (2 * dy) * 64 + 32:(2 * dy) * 64 + 64]
+                        wt[:, :, dy, 1] = wp[:, (2 * dy + 1) * 64:(2 * dy + 1) * 64 + 32]
+                        wt[:, :, dy, 2] = wp[:, (2 * dy + 1) * 64 + 32:(2 * dy + 1) * 64 + 64]
+                else:
+                    wt = wall[g, :op.Cout, :op.K_real].view(op.Cout, op.ksize, op.ksize, op.Cin).permute(0, 3, 1, 2)
                 y = F.conv2d(x[g * gi:(g + 1) * gi], wt.contiguous(), None, op.stride, op.ksize // 2)
                 y = y * sc[g, :op.Cout].view(1, -1, 1, 1) + bi[g, :op.Cout].view(1, -1, 1, 1)
                 outs.append(_act(y, op.act) * op.f0)

@@ -123,6 +123,37 @@ def test_conv_stride2_on_channel_subview(cuda):
     _bf16_close(y.cpu(), (r * torch.sigmoid(r)).permute(0, 2, 3, 1), "conv s2 sub-view")
 
 
+@pytest.mark.parametrize("n,h,w,cout,groups", [(2, 16, 16, 64, 1), (4, 160, 160, 64, 2), (1, 23, 38, 48, 1), (2, 40, 36, 128, 1)])
+def test_conv_stride2_pixel_pair_blocks(cuda, n, h, w, cout, groups):
+    """DCFA_CONV_FLAG_PAIR: 3x3 stride-2 conv with Cin = 32 read as six 64-channel pixel-pair k-blocks per tile."""
+    from dcfa_b200 import abi, pack
+    g = torch.Generator().manual_seed(77 + cout)
+    cin, gi = 32, n // groups
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    ws = [bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / 17.0) for _ in range(groups)]
+    scs = [torch.rand(cout, generator=g) + 0.5 for _ in range(groups)]
+    bis = [torch.randn(cout, generator=g) * 0.1 for _ in range(groups)]
+    packed = [pack.pack_conv_weight_pair(t) for t in ws]
+    m = packed[0][1]
+    npad = m["BN"] * m["n_tiles"]
+    xg = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    W = torch.stack([t[0] for t in packed]).to(cuda)
+    S = torch.stack([pack.pad_channels(t, npad) for t in scs]).to(cuda)
+    B = torch.stack([pack.pad_channels(t, npad) for t in bis]).to(cuda)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.full((n, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=cuda)
+    op = abi.new_op(abi.OP_CONV, act=abi.ACT_SILU, x=nhwc_view(xg, 0), w=flat_view(1), scale=flat_view(2), bias=flat_view(3),
+                    y=nhwc_view(y, 4), n_img=n, group_imgs=gi, Hi=h, Wi=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=3, stride=2,
+                    BN=m["BN"], n_tiles=m["n_tiles"], k_blocks=m["k_blocks"], K_real=m["K_real"], w_gstride=packed[0][0].numel(),
+                    sb_gstride=npad, flags=m["bk"] | abi.CONV_FLAG_PAIR)
+    _run([op], [xg, W, S, B, y])
+    refs = []
+    for gg in range(groups):
+        r = F.conv2d(x[gg * gi:(gg + 1) * gi], ws[gg], None, 2, 1) * scs[gg].view(1, -1, 1, 1) + bis[gg].view(1, -1, 1, 1)
+        refs.append(r * torch.sigmoid(r))
+    _bf16_close(y.cpu(), torch.cat(refs).permute(0, 2, 3, 1), "conv pair")
+
+
 def test_conv_f32_nchw_out(cuda):
     """head-style output: fp32 NCHW at a channel offset, Cout not a multiple of 16 (nc = 1 and 64)."""
     from dcfa_b200 import abi
