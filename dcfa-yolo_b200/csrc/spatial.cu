@@ -99,14 +99,16 @@ struct UpArgs {
   float sy, sx;  // (in-1)/(out-1)
 };
 
+// 8 bf16 channels of one source pixel (plus the second tensor's, if any) as four packed fp32 pairs
 template <bool TWO>
-__device__ __forceinline__ void load_sum8(const __nv_bfloat16* a, const __nv_bfloat16* b, float* v) {
-  unpack8(ldg128(a), v);
+__device__ __forceinline__ void load_sum8(const __nv_bfloat16* a, const __nv_bfloat16* b, F2* v) {
+  unpack8_f2(ldg128(a), v);
   if (TWO) {
-    float w[8];
-    unpack8(ldg128(b), w);
+    F2 w[4];
+    unpack8_f2(ldg128(b), w);
+    const F2 one = f2_make(1.0f, 1.0f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] += w[e];
+    for (int e = 0; e < 4; ++e) f2_fma(v[e], w[e], one);   // v + w (x * 1 + v is exact)
   }
 }
 
@@ -141,14 +143,26 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpArgs p) {
       const int y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0);
       const float ly = fy - (float)y0, hy = 1.0f - ly;
       const int i00 = y0 * p.Wi + x0, i01 = y0 * p.Wi + x1, i10 = y1 * p.Wi + x0, i11 = y1 * p.Wi + x1;
-      float v00[8], v01[8], v10[8], v11[8];
+      // packed fp32x2 arithmetic (fma.rn.f32x2): the kernel is issue-bound, this halves its FMA count
+      F2 v00[4], v01[4], v10[4], v11[4];
       load_sum8<TWO>(pa + (int64_t)i00 * p.a.ld, pb + (int64_t)i00 * p.b.ld, v00);
       load_sum8<TWO>(pa + (int64_t)i01 * p.a.ld, pb + (int64_t)i01 * p.b.ld, v01);
       load_sum8<TWO>(pa + (int64_t)i10 * p.a.ld, pb + (int64_t)i10 * p.b.ld, v10);
       load_sum8<TWO>(pa + (int64_t)i11 * p.a.ld, pb + (int64_t)i11 * p.b.ld, v11);
+      const F2 hx2 = f2_make(hx, hx), lx2 = f2_make(lx, lx), hy2 = f2_make(hy, hy), ly2 = f2_make(ly, ly);
+      const F2 zero = f2_make(0.0f, 0.0f);
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+      for (int e = 0; e < 4; ++e) {
+        F2 t0 = zero, t1 = zero, r = zero;
+        f2_fma(t0, hx2, v00[e]);      // hx * v00
+        f2_fma(t0, lx2, v01[e]);      //  + lx * v01
+        f2_fma(t1, hx2, v10[e]);
+        f2_fma(t1, lx2, v11[e]);
+        f2_fma(r, ly2, t1);           // ly * bottom
+        f2_fma(r, hy2, t0);           //  + hy * top
+        f2_get(r, o[2 * e], o[2 * e + 1]);
+      }
       stg128(py + (int64_t)oy * p.Wo * p.y.ld, pack8(o));
     }
   }
