@@ -318,22 +318,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       uint32_t accA[16], accB[16];
       auto process = [&](const uint32_t (&a)[16], const int j) {
         const int c0 = j * 16;
+        // packed fp32x2 arithmetic (fma.rn.f32x2 / mul.rn.f32x2 are single instructions on sm_100): BN and the FMA
+        // halves of SiLU take half the issue slots; the results are the same IEEE operations as the scalar forms
         float v[16];
+        F2 v2[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 s4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
           const float4 b4 = *reinterpret_cast<const float4*>(sb + 256 + c0 + 4 * q);
-          v[4 * q + 0] = fmaf(__uint_as_float(a[4 * q + 0]), s4.x, b4.x);
-          v[4 * q + 1] = fmaf(__uint_as_float(a[4 * q + 1]), s4.y, b4.y);
-          v[4 * q + 2] = fmaf(__uint_as_float(a[4 * q + 2]), s4.z, b4.z);
-          v[4 * q + 3] = fmaf(__uint_as_float(a[4 * q + 3]), s4.w, b4.w);
+          v2[2 * q] = f2_make(b4.x, b4.y);
+          v2[2 * q + 1] = f2_make(b4.z, b4.w);
+          f2_fma(v2[2 * q], f2_make(__uint_as_float(a[4 * q + 0]), __uint_as_float(a[4 * q + 1])), f2_make(s4.x, s4.y));
+          f2_fma(v2[2 * q + 1], f2_make(__uint_as_float(a[4 * q + 2]), __uint_as_float(a[4 * q + 3])), f2_make(s4.z, s4.w));
         }
-        if (p.act == DCFA_ACT_SILU) {
+        if (p.act == DCFA_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
+          const F2 half2 = f2_make(0.5f, 0.5f), zero2 = f2_make(0.0f, 0.0f);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = silu_fast(v[e]);
-        } else if (p.act == DCFA_ACT_RELU) {
+          for (int e = 0; e < 8; ++e) {
+            F2 h = zero2;
+            f2_fma(h, v2[e], half2);
+            float h0, h1, t0, t1;
+            f2_get(h, h0, h1);
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+            f2_fma(h, h, f2_make(t0, t1));   // h * t + h
+            f2_get(h, v[2 * e], v[2 * e + 1]);
+          }
+        } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+          for (int e = 0; e < 8; ++e) f2_get(v2[e], v[2 * e], v[2 * e + 1]);
+          if (p.act == DCFA_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+          }
         }
         if (p.post_scale != 1.0f) {
 #pragma unroll
