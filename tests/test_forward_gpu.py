@@ -85,6 +85,74 @@ def test_decode_and_nms_on_reference_outputs(cuda, name):
         assert np.array_equal(ws.idx[i, :cnt[i]].cpu().numpy(), oidx[i, :cnt[i]])
 
 
+def _check_against_golden(z, meta, out, sel):
+    """dbox / cls / head maps of the batch rows `sel` against the golden pair(s), north_star tolerance."""
+    dbox, cls, x = out[0], out[1], out[2]
+    np.testing.assert_allclose(dbox[sel].cpu().numpy(), z["dbox"], atol=2e-2, rtol=1e-2)
+    np.testing.assert_allclose(cls[sel].cpu().numpy(), z["cls"], atol=2e-2, rtol=1e-2)
+    compare_x_maps(z, [xi[sel] for xi in x], 2e-2, 1e-2)
+
+
+@pytest.mark.parametrize("name,batch,positions", [("s640_stress", 32, (0, 13, 30)), ("l1280_stress", 4, (0, 3))])
+def test_golden_pairs_inside_the_bench_batch(cuda, name, batch, positions):
+    """Numeric parity at the batch composition the bench runs (BASELINE.json configs[1]: s, 640x640, B=32; configs[3]:
+    l, 1280x1280): the golden pair(s) of the real reference are placed at several positions of a full batch of other
+    images, so the tile schedule, cluster sizes and fused/unfused kernel choices of the real run are the ones compared.
+    Head maps, cls and dbox within 2e-2 + 1e-2*|ref|; decode + NMS of the batch rows reproduce the reference's rows."""
+    from oracle import forward as O
+    from utils.utils_bbox import DecodeBox
+    z, meta, keys = load_golden(name)
+    sd = golden_state_dict(meta, keys)
+    net = build_model(meta, sd, cuda)
+    h, w, gb = meta["H"], meta["W"], meta["B"]
+    grgb, gnir = O.synth_inputs(gb, h, w, meta["seed"] + 1000)
+    g = torch.Generator().manual_seed(99)
+    rgb = torch.rand(batch, 3, h, w, generator=g)
+    nir = torch.rand(batch, 3, h, w, generator=g)
+    for p0 in positions:
+        rgb[p0:p0 + gb], nir[p0:p0 + gb] = grgb, gnir
+    out = net(rgb.to(cuda), nir.to(cuda))
+    torch.cuda.synchronize()
+    for p0 in positions:
+        _check_against_golden(z, meta, out, slice(p0, p0 + gb))
+    # identical pairs give identical results wherever they sit in the batch
+    for p0 in positions[1:]:
+        assert torch.equal(out[0][p0:p0 + gb], out[0][positions[0]:positions[0] + gb])
+    dec = DecodeBox(meta["nc"], (h, w))
+    y = dec.decode_box(out)
+    p0 = positions[-1]
+    np.testing.assert_allclose(y[p0:p0 + gb].cpu().numpy(), z["decoded"], atol=2e-3, rtol=1e-2)
+    # NMS of OUR decoded boxes: bit-exact against the C oracle fed the same tensor (the golden scores of these weights
+    # sit within the bf16 tolerance of the confidence threshold, so the kept SET is only comparable on identical inputs;
+    # NMS on the reference's own decoded boxes is test_decode_and_nms_on_reference_outputs, bit-exact, same goldens)
+    from oracle import nms as onms
+    y_host = y.cpu().numpy().copy()
+    res = dec.non_max_suppression(y, meta["nc"], [h, w], np.array([h, w]), True, conf_thres=meta["conf"], nms_thres=meta["iou"])
+    ref = onms.non_max_suppression(y_host, [h, w], np.array([h, w]), True, meta["conf"], meta["iou"], 0)
+    assert len(res) == batch
+    for r, o in zip(res, ref):
+        assert (r is None) == (o is None)
+        if r is not None:
+            assert r.shape == o.shape and np.array_equal(r[:, 4:], o[:, 4:])
+            np.testing.assert_allclose(r[:, :4], o[:, :4], atol=1e-3, rtol=1e-6)
+
+
+@pytest.mark.parametrize("var,val", [("DCFA_CBAM_FUSED", "0"), ("DCFA_CBAM_FUSED", "2"), ("DCFA_CHAIN", "0"), ("DCFA_CHAIN", "2"),
+                                     ("DCFA_PDL", "1")])
+def test_kernel_path_switches_end_to_end_at_640(cuda, monkeypatch, var, val):
+    """Every alternative kernel path (four-kernel / always-fused CBAM, three-kernel / always-fused ShuffleNet branch)
+    against the s@640x640 golden of the real reference, end to end."""
+    from oracle import forward as O
+    monkeypatch.setenv(var, val)
+    z, meta, keys = load_golden("s640_stress")
+    sd = golden_state_dict(meta, keys)
+    net = build_model(meta, sd, cuda)
+    rgb, nir = O.synth_inputs(meta["B"], meta["H"], meta["W"], meta["seed"] + 1000)
+    out = net(rgb.to(cuda), nir.to(cuda))
+    torch.cuda.synchronize()
+    _check_against_golden(z, meta, out, slice(0, meta["B"]))
+
+
 def test_full_pipeline_vs_oracle_and_shard_invariance(cuda):
     """forward -> decode -> NMS through the public API, vs the fp32 CPU oracle on the same weights; any batch
     shard gives bit-identical results (the multi-GPU path shards the batch with no collective)."""

@@ -52,6 +52,13 @@ def compare_x_maps(z, x, atol, rtol):
         g = z["x%d" % i]
         sub = xi if g.shape == xi.shape else xi[:, :, ::4, ::4]
         np.testing.assert_allclose(sub, g, atol=atol, rtol=rtol, err_msg="head map %d" % i)
+        # checksum over EVERY element of the full-resolution map (the stored map may be a stride-4 subsample): the mean
+        # signed error and the mean magnitude must agree well inside the per-element tolerance -- a systematic bias or a
+        # wrong region outside the subsample grid shows up here
+        s_ref, a_ref = z["x%d_sum" % i]
+        x64 = xi.astype(np.float64)
+        assert abs(x64.sum() - s_ref) <= xi.size * atol / 4 + rtol / 4 * a_ref, "head map %d: sum" % i
+        assert abs(np.abs(x64).sum() - a_ref) <= xi.size * atol / 4 + rtol / 4 * a_ref, "head map %d: abs sum" % i
 
 
 def test_golden_set_is_complete():
