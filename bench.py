@@ -260,7 +260,7 @@ def profile_ops(net, batch, size, device, iters=5):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         evs[0].record(st)
         for gi, (i0, cnt, _, _) in enumerate(groups):
-            _lib.check(_lib.lib.dcfa_run_ops(arrays[gi], cnt, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+            _lib.check(_lib.lib.dcfa_run_ops(arrays[gi], cnt, eng.last_bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
             evs[gi + 1].record(st)
         torch.cuda.synchronize()
         tot += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n)])

@@ -6,6 +6,7 @@ ABI_VERSION = 1
 # op kinds
 OP_STEM, OP_CONV, OP_DWCONV, OP_CBAM_POOL, OP_CBAM_MLP, OP_CBAM_STATS, OP_CBAM_APPLY, OP_MAXPOOL5, OP_UPSAMPLE, OP_DFL = range(1, 11)
 STEM_FLAG_U8 = 0x100   # DCFA_STEM_FLAG_U8
+STEM_FLAG_X2_PLANE = 0x200   # DCFA_STEM_FLAG_X2_PLANE
 CONV_FLAG_CHAIN_HEAD = 0x400   # DCFA_CONV_FLAG_CHAIN_HEAD
 CONV_FLAG_PAIR = 0x800         # DCFA_CONV_FLAG_PAIR
 OP_NAMES = {OP_STEM: "stem", OP_CONV: "conv", OP_DWCONV: "dwconv", OP_CBAM_POOL: "cbam_pool", OP_CBAM_MLP: "cbam_mlp",

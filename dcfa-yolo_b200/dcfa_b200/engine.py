@@ -12,13 +12,15 @@ from . import plan as P
 class Engine:
     """One (batch, H, W) instance of the forward pass on one device."""
 
-    def __init__(self, state_dict, phi, num_classes, batch, height, width, device, input_u8=False):
+    def __init__(self, state_dict, phi, num_classes, batch, height, width, device, input_u8=False, depth_plane=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("dcfa_b200 has no CPU path: the engine needs a CUDA (sm_100a) device")
         _lib.check(_lib.lib.dcfa_device_check(self.device.index if self.device.index is not None else torch.cuda.current_device()))
         self.input_u8 = bool(input_u8)
-        self.plan = P.Plan(state_dict, phi, num_classes, batch, height, width, input_u8=self.input_u8)
+        self.depth_plane = bool(depth_plane)
+        self.plan = P.Plan(state_dict, phi, num_classes, batch, height, width, input_u8=self.input_u8,
+                           depth_plane=self.depth_plane)
         self.B, self.H, self.W, self.nc, self.no, self.A = batch, height, width, self.plan.nc, self.plan.no, self.plan.A
         self.level_shapes = list(self.plan.level_shapes)
         self.blob = self.plan.blob_tensor.to(self.device)
@@ -48,21 +50,26 @@ class Engine:
         return dbox, cls, x
 
     def run(self, rgb, nir, outputs=None, stream=None):
-        """rgb, nir: contiguous CUDA tensors, float32 [B,3,H,W] (or uint8 [B,H,W,3] for an input_u8 engine).
-        Enqueues the whole forward; returns (dbox, cls, x)."""
+        """rgb, nir: contiguous CUDA tensors, float32 [B,3,H,W] (or uint8 [B,H,W,3] for an input_u8 engine; nir is
+        uint8 [B,H,W] for a depth_plane engine).  Enqueues the whole forward; returns (dbox, cls, x).
+
+        One engine = one activation arena: calls on the same engine must be issued on ONE stream at a time (or be
+        ordered by events); concurrent streams need one engine (YoloBody) each."""
         shp = (self.B, self.H, self.W, 3) if self.input_u8 else (self.B, 3, self.H, self.W)
         dt = torch.uint8 if self.input_u8 else torch.float32
-        for t in (rgb, nir):
-            if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+        for t, want in ((rgb, shp), (nir, (self.B, self.H, self.W) if self.depth_plane else shp)):
+            if tuple(t.shape) != want or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
                 raise ValueError("engine.run: expected contiguous %s %s on %s, got %s %s on %s" % (
-                    dt, shp, self.device, tuple(t.shape), t.dtype, t.device))
-        dbox, cls, x = outputs if outputs is not None else self.new_outputs()
-        b = self._bufs
-        b[P.BUF_RGB], b[P.BUF_NIR] = rgb.data_ptr(), nir.data_ptr()
-        b[P.BUF_X0], b[P.BUF_X1], b[P.BUF_X2] = x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr()
-        b[P.BUF_DBOX], b[P.BUF_CLS] = dbox.data_ptr(), cls.data_ptr()
-        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib.dcfa_run_ops(self.plan.op_array, self.n_ops, b, P.NUM_BUFS, C.c_void_p(st)))
+                    dt, want, self.device, tuple(t.shape), t.dtype, t.device))
+        with torch.cuda.device(self.device):   # the library launches on the CURRENT device: make it this engine's
+            dbox, cls, x = outputs if outputs is not None else self.new_outputs()
+            b = (C.c_void_p * P.NUM_BUFS)(*self._bufs)   # per-call pointer table (calls may come from several host threads)
+            b[P.BUF_RGB], b[P.BUF_NIR] = rgb.data_ptr(), nir.data_ptr()
+            b[P.BUF_X0], b[P.BUF_X1], b[P.BUF_X2] = x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr()
+            b[P.BUF_DBOX], b[P.BUF_CLS] = dbox.data_ptr(), cls.data_ptr()
+            st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.dcfa_run_ops(self.plan.op_array, self.n_ops, b, P.NUM_BUFS, C.c_void_p(st)))
+        self.last_bufs = b   # the pointer table of the latest call (profiling tools replay single ops with it)
         return dbox, cls, x
 
 
@@ -77,11 +84,12 @@ def decode_box(dbox, cls, anchors, strides, input_shape):
         cls = cls.float().contiguous()
     anchors = anchors.float().to(dbox.device)
     strides = strides.float().to(dbox.device).reshape(-1).contiguous()
-    out = torch.empty(b, a, 4 + nc, dtype=torch.float32, device=dbox.device)
-    st = torch.cuda.current_stream(dbox.device).cuda_stream
-    _lib.check(_lib.lib.dcfa_decode_box(dbox.data_ptr(), cls.data_ptr(), cls.stride(0), anchors.data_ptr(),
-                                        anchors.stride(0), anchors.stride(1), strides.data_ptr(), b, a, nc,
-                                        float(input_shape[1]), float(input_shape[0]), out.data_ptr(), C.c_void_p(st)))
+    with torch.cuda.device(dbox.device):
+        out = torch.empty(b, a, 4 + nc, dtype=torch.float32, device=dbox.device)
+        st = torch.cuda.current_stream(dbox.device).cuda_stream
+        _lib.check(_lib.lib.dcfa_decode_box(dbox.data_ptr(), cls.data_ptr(), cls.stride(0), anchors.data_ptr(),
+                                            anchors.stride(0), anchors.stride(1), strides.data_ptr(), b, a, nc,
+                                            float(input_shape[1]), float(input_shape[0]), out.data_ptr(), C.c_void_p(st)))
     return out
 
 
@@ -105,10 +113,11 @@ def nms(pred, conf_thres, nms_thres, iou_mode=abi.IOU_TV_CPU, workspace=None):
         raise RuntimeError("dcfa_b200 has no CPU path: nms needs a CUDA tensor")
     assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
     b, a, row = pred.shape
-    ws = workspace if workspace is not None else NmsWorkspace(b, a, pred.device)
-    assert ws.b == b and ws.a == a
-    st = torch.cuda.current_stream(pred.device).cuda_stream
-    _lib.check(_lib.lib.dcfa_nms(pred.data_ptr(), b, a, row - 4, float(conf_thres), float(nms_thres), int(iou_mode),
-                                 ws.det.data_ptr(), ws.idx.data_ptr(), ws.cnt.data_ptr(), ws.cand.data_ptr(),
-                                 ws.ws.data_ptr(), ws.bytes, C.c_void_p(st)))
+    with torch.cuda.device(pred.device):
+        ws = workspace if workspace is not None else NmsWorkspace(b, a, pred.device)
+        assert ws.b == b and ws.a == a
+        st = torch.cuda.current_stream(pred.device).cuda_stream
+        _lib.check(_lib.lib.dcfa_nms(pred.data_ptr(), b, a, row - 4, float(conf_thres), float(nms_thres), int(iou_mode),
+                                     ws.det.data_ptr(), ws.idx.data_ptr(), ws.cnt.data_ptr(), ws.cand.data_ptr(),
+                                     ws.ws.data_ptr(), ws.bytes, C.c_void_p(st)))
     return ws

@@ -87,35 +87,54 @@ def pack_conv_weight(w, bk=None):
     return packed, meta
 
 
+STEM_W_ELEMS = 6 * 128 * 16   # bf16 elements of one group's stem weight tiles: [ky 3][parity 2][128 rows x 16 K]
+
+
 def pack_stem(w, scale, bias, u8=False):
-    """Stem conv [C0,3,3,3] + folded BN -> (weight tile bf16 [128*32], scale [C0pad], bias [C0pad], C0pad).
+    """Stem conv [C0,3,3,3] + folded BN -> (weight tiles bf16 [3*2*128*16], scale [C0pad], bias [C0pad], C0pad).
 
-    u8=True packs for uint8 NHWC inputs (DCFA_STEM_FLAG_U8): K = ky*10 + kx*3 + ci, so that the nine taps of one
-    kernel row are nine consecutive values of an NHWC image row (slots 9, 19, 29, 30, 31 are zero), and the scale
-    carries preprocess_input's 1/255 (utils/utils.py:76-79) -- the kernel multiplies exact integer pixels.
+    The stem kernel never builds an im2col: its B operand is the bf16 [y][x][4 channel] input patch itself, read through a
+    no-swizzle K-major descriptor whose row n is the 16 values starting at pixel 2n (four pixels x 4 channel slots).
+    So per kernel row ky there are two K=16 weight tiles: parity 0 (conv pixel 2n: taps on pixels 2n, 2n+1, 2n+2) has
+    K = kx*4 + ci, parity 1 (conv pixel 2n+1: taps on pixels 2n+1..2n+3) has K = (kx+1)*4 + ci; unused slots are zero.
+    Tiles are stored in the canonical no-swizzle layout of the tcgen05 descriptor: element (m, k) at
+    (m//8)*128 + (k//8)*64 + (m%8)*8 + k%8  (8 rows x 16 bytes core matrices; LBO = 128 B, SBO = 256 B).
 
-    The stem GEMM puts CHANNELS on the 128 MMA rows (replicated C0pad-periodically so every TMEM lane quarter holds
-    a copy) and pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative
-    BN scale get negated weights and |scale| (scale * conv(w) == |scale| * conv(sign * w))."""
+    u8=True: the scale carries preprocess_input's 1/255 (utils/utils.py:76-79) -- the kernel multiplies exact integer
+    pixels.
+
+    CHANNELS sit on the 128 MMA rows (replicated C0pad-periodically so every TMEM lane quarter holds a copy) and the
+    kernel pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative BN scale
+    get negated weights and |scale| (scale * conv(w) == |scale| * conv(sign * w))."""
     c0 = w.shape[0]
     c0pad = 32 if c0 <= 32 else (64 if c0 <= 64 else 128)
     sgn = torch.where(scale < 0, -torch.ones_like(scale), torch.ones_like(scale))
-    wk = (w * sgn.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(c0, 27)     # K = (ky*3 + kx)*3 + ci
-    if u8:
-        wk10 = torch.zeros(c0, 32, dtype=wk.dtype)
-        for ky in range(3):
-            wk10[:, ky * 10: ky * 10 + 9] = wk[:, ky * 9: ky * 9 + 9]
-        wk, nk = wk10, 32
-    else:
-        nk = 27
-    tile = torch.zeros(128, 32, dtype=torch.float32)
-    for m in range(128):
-        c = m % c0pad
-        if c < c0:
-            tile[m, :nk] = wk[c]
-    packed = swizzle_tile(tile.to(torch.bfloat16)).reshape(-1)
+    ws = (w * sgn.view(-1, 1, 1, 1)).float()                      # [c, ci, ky, kx]
+    tiles = torch.zeros(3, 2, 128, 16, dtype=torch.float32)
+    rows = torch.arange(128)
+    src = rows % c0pad
+    valid = src < c0
+    for ky in range(3):
+        for e in range(2):
+            for kx in range(3):
+                for ci in range(3):
+                    tiles[ky, e, rows[valid], (kx + e) * 4 + ci] = ws[src[valid], ci, ky, kx]
+    t = tiles.reshape(3, 2, 16, 8, 2, 8).permute(0, 1, 2, 4, 3, 5)   # [ky, e, m/8, k/8, m%8, k%8]
+    packed = t.reshape(-1).to(torch.bfloat16)
     sc = scale.abs() / 255.0 if u8 else scale.abs()
     return packed, pad_channels(sc, c0pad), pad_channels(bias, c0pad), c0pad
+
+
+def unpack_stem(packed, c0):
+    """Inverse of pack_stem's weight layout (test infrastructure uses it): bf16 [3*2*128*16] -> fp32 [c0,3,3,3] (sign-folded)."""
+    t = packed.float().reshape(3, 2, 16, 2, 8, 8).permute(0, 1, 2, 4, 3, 5).reshape(3, 2, 128, 16)
+    w = torch.zeros(c0, 3, 3, 3)
+    for ky in range(3):
+        for kx in range(3):
+            for ci in range(3):
+                w[:, ci, ky, kx] = t[ky, 0, :c0, kx * 4 + ci]
+                assert torch.equal(t[ky, 1, :c0, (kx + 1) * 4 + ci], w[:, ci, ky, kx])
+    return w
 
 
 def pad_channels(v, n, fill=0.0):

@@ -68,11 +68,14 @@ def _flat(buf, off):
 
 
 class Plan:
-    def __init__(self, sd, phi, num_classes, batch, height, width, input_u8=False):
+    def __init__(self, sd, phi, num_classes, batch, height, width, input_u8=False, depth_plane=False):
         """input_u8: the two inputs are uint8 NHWC images [B,H,W,3] (pre-`preprocess_input`, utils/utils.py:76-79)
-        instead of fp32 NCHW tensors in [0,1]; the stem folds the /255."""
+        instead of fp32 NCHW tensors in [0,1]; the stem folds the /255.  depth_plane (with input_u8): the second input
+        is the single uint8 plane [B,H,W] that cvtColor would replicate to three channels (utils/utils.py:14-19)."""
         self.phi, self.nc, self.B, self.H, self.W = phi, int(num_classes), int(batch), int(height), int(width)
         self.input_u8 = bool(input_u8)
+        self.depth_plane = bool(depth_plane)
+        assert self.input_u8 or not self.depth_plane
         self.sd = {k: v.detach().float().cpu() for k, v in sd.items() if torch.is_floating_point(v)}
         self.blob = pack.Blob()
         self.ops = []
@@ -305,8 +308,9 @@ class Plan:
         self._emit('stem', abi.new_op(abi.OP_STEM, x=_flat(BUF_RGB, 0), x2=_flat(BUF_NIR, 0), w=_flat(BUF_BLOB, w_off),
                                       scale=_flat(BUF_BLOB, sc_off), bias=_flat(BUF_BLOB, b_off), y=x.view(), n_img=N2,
                                       group_imgs=B, Hi=H, Wi=W, Ho=h1, Wo=w1, Cout=bc, Cin=3, ksize=3, stride=1,
-                                      BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad,
-                                      flags=abi.STEM_FLAG_U8 if self.input_u8 else 0))
+                                      BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad,
+                                      flags=(abi.STEM_FLAG_U8 if self.input_u8 else 0) |
+                                      (abi.STEM_FLAG_X2_PLANE if self.depth_plane else 0)))
         self.conv_flops += 2 * N2 * H * W * bc * 27
 
         # ---- dark2..dark5 (nets/yolo_mul.py:258-277)

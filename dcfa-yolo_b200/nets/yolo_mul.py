@@ -174,12 +174,13 @@ class YoloBody(nn.Module):
             self.invalidate_plan()
         return out
 
-    def _engine(self, batch, height, width, device, input_u8=False):
+    def _engine(self, batch, height, width, device, input_u8=False, depth_plane=False):
         from dcfa_b200.engine import Engine
-        key = (batch, height, width, str(device), bool(input_u8))
+        key = (batch, height, width, str(device), bool(input_u8), bool(depth_plane))
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self.state_dict(), self.phi, self.num_classes, batch, height, width, device, input_u8=input_u8)
+            eng = Engine(self.state_dict(), self.phi, self.num_classes, batch, height, width, device, input_u8=input_u8,
+                         depth_plane=depth_plane)
             self._engines[key] = eng
         return eng
 
@@ -192,12 +193,19 @@ class YoloBody(nn.Module):
         if rgb.dtype == torch.uint8 or nir.dtype == torch.uint8:
             # Extension of the reference signature: raw uint8 images [B,H,W,3] (what cvtColor/resize_image produce,
             # utils/utils.py:9-37).  preprocess_input's /255 and the HWC->CHW transpose (yolo_mul.py:76) happen
-            # inside the stem kernel; the upload is 4x smaller than the fp32 tensor.
-            if rgb.dtype != nir.dtype or rgb.shape != nir.shape or rgb.dim() != 4 or rgb.shape[3] != 3:
-                raise ValueError("expected two uint8 (B,H,W,3) tensors, got %s %s and %s %s" % (
+            # inside the stem kernel; the upload is 4x smaller than the fp32 tensor.  The depth image may also be
+            # given as the single plane [B,H,W] (or [B,H,W,1]) that cvtColor replicates to three channels
+            # (utils/utils.py:14-19): the stem replicates it, the result is identical, the upload a third.
+            plane = nir.dim() == 3 or (nir.dim() == 4 and nir.shape[3] == 1)
+            ok = (rgb.dtype == nir.dtype and rgb.dim() == 4 and rgb.shape[3] == 3 and
+                  (tuple(nir.shape[:3]) == tuple(rgb.shape[:3])) and (plane or nir.shape == rgb.shape))
+            if not ok:
+                raise ValueError("expected uint8 (B,H,W,3) images (depth optionally (B,H,W)), got %s %s and %s %s" % (
                     rgb.dtype, tuple(rgb.shape), nir.dtype, tuple(nir.shape)))
             b, h, w, _ = rgb.shape
-            eng = self._engine(b, h, w, rgb.device, input_u8=True)
+            if plane:
+                nir = nir.reshape(b, h, w)
+            eng = self._engine(b, h, w, rgb.device, input_u8=True, depth_plane=plane)
             with torch.no_grad():
                 dbox, cls, x = eng.run(rgb.detach().contiguous(), nir.detach().contiguous())
             self.anchors, self.strides, self.shape = eng.anchors, eng.strides, (b, x[0].shape[1], x[0].shape[2], x[0].shape[3])

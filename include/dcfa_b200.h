@@ -72,7 +72,13 @@ enum { DCFA_ACT_NONE = 0, DCFA_ACT_RELU = 1, DCFA_ACT_SILU = 2 };
 
 /* DCFA_OP_STEM flags: the inputs are uint8 NHWC images [group_imgs,Hi,Wi,3] (the output of cvtColor/resize_image,
  * utils/utils.py:9-37, before preprocess_input's /255, which the caller folds into `scale`) instead of fp32 NCHW */
-enum { DCFA_STEM_FLAG_U8 = 0x100 };
+enum {
+  DCFA_STEM_FLAG_U8 = 0x100,
+  /* with DCFA_STEM_FLAG_U8 and two groups: x2 is ONE uint8 plane per image [group_imgs,Hi,Wi] -- the depth image before
+   * cvtColor replicates it to three channels (utils/utils.py:14-19); the kernel replicates it, so the result is
+   * identical to passing the replicated image and the upload is a third of it */
+  DCFA_STEM_FLAG_X2_PLANE = 0x200
+};
 
 /* DCFA_OP_CONV flags (above the low 8 bits, which hold the k-block width of the TMA packing): this 1x1 conv, the DWCONV
  * after it and the 1x1 CONV after that form a chain whose two intermediate tensors nobody else reads and whose output
@@ -110,12 +116,14 @@ typedef struct dcfa_view {
 /*
  * One op of the flat execution plan.  Field use per kind:
  *
- * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 [G][128*32]: one 64B-swizzled
- *        K-major tile per group whose 128 rows are the Cout channels repeated with period BN (= Cout rounded up
- *        to 32/64/128), K = (ky*3+kx)*3+ci padded to 32, rows of channels with a negative BN scale negated;
+ * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 [G][3][2][128*16]: per group,
+ *        kernel row ky and pixel parity e one K-major tile in the canonical NO-SWIZZLE layout (element (m,k) at
+ *        (m/8)*128 + (k/8)*64 + (m%8)*8 + k%8) whose 128 rows are the Cout channels repeated with period BN (= Cout
+ *        rounded up to 32/64/128), K = (kx+e)*4 + ci (four consecutive pixels x 4 channel slots; unused slots zero),
+ *        rows of channels with a negative BN scale negated; w_gstride = 6*128*16;
  *        scale (>= 0), bias = fp32 [G][BN]; y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
- *        With flags & DCFA_STEM_FLAG_U8: x,x2 = uint8 NHWC [group_imgs,Hi,Wi,3], K = ky*10+kx*3+ci (slots 9,19,29
- *        and 30,31 zero), scale already divided by 255.
+ *        With flags & DCFA_STEM_FLAG_U8: x,x2 = uint8 NHWC [group_imgs,Hi,Wi,3] (x2 a single plane [group_imgs,Hi,Wi]
+ *        with DCFA_STEM_FLAG_X2_PLANE), scale already divided by 255.
  * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed
  *        [G][n_tiles][k_blocks][BN*64] (128B-swizzled K-major tile images, K = (ky*ks+kx)*Cin+ci, zero
  *        padded to k_blocks*64); scale,bias = fp32 [G][n_tiles*BN]; x2 = optional bf16 residual added

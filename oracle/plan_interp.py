@@ -80,21 +80,21 @@ def run_ops(ops, bufs):
         gi = n // G
         if k == 1:  # STEM: bf16 inputs and weights, fp32 accumulate, fp32 scale/bias, ReLU, pool, bf16 store
             c0 = op.Cout
-            # weight tile: 128 replicated rows x 32 K (SWIZZLE_64B); rows 0..C0-1 are one replica, sign-folded
-            wall = unswizzle_weights(bufs[op.w.buf], op.w.off, G, op.w_gstride, 128, 1, 1, 32)
+            # weight tiles [G][3][2][128 x 16] in the canonical no-swizzle K-major layout (pack.pack_stem); sign-folded
+            from dcfa_b200 import pack as _pack
+            wraw = bufs[op.w.buf][op.w.off:op.w.off + 2 * G * op.w_gstride].view(torch.bfloat16).view(G, -1)
             sc = _f32(bufs[op.scale.buf], op.scale.off, G * op.sb_gstride).view(G, -1)
             bi = _f32(bufs[op.bias.buf], op.bias.off, G * op.sb_gstride).view(G, -1)
             outs = []
             for g in range(G):
                 src = bufs[op.x.buf] if g == 0 else bufs[op.x2.buf]
-                if op.flags & 0x100:   # uint8 NHWC pixels, K = ky*10 + kx*3 + ci, scale already / 255
+                if (op.flags & 0x200) and g == 1:   # single uint8 plane, replicated to three channels by the kernel
+                    x = src.view(gi, 1, op.Hi, op.Wi).expand(gi, 3, op.Hi, op.Wi).float()
+                elif op.flags & 0x100:   # uint8 NHWC pixels, scale already / 255
                     x = src.view(gi, op.Hi, op.Wi, 3).permute(0, 3, 1, 2).float()
-                    wk = torch.cat([wall[g, :c0, ky * 10: ky * 10 + 9] for ky in range(3)], 1)
-                    assert float(wall[g, :, [9, 19, 29, 30, 31]].abs().max()) == 0.0
                 else:
                     x = src.view(torch.float32).view(gi, 3, op.Hi, op.Wi).to(torch.bfloat16).float()
-                    wk = wall[g, :c0, :27]
-                wt = wk.reshape(c0, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                wt = _pack.unpack_stem(wraw[g], c0)
                 y = F.conv2d(x, wt, None, 1, 1) * sc[g, :c0].view(1, -1, 1, 1) + bi[g, :c0].view(1, -1, 1, 1)
                 y = F.max_pool2d(F.relu(y), 3, 2, 1)
                 outs.append(y.permute(0, 2, 3, 1))

@@ -196,6 +196,13 @@ def test_uint8_nhwc_inputs_match_oracle_on_preprocessed_pixels(cuda):
     np.testing.assert_allclose(out[0].cpu().numpy(), out_f[0].cpu().numpy(), atol=4e-2, rtol=2e-2)
     with pytest.raises(ValueError):
         net(rgb8.permute(0, 3, 1, 2).contiguous().to(cuda), nir8.permute(0, 3, 1, 2).contiguous().to(cuda))
+    # the depth image as the single plane cvtColor would replicate (utils/utils.py:14-19): bit-identical outputs
+    plane = nir8[..., 0].contiguous()
+    rep = plane[..., None].expand(-1, -1, -1, 3).contiguous()
+    out_rep = net(rgb8.to(cuda), rep.to(cuda))
+    for shape in (plane, plane[..., None]):
+        out_pl = net(rgb8.to(cuda), shape.to(cuda))
+        assert torch.equal(out_pl[0], out_rep[0]) and torch.equal(out_pl[1], out_rep[1])
 
 
 def test_full_size_properties_at_the_bench_workload(cuda):

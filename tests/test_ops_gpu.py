@@ -174,7 +174,8 @@ def test_conv_f32_nchw_out(cuda):
 
 
 @pytest.mark.parametrize("b,h,w,c0,groups", [(1, 32, 64, 16, 1), (2, 40, 72, 32, 2), (1, 70, 130, 32, 1), (3, 33, 47, 48, 2),
-                                            (1, 64, 64, 80, 1), (2, 96, 128, 64, 2), (1, 640, 640, 32, 1)])
+                                            (1, 64, 64, 80, 1), (2, 96, 128, 64, 2), (1, 640, 640, 32, 1), (2, 5, 12, 32, 2),
+                                            (1, 100, 36, 128, 1)])
 def test_stem(cuda, b, h, w, c0, groups):
     """fused conv3x3+BN+ReLU+maxpool3/2 vs F.conv2d + F.max_pool2d (nets/yolo_mul.py:104-115)."""
     from dcfa_b200 import abi
@@ -199,7 +200,7 @@ def test_stem(cuda, b, h, w, c0, groups):
     bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
     op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
                     bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
-                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad)
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad)
     _run([op], bufs)
     bs = [bs[i] for i in range(groups)]
     ws = [ws[i] * 1.0 for i in range(groups)]
@@ -208,8 +209,40 @@ def test_stem(cuda, b, h, w, c0, groups):
     _bf16_close(y.cpu(), ref.permute(0, 2, 3, 1), "stem")
 
 
+@pytest.mark.parametrize("b,h,w,c0", [(2, 48, 64, 32), (1, 70, 130, 16), (2, 33, 47, 64), (1, 640, 640, 32)])
+def test_stem_uint8_depth_plane(cuda, b, h, w, c0):
+    """DCFA_STEM_FLAG_X2_PLANE: group 1 is ONE uint8 plane per image; bit-identical to the replicated 3-channel image
+    (what cvtColor produces, utils/utils.py:14-19) through the plain uint8 path."""
+    from dcfa_b200 import abi, pack
+    g = torch.Generator().manual_seed(8)
+    rgb = torch.randint(0, 256, (b, h, w, 3), generator=g, dtype=torch.uint8)
+    plane = torch.randint(0, 256, (b, h, w), generator=g, dtype=torch.uint8)
+    ws = [bf16_round(torch.randn(c0, 3, 3, 3, generator=g) * 0.3) for _ in range(2)]
+    bs = [torch.randn(c0, generator=g) * 0.2 for _ in range(2)]
+    scs = [torch.rand(c0, generator=g) - 0.3 for _ in range(2)]
+    packed, sks, bks, c0pad = [], [], [], 32
+    for i in range(2):
+        pk, sca, bia, c0pad = pack.pack_stem(ws[i], scs[i], bs[i], u8=True)
+        packed.append(pk); sks.append(sca); bks.append(bia)
+    wk, sk, bk = torch.stack(packed).to(cuda), torch.stack(sks).to(cuda), torch.stack(bks).to(cuda)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    outs = []
+    for flag, x2 in ((abi.STEM_FLAG_X2_PLANE, plane), (0, plane[..., None].expand(b, h, w, 3).contiguous())):
+        y = torch.zeros(2 * b, ho, wo, c0, dtype=torch.bfloat16, device=cuda)
+        bufs = [rgb.to(cuda), x2.to(cuda), wk, bk, y, sk]
+        op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1), w=flat_view(2), bias=flat_view(3), scale=flat_view(5),
+                        y=nhwc_view(y, 4), n_img=2 * b, group_imgs=b, Hi=h, Wi=w, Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1,
+                        k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad, flags=abi.STEM_FLAG_U8 | flag)
+        _run([op], bufs)
+        outs.append(y.cpu())
+    assert torch.equal(outs[0], outs[1])
+    x1 = plane[:, None].expand(b, 3, h, w).float() / 255.0
+    ref = F.max_pool2d(F.relu(F.conv2d(x1, ws[1], None, 1, 1) * scs[1].view(1, -1, 1, 1) + bs[1].view(1, -1, 1, 1)), 3, 2, 1)
+    _bf16_close(outs[0][b:], ref.permute(0, 2, 3, 1), "stem_u8_plane")
+
+
 @pytest.mark.parametrize("b,h,w,c0,groups", [(1, 32, 64, 16, 1), (2, 40, 80, 32, 2), (1, 70, 130, 32, 1), (3, 33, 47, 48, 2),
-                                            (2, 96, 128, 64, 2), (1, 640, 640, 32, 1)])
+                                            (2, 96, 128, 64, 2), (1, 640, 640, 32, 1), (1, 64, 64, 80, 1), (2, 9, 7, 32, 2)])
 def test_stem_uint8_nhwc(cuda, b, h, w, c0, groups):
     """DCFA_STEM_FLAG_U8: raw uint8 NHWC pixels; the kernel folds preprocess_input's /255 (utils/utils.py:76-79).
     Widths whose rows are 16-byte multiples take the TMA path, the others the plain-load path."""
@@ -230,7 +263,7 @@ def test_stem_uint8_nhwc(cuda, b, h, w, c0, groups):
     bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
     op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
                     bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
-                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=128 * 32, sb_gstride=c0pad,
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad,
                     flags=abi.STEM_FLAG_U8)
     _run([op], bufs)
     ref = torch.cat([F.max_pool2d(F.relu(F.conv2d(xs[i].permute(0, 3, 1, 2).float() / 255.0, ws[i], None, 1, 1)

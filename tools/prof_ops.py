@@ -58,7 +58,7 @@ def main():
         ts = []
         for _ in range(a.iters):
             e0.record(st)
-            _lib.check(_lib.lib.dcfa_run_ops(op1, count, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+            _lib.check(_lib.lib.dcfa_run_ops(op1, count, eng.last_bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
             e1.record(st)
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))

@@ -18,7 +18,7 @@ for name in sys.argv[1:]:
     i = eng.plan.op_names.index(name)
     op1 = (abi.Op * 1)(eng.plan.ops[i])
     for _ in range(2):
-        _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng._bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+        _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng.last_bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
     torch.cuda.synchronize()
     buf = np.zeros((8, 2048), np.int64)
     _lib.lib.dcfa_debug_read_timeline(buf.ctypes.data, buf.nbytes)
