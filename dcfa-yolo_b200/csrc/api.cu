@@ -13,7 +13,7 @@ namespace dcfa {
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-int g_sms = 0;
+int g_sms[64] = {};
 }  // namespace
 
 int fail(int code, const char* fmt, ...) {
@@ -35,16 +35,19 @@ bool pdl_enabled() {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  if (g_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sms = n;
-    else
-      g_sms = 148;
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (g_sms[dev] == 0) {
+    int n = 0;
+    g_sms[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return g_sms;
+  return g_sms[dev];
 }
 
 }  // namespace dcfa

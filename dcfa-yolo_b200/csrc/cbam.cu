@@ -716,11 +716,11 @@ int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& st
                         ((a.rows_per * a.W + 3) & ~3) + scratch;
   const size_t smem = floats * sizeof(float);
   if (smem > 200 * 1024) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(cbam_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.mark();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.n_img * CS));

@@ -449,13 +449,13 @@ int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "chain: cuTensorMapEncodeTiled failed with %d", (int)cr);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(chain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.mark();
   }
   const int ctas = C == 32 ? 3 : (C == 64 ? 2 : 1);   // matches the kernel's launch bounds; shared memory allows it
   int64_t grid = (int64_t)sm_count() * ctas;

@@ -16,7 +16,16 @@ namespace dcfa {
 // ---------------------------------------------------------------------------------------------
 int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
-int sm_count();
+int sm_count();        // SM count of the CURRENT device (cached per device ordinal)
+int current_device();  // cudaGetDevice, -1 on failure
+
+// One-time, PER-DEVICE setup guard (cudaFuncSetAttribute is a per-device property: a process-wide `static bool` would leave
+// the second GPU of a multi-device process without its shared-memory opt-in).  Use as a function-local static.
+struct DeviceOnce {
+  unsigned char done[64] = {};
+  bool needed() const { const int d = current_device(); return d < 0 || d >= 64 || !done[d]; }
+  void mark() { const int d = current_device(); if (d >= 0 && d < 64) done[d] = 1; }
+};
 
 #define DCFA_CHECK_LAUNCH(name)                                                         \
   do {                                                                                  \

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvArgs p
         const uint32_t ph = (it / (uint32_t)S) & 1u;
         ptx::mbar_wait(bar_full + 8u * s, ph);
         if (lane == 0) {
-          if (p.dbg & 1) ptx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+          ptx::fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_sw128_kmajor_desc(smem_a + s * A_STAGE_BYTES);
           const uint64_t bdesc = ptx::make_sw128_kmajor_desc(smem_b + s * b_stage_bytes);
@@ -415,13 +415,13 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
-  { const char* e = getenv("DCFA_DBG"); a.dbg = e ? atoi(e) : 1; }
+  a.dbg = 0;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.mark();
   }
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
   conv_gemm_kernel<<<grid, kThreads, smem, st>>>(a);

@@ -649,11 +649,11 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled failed with %d", (int)cr);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "conv(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.mark();
   }
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
   alignas(64) CUtensorMap tmap_y;

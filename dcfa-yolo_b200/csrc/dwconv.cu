@@ -454,14 +454,14 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
       t.res_slots = 1;
     }
     const size_t smem = (size_t)fixed + (size_t)t.nin * t.in_buf + (size_t)t.res_slots * t.out_buf;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.needed()) {
       const int mx_smem = 1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * CB + CB) * 4 + 64;
       cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e != cudaSuccess) return fail(DCFA_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
+      attr_set.mark();
     }
     int64_t grid = (int64_t)sm_count() * ctas;
     if (grid > total) grid = total;

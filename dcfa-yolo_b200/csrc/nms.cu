@@ -548,13 +548,13 @@ extern "C" int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, dou
     smem = std::max(smem, (size_t)(nloc + nloc / 16) * 8);
   }
   GreedyArgs ga{pred, keys, sbox, out_det, out_idx, out_cnt, out_cand, cand, B, A, Apad, nc, cap, (float)nms_thres, nms_thres};
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (attr_done.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(nms_cluster_kernel<DCFA_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemMax);
     cudaError_t e2 = cudaFuncSetAttribute(nms_cluster_kernel<DCFA_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemMax);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return fail(DCFA_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    attr_done = true;
+    attr_done.mark();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CS));

@@ -6,24 +6,29 @@
 // Round-1 version (ncu: 41 % issue-active, 0.97 TB/s): a generic-proxy im2col (27 LDS + converts + 4 STS per conv
 // pixel) and four CTA-wide phases per tile serialised behind __syncthreads.  This version has NO im2col:
 //
-//   * the input patch of a tile (9 x 36 pixels) is converted ONCE to bf16 [y][x][4 channels] (8 bytes per pixel,
+//   * the input patch of a tile (11 x 28 pixels) is converted ONCE to bf16 [y][x][4 channels] (8 bytes per pixel,
 //     channel 3 = 0) -- 1.3 shared-memory operations per input pixel instead of ~35 per conv pixel;
 //   * the tcgen05 shared-memory descriptor does the im2col: NO-SWIZZLE K-major layout with LBO = 16 B (next K chunk =
 //     next pixel pair) and SBO = 128 B (next 8 rows), i.e. operand row n = the 16 bf16 starting at pixel 2n of the
-//     LINEAR patch (pitch 36): four consecutive pixels x 4 channels.  Rows overlap in memory; the hardware only
-//     computes addresses (tools/umma_overlap_test.cu proves it).  One K=16 MMA per kernel row and per pixel PARITY:
-//     the even conv pixel 2n uses weights [w(ky,0) | w(ky,1) | w(ky,2) | 0], the odd conv pixel 2n+1 uses
+//     LINEAR patch (pitch 28): four consecutive pixels x 4 channels.  Rows overlap in memory; the hardware only
+//     computes addresses (tools/umma_overlap_test.cu proves it on a B200).  One K=16 MMA per kernel row and per pixel
+//     PARITY: the even conv pixel 2n uses weights [w(ky,0) | w(ky,1) | w(ky,2) | 0], the odd conv pixel 2n+1 uses
 //     [0 | w(ky,0) | w(ky,1) | w(ky,2)] over the SAME operand rows, into a second accumulator;
 //   * the GEMM is turned so that CHANNELS are the 128 MMA rows (C0 replicated 128/C0pad times) and pixels are TMEM
-//     columns: after tcgen05.ld a thread holds a window of ONE channel and the 3x3/2 max-pool is pure register
-//     arithmetic with three-input max; BN + ReLU after pooling (exact: the sign of the BN scale is folded into the
-//     weights, so the pooled quantity is monotone in the accumulator);
+//     columns: replica r of a channel owns POOLED ROW r of the tile (three conv rows, 14 TMEM columns per row and
+//     accumulator); the 3x3/2 max-pool is pure register arithmetic with three-input max; BN + ReLU after pooling
+//     (exact: the sign of the BN scale is folded into the weights, so the pooled quantity is monotone in the
+//     accumulator); the 6 pooled pixels x 32 channels of a warp leave through a 384-byte shared-memory slab and ONE
+//     TMA store (no global address arithmetic, edges clipped by the tensor map);
 //   * warp-specialised pipeline, one CTA per SM, all of TMEM (2 tiles x 2 parities x 128 columns):
-//       warp 12      TMA producer: raw patch ring (fp32 NCHW planes, uint8 NHWC rows or a uint8 depth plane)
-//       warps 8-11   converters: raw -> bf16 [y][x][4] (ring of 3), fence.proxy.async, arrive
-//       warp 13      MMA issuer: 6 x (M128 N128 K16) per tile, commits free the converted slot / publish the accumulators
-//       warps 0-7    two epilogue groups alternating tiles: tcgen05.ld, pool, BN, ReLU, 64-byte-per-pixel stores.
-// Tile: 3 x 16 pooled pixels = 7 x 33 conv pixels (linear index L = cy*36 + cx, parity = cx & 1, TMEM column L >> 1).
+//       warp 20      TMA producer: raw patch ring (fp32 NCHW planes, uint8 NHWC rows or a uint8 depth plane)
+//       warps 16-19  converters, ONE TILE PER WARP (four tiles in flight: the dependent LDS -> convert -> STS chain and the
+//                    proxy fence of one tile overlap the other three): raw -> bf16 [y][x][4], fence.proxy.async, arrive
+//       warp 21      MMA issuer: 6 x (M128 N128 K16) per tile, commits free the converted slot / publish the accumulators
+//       warps 0-15   two epilogue groups alternating tiles; per group two warps per TMEM lane quarter, each taking half of
+//                    the tile's pooled columns (ncu: one warp per quarter spent ~1 800 cycles per tile in dependent
+//                    tcgen05.ld -> max -> convert -> st.shared -> proxy fence -> TMA store chains).
+// Tile: 4 x 12 pooled pixels = 9 x 25 conv pixels (linear index L = cy*28 + cx, parity = cx & 1, TMEM column L >> 1).
 // Out-of-image conv positions are excluded from the max (reference: -inf pool padding); zero padding of the conv comes
 // from the TMA's out-of-bounds fill.
 #include <cuda.h>
@@ -36,32 +41,35 @@
 namespace dcfa {
 namespace {
 
-constexpr int TPH = 3, TPW = 16;              // pooled tile
-constexpr int CH = 2 * TPH + 1;               // 7 conv rows
-constexpr int CW = 2 * TPW + 1;               // 33 conv cols
-constexpr int PH = CH + 2;                    // 9 patch rows
-constexpr int PP = 36;                        // patch pitch in pixels (35 needed; even, so that parity(L) = parity(cx))
-constexpr int NCOL = 128;                     // MMA N = pixel pairs per parity (7 * 18 = 126 used)
+constexpr int TPH = 4, TPW = 12;              // pooled tile
+constexpr int CH = 2 * TPH + 1;               // 9 conv rows
+constexpr int CW = 2 * TPW + 1;               // 25 conv cols
+constexpr int PH = CH + 2;                    // 11 patch rows
+constexpr int PP = 28;                        // patch pitch in pixels (27 needed; even, so that parity(L) = parity(cx))
+constexpr int HP = PP / 2;                    // TMEM columns per conv row and parity
+constexpr int NCOL = 128;                     // MMA N = pixel pairs per parity (9 * 14 = 126 used)
 constexpr int XOFF = 2;                       // fp32: the TMA box starts 2 floats left of the patch (16-byte aligned start)
-constexpr int PWB = 40;                       // fp32 raw row pitch in floats (XOFF + 36, rounded to 16 bytes)
-constexpr int RAW_F32_BYTES = 3 * PH * PWB * 4;   // 4320
-constexpr int U8_LEFT = 16;                   // uint8: the box starts 16 pixels left of the tile's first pooled pixel column * 2
-constexpr int RAWB = 160;                     // uint8 NHWC raw row bytes: 3 * (14 + 36) = 150, rounded to 16
-constexpr int RAW_U8_BYTES = RAWB * PH;       // 1440
-constexpr int RAW1B = 64;                     // uint8 single plane raw row bytes: 14 + 36 = 50, rounded to 16
-constexpr int RAW_C1_BYTES = RAW1B * PH;      // 576
-constexpr int RAW_SLOT = 4352;                // bytes per raw ring slot (>= 4320, multiple of 128)
-constexpr int NRAW = 4;                       // raw ring depth
-constexpr int CVT_BYTES = PH * PP * 8;        // 2592: bf16 [9][36][4]
-constexpr int CVT_SLOT = 2688;                // + the rows the last MMA over-reads (columns 126, 127: never used), mult. of 128
-constexpr int NCVT = 3;                       // converted-patch ring depth
+constexpr int PWB = 32;                       // fp32 raw row pitch in floats (XOFF + 28, rounded to 16 bytes)
+constexpr int RAW_F32_BYTES = 3 * PH * PWB * 4;   // 4224
+constexpr int RAWB = 128;                     // uint8 NHWC raw row bytes: 3 * (14 + 28) = 126, rounded to 16
+constexpr int RAW_U8_BYTES = RAWB * PH;       // 1408
+constexpr int RAW1B = 48;                     // uint8 single plane raw row bytes: 14 + 28 = 42, rounded to 16
+constexpr int RAW_C1_BYTES = RAW1B * PH;      // 528
+constexpr int RAW_SLOT = 4224;                // bytes per raw ring slot (multiple of 128)
+constexpr int NRAW = 4;                       // raw ring depth = converter warps (warp w owns slot w)
+constexpr int CVT_SLOT = 2560;                // bf16 [11][28][4] = 2464 + the rows the last MMA over-reads (columns 126, 127)
+constexpr int NCVT = 4;                       // converted-patch ring depth = converter warps
 constexpr int A_TILE_BYTES = 128 * 16 * 2;    // one (kernel row, parity) weight tile
 constexpr int A_GROUP_BYTES = 6 * A_TILE_BYTES;
-constexpr int kEpiWarps = 8, kCvtWarps = 4;
+constexpr int HW = TPW / 2;                    // pooled pixels per epilogue warp (half a tile row)
+constexpr int OUT_SLAB = HW * 32 * 2;         // 384: half a pooled row of one warp, [6 pixels][32 channels] bf16
+constexpr int kEpiWarps = 16, kCvtWarps = 4;
 constexpr int kCvtWarp0 = kEpiWarps, kTmaWarp = kEpiWarps + kCvtWarps, kMmaWarp = kTmaWarp + 1;
-constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 448
+constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
 constexpr uint32_t kTmemCols = 512;
+static_assert(NRAW == kCvtWarps && NCVT == kCvtWarps, "converter warp w owns raw slot w and converted slot w");
 static_assert(2 * PP * 8 + (NCOL - 1) * 16 + 32 <= CVT_SLOT, "MMA over-read must stay inside the slot");
+static_assert((CH - 1) * HP + TPW + 1 <= NCOL, "tile does not fit the accumulator");
 
 enum { MODE_F32 = 0, MODE_U8 = 1, MODE_U8_C1 = 2 };   // MODE_U8_C1: group 0 uint8 NHWC, group 1 a single uint8 plane
 
@@ -73,7 +81,10 @@ struct StemArgs {
   View<__nv_bfloat16> y;
   int n_img, group_imgs, groups, Hi, Wi, Ho, Wo, C0, C0pad;
   int tiles_x, tiles_y;
-  int use_tma;
+  int use_tma;             // inputs through TMA boxes (else: plain loads with explicit zero padding)
+  int tma_out;             // output through per-warp slabs + TMA stores (else: direct 2-byte stores)
+  int box_c;               // channels per output slab row (min(32, C0) rounded to 8)
+  int dbg;                 // experiments only (DCFA_STEM_DBG): 1 no stores, 2 no input loads, 4 no MMAs, 8 direct stores
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
@@ -88,11 +99,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -103,12 +135,16 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 __device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
+// uint8 boxes must start on a 16-byte boundary: 3 * (2 * 12 * tx - L) = 72 tx - 3 L (and 24 tx - L for a single plane) is a
+// multiple of 16 for L = 16 on even tile columns and L = 8 on odd ones.  L = pixels between the box start and pooled column
+// px0's first conv input column + 2; the patch starts L - 2 pixels into the box.
+__device__ __forceinline__ int u8_left(int tx) { return (tx & 1) ? 8 : 16; }
 
-// Tile coordinates advanced incrementally (tile index += gridDim.x): the per-tile path has no divisions.
+// Tile coordinates advanced incrementally (tile index += step): the per-tile path has no divisions.
 // Tiles are ordered (image over both groups, tile row, tile column).
 struct TileIter {
   int tx, ty, n;       // tile column, tile row, image index over both groups
-  int sx, sy, sn;      // mixed-radix digits of the step gridDim.x
+  int sx, sy, sn;      // mixed-radix digits of the step
   __device__ __forceinline__ void init(int tile, int step, int tiles_x, int tiles_y) {
     const int per_img = tiles_x * tiles_y;
     n = tile / per_img;
@@ -135,38 +171,44 @@ __device__ __forceinline__ uint32_t u8x2_bf16(uint32_t lo, uint32_t hi) {   // t
 
 template <int MODE>
 __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_constant__ CUtensorMap map0,
-                                                              const __grid_constant__ CUtensorMap map1, const StemArgs p) {
+                                                              const __grid_constant__ CUtensorMap map1,
+                                                              const __grid_constant__ CUtensorMap map_y, const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: A weight tiles (2 groups x 24 KB) | raw ring | converted ring | barriers | tmem slot
+  // layout: A weight tiles (2 groups x 24 KB) | raw ring | converted ring | output slabs (8 warps x 2) | barriers | tmem slot
   const uint32_t s_a = base;
   const uint32_t s_raw = s_a + 2u * A_GROUP_BYTES;
   const uint32_t s_cvt = s_raw + (uint32_t)(NRAW * RAW_SLOT);
-  const uint32_t bars = s_cvt + (uint32_t)(NCVT * CVT_SLOT);
+  const uint32_t s_out = s_cvt + (uint32_t)(NCVT * CVT_SLOT);
+  const uint32_t bars = s_out + (uint32_t)(kEpiWarps * 2 * OUT_SLAB);
   const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8u * NRAW;
   const uint32_t bar_cvt_full = bars + 16u * NRAW, bar_cvt_empty = bar_cvt_full + 8u * NCVT;
   const uint32_t bar_tm_full = bar_cvt_empty + 8u * NCVT, bar_tm_empty = bar_tm_full + 16u;
   const uint32_t tmem_slot = bar_tm_empty + 16u;
   uint8_t* raw_ptr = gbase + 2 * A_GROUP_BYTES;
   uint8_t* cvt_ptr = raw_ptr + NRAW * RAW_SLOT;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(cvt_ptr + NCVT * CVT_SLOT + (tmem_slot - bars));
+  uint8_t* out_ptr = cvt_ptr + NCVT * CVT_SLOT;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(out_ptr + kEpiWarps * 2 * OUT_SLAB + (tmem_slot - bars));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(bar_raw_full + 8u * i, 1); ptx::mbar_init(bar_raw_empty + 8u * i, kCvtWarps); }
-      for (int i = 0; i < NCVT; ++i) { ptx::mbar_init(bar_cvt_full + 8u * i, kCvtWarps); ptx::mbar_init(bar_cvt_empty + 8u * i, 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 4); }
+      for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(bar_raw_full + 8u * i, 1); ptx::mbar_init(bar_raw_empty + 8u * i, 1); }
+      for (int i = 0; i < NCVT; ++i) { ptx::mbar_init(bar_cvt_full + 8u * i, 1); ptx::mbar_init(bar_cvt_empty + 8u * i, 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 8); }
       ptx::fence_mbar_init();
     }
     __syncwarp();
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
-  if (warp == kTmaWarp && lane == 0 && p.use_tma) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
-    if (p.groups > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
+  if (warp == kTmaWarp && lane == 0) {
+    if (p.use_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
+      if (p.groups > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
+    }
+    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_y)) : "memory");
   }
   {  // weight tiles of every group (constant parameters: no dependency on the previous kernel) and zeroed patch slots
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
@@ -184,16 +226,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot_ptr;
   ptx::pdl_wait();
 
-  TileIter cur;
-  cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0 && p.use_tma) {
+    if (lane == 0 && p.use_tma && !(p.dbg & 2)) {
+      TileIter cur;
+      cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
       uint32_t s = 0, ph = 0;
       for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y)) {
         const uint32_t full = bar_raw_full + 8u * s, dst = s_raw + s * (uint32_t)RAW_SLOT;
-        ptx::mbar_wait(bar_raw_empty + 8u * s, ph ^ 1u);
+        ptx::mbar_wait_parked(bar_raw_empty + 8u * s, ph ^ 1u);
         const int g = cur.n >= p.group_imgs ? 1 : 0;
         const int nl = cur.n - g * p.group_imgs;
         const int y = 2 * cur.ty * TPH - 2;
@@ -204,12 +245,12 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
           if (g == 0) tma_load_4d(dst, &map0, x, y, 0, nl, full);
           else tma_load_4d(dst, &map1, x, y, 0, nl, full);
         } else if (MODE == MODE_U8 || g == 0) {
-          const int xb = 3 * (2 * cur.tx * TPW - U8_LEFT);
+          const int xb = 3 * (2 * cur.tx * TPW - u8_left(cur.tx));
           ptx::mbar_arrive_expect_tx(full, RAW_U8_BYTES);
           if (g == 0) tma_load_3d(dst, &map0, xb, y, nl, full);
           else tma_load_3d(dst, &map1, xb, y, nl, full);
         } else {
-          const int xb = 2 * cur.tx * TPW - U8_LEFT;
+          const int xb = 2 * cur.tx * TPW - u8_left(cur.tx);
           ptx::mbar_arrive_expect_tx(full, RAW_C1_BYTES);
           tma_load_3d(dst, &map1, xb, y, nl, full);
         }
@@ -219,7 +260,12 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
+      TileIter cur;
+      cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
       const uint32_t idesc = ptx::make_idesc_bf16_f32(128, NCOL);
+      // descriptors: only the 14-bit start-address field changes
+      const uint64_t bd_hi = desc_nosw(0u, 16u, 128u);    // operand rows: row n = 16 bf16 at pixel 2n (linear): LBO 16, SBO 128
+      const uint64_t ad_hi = desc_nosw(0u, 128u, 256u);   // canonical weight tiles
       uint32_t cs = 0, cph = 0, it = 0;
       for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), ++it) {
         const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
@@ -227,17 +273,17 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
         ptx::mbar_wait(bar_tm_empty + 8u * ab, aph ^ 1u);
         ptx::mbar_wait(bar_cvt_full + 8u * cs, cph);
         ptx::tc_fence_after();
-        const uint32_t b0 = s_cvt + cs * (uint32_t)CVT_SLOT;
-        const uint32_t a0 = s_a + (uint32_t)g * A_GROUP_BYTES;
+        const uint32_t b0 = ((s_cvt + cs * (uint32_t)CVT_SLOT) & 0x3FFFFu) >> 4;
+        const uint32_t a0 = ((s_a + (uint32_t)g * A_GROUP_BYTES) & 0x3FFFFu) >> 4;
         const uint32_t d0 = tmem_base + ab * 256u;
+        if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          // operand rows: row n = 16 bf16 at pixel 2n of patch row ky (+ the tile's conv rows, linear): LBO 16, SBO 128
-          const uint64_t bd = desc_nosw(b0 + (uint32_t)(ky * PP * 8), 16u, 128u);
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t bd = bd_hi | (uint64_t)(b0 + (uint32_t)(ky * PP * 8 / 16));
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const uint64_t ad = desc_nosw(a0 + (uint32_t)((ky * 2 + e) * A_TILE_BYTES), 128u, 256u);
-            ptx::umma_bf16(d0 + (uint32_t)(e * NCOL), ad, bd, idesc, ky > 0 ? 1u : 0u);
+            for (int e = 0; e < 2; ++e)
+              ptx::umma_bf16(d0 + (uint32_t)(e * NCOL), ad_hi | (uint64_t)(a0 + (uint32_t)((ky * 2 + e) * A_TILE_BYTES / 16)), bd, idesc,
+                             ky > 0 ? 1u : 0u);
           }
         }
         ptx::umma_commit(bar_cvt_empty + 8u * cs);   // the converted patch may be overwritten
@@ -247,185 +293,222 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
   } else if (warp >= kCvtWarp0) {
     // ------------------------------------------------------------------ converters: raw patch -> bf16 [y][x][4]
-    const int ctid = tid - kCvtWarp0 * 32;
-    uint32_t rs = 0, rph = 0, cs = 0, cph = 0;
-    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y)) {
+    // Converter warp w owns the tiles blockIdx.x + (4 i + w) * gridDim.x, raw slot w and converted slot w.
+    const int cw = warp - kCvtWarp0;
+    TileIter cur;
+    cur.init(blockIdx.x + cw * gridDim.x, kCvtWarps * gridDim.x, p.tiles_x, p.tiles_y);
+    const bool tma_in = p.use_tma && !(p.dbg & 2);
+    const uint8_t* raw = raw_ptr + cw * RAW_SLOT;
+    uint8_t* cvt = cvt_ptr + cw * CVT_SLOT;
+    const uint32_t b_raw_full = bar_raw_full + 8u * cw, b_raw_empty = bar_raw_empty + 8u * cw;
+    const uint32_t b_cvt_full = bar_cvt_full + 8u * cw, b_cvt_empty = bar_cvt_empty + 8u * cw;
+    // tile-invariant item geometry of this lane.  fp32: item = (patch row r, pixel pair q), 154 items = 5 per lane;
+    // uint8: item = (patch row r, 4 pixels q), 77 items = 3 per lane
+    constexpr int NI_F = (PH * HP + 31) / 32, NI_U = (PH * (PP / 4) + 31) / 32;
+    int rr[NI_F], qq[NI_F];
+#pragma unroll
+    for (int k = 0; k < NI_F; ++k) {
+      const int item = lane + 32 * k;
+      const int per = MODE == MODE_F32 ? HP : PP / 4;
+      rr[k] = item / per;
+      qq[k] = item - rr[k] * per;
+    }
+    uint32_t ph = 0;
+    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), ph ^= 1u) {
       const int g = cur.n >= p.group_imgs ? 1 : 0;
       const int nl = cur.n - g * p.group_imgs;
-      ptx::mbar_wait(bar_cvt_empty + 8u * cs, cph ^ 1u);
-      if (p.use_tma) ptx::mbar_wait(bar_raw_full + 8u * rs, rph);
-      const uint8_t* raw = raw_ptr + rs * RAW_SLOT;
-      uint8_t* cvt = cvt_ptr + cs * CVT_SLOT;
+      ptx::mbar_wait_parked(b_cvt_empty, ph ^ 1u);
+      if (tma_in) ptx::mbar_wait_parked(b_raw_full, ph);
       const int iy0 = 2 * cur.ty * TPH - 2, ix0 = 2 * cur.tx * TPW - 2;   // image coordinates of patch pixel (0, 0)
       if (MODE == MODE_F32) {
-        // item = (patch row r, pixel pair q): three 64-bit loads (one per channel plane), one 128-bit store
-        for (int item = ctid; item < PH * (PP / 2); item += kCvtWarps * 32) {
-          const int r = item / (PP / 2), q = item - r * (PP / 2);
-          float2 c0, c1, c2;
-          if (p.use_tma) {
-            const float* src = reinterpret_cast<const float*>(raw) + r * PWB + XOFF + 2 * q;
-            c0 = *reinterpret_cast<const float2*>(src);
-            c1 = *reinterpret_cast<const float2*>(src + PH * PWB);
-            c2 = *reinterpret_cast<const float2*>(src + 2 * PH * PWB);
-          } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
-            const float* img = reinterpret_cast<const float*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
-            const int iy = iy0 + r, ix = ix0 + 2 * q;
-            const bool yok = iy >= 0 && iy < p.Hi, a = yok && ix >= 0 && ix < p.Wi, b = yok && ix + 1 >= 0 && ix + 1 < p.Wi;
-            const int64_t o = (int64_t)iy * p.Wi + ix, pl = (int64_t)p.Hi * p.Wi;
-            c0 = make_float2(a ? __ldg(img + o) : 0.f, b ? __ldg(img + o + 1) : 0.f);
-            c1 = make_float2(a ? __ldg(img + pl + o) : 0.f, b ? __ldg(img + pl + o + 1) : 0.f);
-            c2 = make_float2(a ? __ldg(img + 2 * pl + o) : 0.f, b ? __ldg(img + 2 * pl + o + 1) : 0.f);
-          }
-          const uint4 o4 = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f));
-          *reinterpret_cast<uint4*>(cvt + (r * PP + 2 * q) * 8) = o4;
-        }
-      } else if (MODE == MODE_U8 || g == 0) {
-        // item = (patch row r, 4 pixels): 12 bytes -> 32 bytes.  0..255 are exact bf16 integers; preprocess_input's 1/255
-        // (utils/utils.py:76-79) is folded into the BN scale.
-        for (int item = ctid; item < PH * (PP / 4); item += kCvtWarps * 32) {
-          const int r = item / (PP / 4), q = item - r * (PP / 4);
-          uint32_t b[12];
-          if (p.use_tma) {
-            const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAWB + 3 * (U8_LEFT - 2) + 12 * q);
+        // three 64-bit loads (one per channel plane) and one 128-bit store per item; all loads of the lane's items are
+        // issued before the first convert (independent chains)
+        float2 c[NI_F][3];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { const uint32_t h = src[k]; b[2 * k] = h & 0xffu; b[2 * k + 1] = h >> 8; }
-          } else {
-            const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * p.Hi * p.Wi * 3;
-            const int iy = iy0 + r;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-              const int ix = ix0 + 4 * q + k / 3;
-              b[k] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + ((int64_t)iy * p.Wi + ix) * 3 + k % 3) : 0u;
+        for (int k = 0; k < NI_F; ++k) {
+          if (lane + 32 * k < PH * HP) {
+            const int r = rr[k], q = qq[k];
+            if (p.use_tma) {
+              const float* src = reinterpret_cast<const float*>(raw) + r * PWB + XOFF + 2 * q;
+              c[k][0] = *reinterpret_cast<const float2*>(src);
+              c[k][1] = *reinterpret_cast<const float2*>(src + PH * PWB);
+              c[k][2] = *reinterpret_cast<const float2*>(src + 2 * PH * PWB);
+            } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
+              const float* img = reinterpret_cast<const float*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
+              const int iy = iy0 + r, ix = ix0 + 2 * q;
+              const bool yok = iy >= 0 && iy < p.Hi, a = yok && ix >= 0 && ix < p.Wi, b = yok && ix + 1 >= 0 && ix + 1 < p.Wi;
+              const int64_t o = (int64_t)iy * p.Wi + ix, pl = (int64_t)p.Hi * p.Wi;
+              c[k][0] = make_float2(a ? __ldg(img + o) : 0.f, b ? __ldg(img + o + 1) : 0.f);
+              c[k][1] = make_float2(a ? __ldg(img + pl + o) : 0.f, b ? __ldg(img + pl + o + 1) : 0.f);
+              c[k][2] = make_float2(a ? __ldg(img + 2 * pl + o) : 0.f, b ? __ldg(img + 2 * pl + o + 1) : 0.f);
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
-          dst[0] = make_uint4(u8x2_bf16(b[0], b[1]), u8x2_bf16(b[2], 0u), u8x2_bf16(b[3], b[4]), u8x2_bf16(b[5], 0u));
-          dst[1] = make_uint4(u8x2_bf16(b[6], b[7]), u8x2_bf16(b[8], 0u), u8x2_bf16(b[9], b[10]), u8x2_bf16(b[11], 0u));
+        }
+#pragma unroll
+        for (int k = 0; k < NI_F; ++k) {
+          if (lane + 32 * k < PH * HP) {
+            const uint4 o4 = make_uint4(pack_bf16x2(c[k][0].x, c[k][1].x), pack_bf16x2(c[k][2].x, 0.f),
+                                        pack_bf16x2(c[k][0].y, c[k][1].y), pack_bf16x2(c[k][2].y, 0.f));
+            *reinterpret_cast<uint4*>(cvt + (rr[k] * PP + 2 * qq[k]) * 8) = o4;
+          }
+        }
+      } else if (MODE == MODE_U8 || g == 0) {
+        // 12 bytes -> 32 bytes per item.  0..255 are exact bf16 integers; preprocess_input's 1/255 (utils/utils.py:76-79)
+        // is folded into the BN scale.
+        const int left = 3 * (u8_left(cur.tx) - 2);
+#pragma unroll
+        for (int k = 0; k < NI_U; ++k) {
+          if (lane + 32 * k < PH * (PP / 4)) {
+            const int r = rr[k], q = qq[k];
+            uint32_t b[12];
+            if (p.use_tma) {
+              const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAWB + left + 12 * q);
+#pragma unroll
+              for (int j = 0; j < 6; ++j) { const uint32_t h = src[j]; b[2 * j] = h & 0xffu; b[2 * j + 1] = h >> 8; }
+            } else {
+              const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * p.Hi * p.Wi * 3;
+              const int iy = iy0 + r;
+#pragma unroll
+              for (int j = 0; j < 12; ++j) {
+                const int ix = ix0 + 4 * q + j / 3;
+                b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + ((int64_t)iy * p.Wi + ix) * 3 + j % 3) : 0u;
+              }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
+            dst[0] = make_uint4(u8x2_bf16(b[0], b[1]), u8x2_bf16(b[2], 0u), u8x2_bf16(b[3], b[4]), u8x2_bf16(b[5], 0u));
+            dst[1] = make_uint4(u8x2_bf16(b[6], b[7]), u8x2_bf16(b[8], 0u), u8x2_bf16(b[9], b[10]), u8x2_bf16(b[11], 0u));
+          }
         }
       } else {
         // single uint8 plane (the depth image before cvtColor replicates it, utils/utils.py:14-19): 4 bytes -> 32 bytes,
         // each value written to the three channel slots -- identical to uploading the replicated image
-        for (int item = ctid; item < PH * (PP / 4); item += kCvtWarps * 32) {
-          const int r = item / (PP / 4), q = item - r * (PP / 4);
-          uint32_t b[4];
-          if (p.use_tma) {
-            const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAW1B + (U8_LEFT - 2) + 4 * q);
-            const uint32_t h0 = src[0], h1 = src[1];
-            b[0] = h0 & 0xffu; b[1] = h0 >> 8; b[2] = h1 & 0xffu; b[3] = h1 >> 8;
-          } else {
-            const uint8_t* img = reinterpret_cast<const uint8_t*>(p.x[1]) + (int64_t)nl * p.Hi * p.Wi;
-            const int iy = iy0 + r;
+        const int left = u8_left(cur.tx) - 2;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ix = ix0 + 4 * q + k;
-              b[k] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + (int64_t)iy * p.Wi + ix) : 0u;
+        for (int k = 0; k < NI_U; ++k) {
+          if (lane + 32 * k < PH * (PP / 4)) {
+            const int r = rr[k], q = qq[k];
+            uint32_t b[4];
+            if (p.use_tma) {
+              const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAW1B + left + 4 * q);
+              const uint32_t h0 = src[0], h1 = src[1];
+              b[0] = h0 & 0xffu; b[1] = h0 >> 8; b[2] = h1 & 0xffu; b[3] = h1 >> 8;
+            } else {
+              const uint8_t* img = reinterpret_cast<const uint8_t*>(p.x[1]) + (int64_t)nl * p.Hi * p.Wi;
+              const int iy = iy0 + r;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ix = ix0 + 4 * q + j;
+                b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + (int64_t)iy * p.Wi + ix) : 0u;
+              }
             }
+            uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
+            const uint32_t p0 = u8x2_bf16(b[0], b[0]), p1 = u8x2_bf16(b[1], b[1]), p2 = u8x2_bf16(b[2], b[2]), p3 = u8x2_bf16(b[3], b[3]);
+            dst[0] = make_uint4(p0, p0 & 0xffffu, p1, p1 & 0xffffu);
+            dst[1] = make_uint4(p2, p2 & 0xffffu, p3, p3 & 0xffffu);
           }
-          uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
-          const uint32_t p0 = u8x2_bf16(b[0], b[0]), p1 = u8x2_bf16(b[1], b[1]), p2 = u8x2_bf16(b[2], b[2]), p3 = u8x2_bf16(b[3], b[3]);
-          dst[0] = make_uint4(p0, p0 & 0xffffu, p1, p1 & 0xffffu);
-          dst[1] = make_uint4(p2, p2 & 0xffffu, p3, p3 & 0xffffu);
         }
       }
       ptx::fence_proxy_async_smem();   // this thread's st.shared -> visible to the async proxy (MMA operand reads)
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_arrive(bar_cvt_full + 8u * cs);
-        if (p.use_tma) ptx::mbar_arrive(bar_raw_empty + 8u * rs);
+        ptx::mbar_arrive(b_cvt_full);
+        if (tma_in) ptx::mbar_arrive(b_raw_empty);
       }
-      if (++rs == NRAW) { rs = 0; rph ^= 1u; }
-      if (++cs == NCVT) { cs = 0; cph ^= 1u; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: group = tile parity, warp & 3 = TMEM lane quarter
-    const int q4 = warp & 3, grp = warp >> 2;
+    const int q4 = warp & 3, grp = (warp >> 2) & 1, half = warp >> 3;
     const int mrow = q4 * 32 + lane;              // accumulator row (TMEM lane)
     const int ch = mrow & (p.C0pad - 1);          // C0pad is 32, 64 or 128
-    const int rep = mrow / p.C0pad;               // replica: handles the units rep, rep + nrep, ...
+    const int rep = mrow / p.C0pad;               // replica: handles the pooled rows rep, rep + nrep, ...
     const int nrep = 128 / p.C0pad;
+    const int chan0 = ch - lane;                  // first channel of this warp (multiple of 32)
     const bool ch_valid = ch < p.C0;
+    const bool warp_valid = chan0 < p.C0;
     float sc[2], bi[2];
     sc[0] = __ldg(p.scale + ch); bi[0] = __ldg(p.bias + ch);
     sc[1] = p.groups > 1 ? __ldg(p.scale + p.C0pad + ch) : sc[0];
     bi[1] = p.groups > 1 ? __ldg(p.bias + p.C0pad + ch) : bi[0];
-    uint32_t it = 0;
-    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), ++it) {
-      if ((int)(it & 1u) != grp) continue;
-      const uint32_t aph = (it >> 1) & 1u;
+    const uint32_t slab0 = s_out + (uint32_t)(warp * 2 * OUT_SLAB);
+    uint8_t* slab_ptr0 = out_ptr + warp * 2 * OUT_SLAB;
+    const int pitch = p.box_c * 2;                // slab row pitch in bytes (channels of one pixel)
+    const bool tma_out = p.tma_out && !(p.dbg & 8);
+    uint32_t slab_sel = 0;
+    TileIter cur;                                 // this group's tiles: blockIdx.x + (2 i + grp) * gridDim.x
+    cur.init(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, p.tiles_x, p.tiles_y);
+    uint32_t aph = 0;
+    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), aph ^= 1u) {
       const int g = cur.n >= p.group_imgs ? 1 : 0;
       const float s = g ? sc[1] : sc[0], b = g ? bi[1] : bi[0];
-      const int py0 = cur.ty * TPH, px0 = cur.tx * TPW;
-      const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // image coordinates of conv pixel (0, 0) of the tile
-      const bool border = cy0 < 0 || cx0 < 0 || cy0 + CH > p.Hi || cx0 + CW > p.Wi;
-      __nv_bfloat16* ybase = p.y.p + p.y.img_off(cur.n) + ch;
-      ptx::mbar_wait(bar_tm_full + 8u * grp, aph);
+      const int py0 = cur.ty * TPH, px0 = cur.tx * TPW + HW * half;
+      const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // image coordinates of this warp's first conv pixel
+      const bool border = cy0 < 0 || cx0 < 0 || cy0 + CH > p.Hi || cx0 + 2 * HW + 1 > p.Wi;
+      ptx::mbar_wait_parked(bar_tm_full + 8u * grp, aph);
       ptx::tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)grp * 256u;
-      for (int u = rep; u < TPW / 4; u += nrep) {
-        // unit u: pooled columns 4u..4u+3 = conv columns 8u..8u+8: per conv row five even columns (accumulator 0,
-        // TMEM columns cy*18 + 4u + 0..4) and four odd ones (accumulator 1, columns cy*18 + 4u + 0..3)
-        uint32_t E[CH][8], O[CH][4];
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)grp * 256u + (uint32_t)(HW * half);
+      for (int r = rep; r < TPH; r += nrep) {
+        // pooled row r, pooled columns 6*half .. 6*half+5 = conv rows 2r..2r+2 x conv columns 12*half .. 12*half+12: per conv
+        // row 7 even columns (accumulator 0, TMEM columns 14*(2r+j) + 6*half + 0..6) and 6 odd ones (accumulator 1)
+        uint32_t E[3][8], O[3][8];
 #pragma unroll
-        for (int cy = 0; cy < CH; ++cy) {
-          tmem_ld_x8(t0 + (uint32_t)(cy * (PP / 2) + 4 * u), E[cy]);
-          ptx::tmem_ld_x4(t0 + (uint32_t)(NCOL + cy * (PP / 2) + 4 * u), O[cy]);
+        for (int j = 0; j < 3; ++j) {
+          tmem_ld_x8(t0 + (uint32_t)(HP * (2 * r + j)), E[j]);
+          tmem_ld_x8(t0 + (uint32_t)(NCOL + HP * (2 * r + j)), O[j]);
         }
         ptx::tmem_ld_wait();
-        if (u + nrep >= TPW / 4) {   // last unit of this thread: the accumulators may be overwritten by the next tile
+        if (r + nrep >= TPH) {   // last row of this thread: the accumulators may be overwritten by the next tile
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar_tm_empty + 8u * grp);
         }
-        float ve[5][CH], vo[4][CH];
-#pragma unroll
-        for (int cy = 0; cy < CH; ++cy) {
-#pragma unroll
-          for (int i = 0; i < 5; ++i) ve[i][cy] = __uint_as_float(E[cy][i]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) vo[i][cy] = __uint_as_float(O[cy][i]);
-        }
         if (border) {   // exclude out-of-image conv positions from the max (reference: -inf pool padding)
 #pragma unroll
-          for (int cy = 0; cy < CH; ++cy) {
-            const bool yok = cy0 + cy >= 0 && cy0 + cy < p.Hi;
+          for (int j = 0; j < 3; ++j) {
+            const bool yok = cy0 + 2 * r + j >= 0 && cy0 + 2 * r + j < p.Hi;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const int gx = cx0 + 8 * u + 2 * i;
-              if (!(yok && gx >= 0 && gx < p.Wi)) ve[i][cy] = -INFINITY;
-            }
+            for (int i = 0; i < HW + 1; ++i)
+              if (!(yok && cx0 + 2 * i >= 0 && cx0 + 2 * i < p.Wi)) E[j][i] = 0xff800000u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int gx = cx0 + 8 * u + 2 * i + 1;
-              if (!(yok && gx >= 0 && gx < p.Wi)) vo[i][cy] = -INFINITY;
-            }
+            for (int i = 0; i < HW; ++i)
+              if (!(yok && cx0 + 2 * i + 1 < p.Wi)) O[j][i] = 0xff800000u;
           }
         }
-        // vertical 3-max at stride 2 per conv column, then horizontal 3-max at stride 2
-        float he[5][TPH], ho[4][TPH];
+        // vertical 3-max per conv column, then horizontal 3-max at stride 2
+        float ve[HW + 1], vo[HW];
 #pragma unroll
-        for (int pr = 0; pr < TPH; ++pr) {
+        for (int i = 0; i < HW + 1; ++i) ve[i] = max3(__uint_as_float(E[0][i]), __uint_as_float(E[1][i]), __uint_as_float(E[2][i]));
 #pragma unroll
-          for (int i = 0; i < 5; ++i) he[i][pr] = max3(ve[i][2 * pr], ve[i][2 * pr + 1], ve[i][2 * pr + 2]);
+        for (int i = 0; i < HW; ++i) vo[i] = max3(__uint_as_float(O[0][i]), __uint_as_float(O[1][i]), __uint_as_float(O[2][i]));
+        float o[HW];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ho[i][pr] = max3(vo[i][2 * pr], vo[i][2 * pr + 1], vo[i][2 * pr + 2]);
-        }
-        if (ch_valid) {
+        for (int pc = 0; pc < HW; ++pc) o[pc] = fmaxf(fmaf(max3(ve[pc], vo[pc], ve[pc + 1]), s, b), 0.0f);
+        const int py = py0 + r;
+        if (tma_out) {
+          // [6 pixels][box_c channels] slab -> one TMA store (clipped at the image edge and at C0 by the tensor map)
+          const uint32_t slab = slab0 + slab_sel * (uint32_t)OUT_SLAB;
+          uint8_t* sp = slab_ptr0 + slab_sel * OUT_SLAB + lane * 2;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this slab
+          __syncwarp();
+          if (ch_valid) {
 #pragma unroll
-          for (int pr = 0; pr < TPH; ++pr) {
-            const int py = py0 + pr;
-            if (py < p.Ho) {
-              __nv_bfloat16* yrow = ybase + (int64_t)(py * p.Wo + px0 + 4 * u) * p.y.ld;
-#pragma unroll
-              for (int pc = 0; pc < 4; ++pc) {
-                const float m = max3(he[pc][pr], ho[pc][pr], he[pc + 1][pr]);
-                const float o = fmaxf(fmaf(m, s, b), 0.0f);
-                if (px0 + 4 * u + pc < p.Wo) yrow[pc * p.y.ld] = __float2bfloat16_rn(o);
-              }
-            }
+            for (int pc = 0; pc < HW; ++pc) *reinterpret_cast<__nv_bfloat16*>(sp + pc * pitch) = __float2bfloat16_rn(o[pc]);
           }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (warp_valid && py < p.Ho && px0 < p.Wo && !(p.dbg & 1)) tma_store_4d(&map_y, slab, chan0, px0, py, cur.n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          slab_sel ^= 1u;
+        } else if (ch_valid && py < p.Ho && !(p.dbg & 1)) {
+          __nv_bfloat16* yrow = p.y.p + p.y.img_off(cur.n) + (int64_t)(py * p.Wo + px0) * p.y.ld + ch;
+#pragma unroll
+          for (int pc = 0; pc < HW; ++pc)
+            if (px0 + pc < p.Wo) yrow[pc * p.y.ld] = __float2bfloat16_rn(o[pc]);
         }
       }
     }
+    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs must outlive their stores
   }
 
   ptx::tc_fence_before();
@@ -480,6 +563,11 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0, "stem: weights must be 16-byte aligned");
   a.groups = a.n_img / a.group_imgs;
   DCFA_REQUIRE(!c1 || (u8 && a.groups == 2), "stem: the single-plane flag needs uint8 inputs and two groups");
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DCFA_STEM_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   a.tiles_x = ceil_div(a.Wo, TPW);
   a.tiles_y = ceil_div(a.Ho, TPH);
   const int64_t total = (int64_t)a.n_img * a.tiles_x * a.tiles_y;
@@ -525,16 +613,37 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
       if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled failed with %d", (int)cr);
     }
   }
-  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + 256;
-  cudaError_t e = cudaFuncSetAttribute(stem_kernel<MODE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_kernel<MODE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_kernel<MODE_U8_C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(DCFA_E_CUDA, "stem: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  // ---- output tensor map: dims (C0, Wo, Ho, N) over the NHWC view, box (box_c channels, 12 pixels, 1, 1)
+  alignas(64) CUtensorMap map_y;
+  memset(&map_y, 0, sizeof(map_y));
+  a.box_c = a.C0 >= 32 ? 32 : (a.C0 + 7) / 8 * 8;
+  a.tma_out = (a.C0 % 8 == 0 && ((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 &&
+               (a.y.gi <= 0 || a.y.gstride == (int64_t)a.y.gi * a.y.img_stride)) ? 1 : 0;
+  if (a.tma_out) {
+    EncodeTiledFn enc = stem_encode_fn();
+    DCFA_REQUIRE(enc != nullptr, "stem: cuTensorMapEncodeTiled entry point unavailable");
+    const cuuint64_t ydim[4] = {(cuuint64_t)a.C0, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.n_img};
+    const cuuint64_t ystr[3] = {(cuuint64_t)a.y.ld * 2, (cuuint64_t)a.Wo * a.y.ld * 2, (cuuint64_t)a.y.img_stride * 2};
+    const cuuint32_t ybox[4] = {(cuuint32_t)a.box_c, (cuuint32_t)HW, 1u, 1u};
+    const cuuint32_t yes[4] = {1u, 1u, 1u, 1u};
+    CUresult cr = enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.y.p, ydim, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
+  }
+  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + kEpiWarps * 2 * OUT_SLAB + 256;
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(stem_kernel<MODE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_kernel<MODE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_kernel<MODE_U8_C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "stem: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set.mark();
+  }
   int64_t grid = sm_count();   // one CTA per SM: the kernel owns all 512 TMEM columns
   if (grid > total) grid = total;
-  if (!u8) launch_pdl(stem_kernel<MODE_F32>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], a);
-  else if (!c1) launch_pdl(stem_kernel<MODE_U8>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], a);
-  else launch_pdl(stem_kernel<MODE_U8_C1>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], a);
+  if (!u8) launch_pdl(stem_kernel<MODE_F32>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+  else if (!c1) launch_pdl(stem_kernel<MODE_U8>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+  else launch_pdl(stem_kernel<MODE_U8_C1>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
   DCFA_CHECK_LAUNCH("stem_kernel");
   return DCFA_OK;
 }

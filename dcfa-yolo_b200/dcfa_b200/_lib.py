@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdcfa_b200.so")
 
 # every symbol include/dcfa_b200.h declares
 SYMBOLS = ("dcfa_abi_version", "dcfa_sizeof_view", "dcfa_sizeof_op", "dcfa_last_error", "dcfa_device_check",
-           "dcfa_launch_count", "dcfa_run_ops", "dcfa_decode_box", "dcfa_nms_workspace_bytes", "dcfa_nms")
+           "dcfa_launch_count", "dcfa_run_ops", "dcfa_decode_box", "dcfa_nms_workspace_bytes", "dcfa_nms",
+           "dcfa_letterbox_workspace_bytes", "dcfa_letterbox_u8", "dcfa_pack_detections")
 
 
 class DcfaError(RuntimeError):
@@ -35,6 +36,12 @@ def _load():
                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.dcfa_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.dcfa_letterbox_workspace_bytes.restype = C.c_int64
+    lib.dcfa_letterbox_workspace_bytes.argtypes = [C.c_int] * 5
+    lib.dcfa_letterbox_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int64, C.c_void_p]
+    lib.dcfa_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p]
     if lib.dcfa_abi_version() != abi.ABI_VERSION:
         raise ImportError("dcfa_b200: ABI version %d != %d" % (lib.dcfa_abi_version(), abi.ABI_VERSION))
     if lib.dcfa_sizeof_view() != C.sizeof(abi.View) or lib.dcfa_sizeof_op() != C.sizeof(abi.Op):

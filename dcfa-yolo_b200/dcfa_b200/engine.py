@@ -121,3 +121,36 @@ def nms(pred, conf_thres, nms_thres, iou_mode=abi.IOU_TV_CPU, workspace=None):
                                      ws.det.data_ptr(), ws.idx.data_ptr(), ws.cnt.data_ptr(), ws.cand.data_ptr(),
                                      ws.ws.data_ptr(), ws.bytes, C.c_void_p(st)))
     return ws
+
+
+def letterbox_u8(src, dst, letterbox_image, workspace=None):
+    """resize_image (reference utils/utils.py:24-37) on the device: src uint8 CUDA [h,w,3] or [h,w] -> dst uint8 CUDA
+    [H,W,3] / [H,W] (typically one image slot of the batch tensor), bit-exact with PIL's BICUBIC + grey letterbox."""
+    if not (src.is_cuda and dst.is_cuda and src.dtype == torch.uint8 and dst.dtype == torch.uint8):
+        raise RuntimeError("dcfa_b200 has no CPU path: letterbox_u8 needs uint8 CUDA tensors")
+    c = 1 if src.dim() == 2 else int(src.shape[2])
+    if (dst.dim() == 2) != (src.dim() == 2) or (dst.dim() == 3 and dst.shape[2] != c) or not (src.is_contiguous() and dst.is_contiguous()):
+        raise ValueError("letterbox_u8: src %s / dst %s mismatch" % (tuple(src.shape), tuple(dst.shape)))
+    sh, sw, oh, ow = int(src.shape[0]), int(src.shape[1]), int(dst.shape[0]), int(dst.shape[1])
+    need = int(_lib.lib.dcfa_letterbox_workspace_bytes(sh, sw, c, oh, ow))
+    with torch.cuda.device(src.device):
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=src.device)
+        st = torch.cuda.current_stream(src.device).cuda_stream
+        _lib.check(_lib.lib.dcfa_letterbox_u8(src.data_ptr(), sh, sw, c, dst.data_ptr(), oh, ow, 1 if letterbox_image else 0,
+                                              workspace.data_ptr(), workspace.numel(), C.c_void_p(st)))
+    return workspace
+
+
+def pack_detections(ws, k, out, image_hw=None, input_shape=None, letterbox_image=True):
+    """(count, first k rows) per image of an NmsWorkspace into out [B, 1 + 6k] fp32 (device).  With image_hw (int32 CUDA
+    [B,2], original (h, w) per image) the rows are un-letterboxed on the device exactly as DecodeBox.yolo_correct_boxes
+    does on the host (reference utils/utils_bbox.py:60-85)."""
+    b, a = ws.b, ws.a
+    with torch.cuda.device(ws.det.device):
+        st = torch.cuda.current_stream(ws.det.device).cuda_stream
+        ih, iw = (int(input_shape[0]), int(input_shape[1])) if input_shape is not None else (0, 0)
+        _lib.check(_lib.lib.dcfa_pack_detections(ws.det.data_ptr(), ws.cnt.data_ptr(), b, a, int(k),
+                                                 image_hw.data_ptr() if image_hw is not None else None, ih, iw,
+                                                 1 if letterbox_image else 0, out.data_ptr(), C.c_void_p(st)))
+    return out

@@ -6,10 +6,12 @@ entry point the reference lacks:
     results = yolo.detect_images(list_of_rgb_pil_images, list_of_depth_pil_images)
     # results[i]: None or float32 (n_i, 6) rows (top, left, bottom, right, score, class) in ORIGINAL image pixels
 
-Per batch: PIL letterbox on the host (BICUBIC, as the reference), ONE upload of raw uint8 pixels (the stem kernel folds
-preprocess_input and the HWC->CHW transpose), forward + decode + NMS on the device, ONE download of the kept rows, and
-the un-letterbox with each image's own shape.  `model_path=None` keeps the constructor's random initialisation
-(tests, benchmarks).  Heat-map rendering and ONNX export are out of scope.
+Per batch: ONE upload of the images' own uint8 pixels (any sizes; a single-channel depth frame stays one plane), the
+reference's letterbox (PIL BICUBIC resize + grey padding, utils/utils.py:24-37) bit-exactly on the device, forward (the stem
+kernel folds preprocess_input, the HWC->CHW transpose and cvtColor's replication of the depth plane) + decode + NMS + the
+un-letterbox to each image's own pixel frame (utils/utils_bbox.py:60-85) on the device, ONE download of the kept rows.
+`device_letterbox=False` keeps the PIL letterbox on the host.  `model_path=None` keeps the constructor's random
+initialisation (tests, benchmarks).  Heat-map rendering and ONNX export are out of scope.
 """
 import colorsys
 import os
@@ -36,6 +38,7 @@ class YOLO(object):
         "nms_iou": 0.3,
         "letterbox_image": True,
         "cuda": True,
+        "device_letterbox": True,     # extension: resize_image on the GPU (bit-exact with PIL); False = PIL on the host
     }
 
     @classmethod
@@ -54,6 +57,7 @@ class YOLO(object):
             classes_path = os.path.join(_HERE, classes_path)      # the copy shipped next to this file
         self.class_names, self.num_classes = get_classes(classes_path)
         self.bbox_util = DecodeBox(self.num_classes, (self.input_shape[0], self.input_shape[1]))
+        self.bbox_util.iou_mode = 'cuda'   # the reference with cuda=True calls torchvision's CUDA nms kernel
         hsv = [(i / self.num_classes, 1.0, 1.0) for i in range(self.num_classes)]
         self.colors = [tuple(int(c * 255) for c in colorsys.hsv_to_rgb(*t)) for t in hsv]
         self._pinned = {}
@@ -74,16 +78,38 @@ class YOLO(object):
         self.net = self.net.eval().cuda()   # no nn.DataParallel: one process per GPU
 
     # ------------------------------------------------------------------------------------------ batched path
-    def _upload(self, images, tag):
-        """letterbox on the host into a reused pinned buffer, one async copy to the device"""
+    def _upload(self, images, tag, allow_plane=False):
+        """-> (uint8 CUDA [B,H,W,3] (or [B,H,W] for single-channel frames when allow_plane), original (h, w) shapes [B,2])."""
         b = len(images)
         h, w = int(self.input_shape[0]), int(self.input_shape[1])
-        key = (tag, b, h, w)
-        host = self._pinned.get(key)
-        if host is None:
-            host = self._pinned[key] = torch.empty(b, h, w, 3, dtype=torch.uint8).pin_memory()
-        _, shapes = letterbox_batch(images, (h, w), self.letterbox_image, out=host.numpy())
-        return host.cuda(non_blocking=True), shapes
+        if not self.device_letterbox:   # PIL letterbox on the host into a reused pinned buffer, one async copy
+            key = (tag, b, h, w)
+            host = self._pinned.get(key)
+            if host is None:
+                host = self._pinned[key] = torch.empty(b, h, w, 3, dtype=torch.uint8).pin_memory()
+            _, shapes = letterbox_batch(images, (h, w), self.letterbox_image, out=host.numpy())
+            return host.cuda(non_blocking=True), shapes
+        # the images' own pixels in ONE pinned staging buffer and one async copy, then resize_image on the device
+        from dcfa_b200.engine import letterbox_u8
+        arrs = [np.asarray(im) for im in images]
+        plane = allow_plane and all(a.ndim == 2 for a in arrs)
+        if not plane:
+            arrs = [a if (a.ndim == 3 and a.shape[2] == 3) else np.asarray(cvtColor(im)) for a, im in zip(arrs, images)]
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in arrs]
+        shapes = np.array([a.shape[:2] for a in arrs], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum([(a.size + 255) // 256 * 256 for a in arrs])])
+        host = self._pinned.get(tag)
+        if host is None or host.numel() < offs[-1]:
+            host = self._pinned[tag] = torch.empty(int(offs[-1] * 1.5) + 256, dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        for a, o in zip(arrs, offs):
+            hv[o:o + a.size] = a.reshape(-1)
+        dev = host[:int(offs[-1])].cuda(non_blocking=True)
+        out = torch.empty((b, h, w) if plane else (b, h, w, 3), dtype=torch.uint8, device=dev.device)
+        for i, (a, o) in enumerate(zip(arrs, offs)):
+            src = dev[int(o):int(o) + a.size].view(a.shape)
+            self._lb_ws = letterbox_u8(src, out[i], self.letterbox_image, getattr(self, '_lb_ws', None))
+        return out, shapes
 
     def detect_images(self, images_rgb, images_nir):
         """Lists of PIL images (same length, same size per pair) -> list of None | (n_i, 6) float32 rows
@@ -91,7 +117,7 @@ class YOLO(object):
         if len(images_rgb) != len(images_nir) or len(images_rgb) == 0:
             raise ValueError("detect_images needs two non-empty lists of the same length")
         rgb, shapes = self._upload(images_rgb, 'rgb')
-        nir, _ = self._upload(images_nir, 'nir')
+        nir, _ = self._upload(images_nir, 'nir', allow_plane=True)
         with torch.no_grad():
             outputs = self.bbox_util.decode_box(self.net(rgb, nir))
             return self.bbox_util.non_max_suppression(outputs, self.num_classes, self.input_shape, shapes,

@@ -22,6 +22,8 @@
  *   DCFA_OP_DFL         nets/yolo_mul.py:312-322,459-461  view/split + DFL softmax expectation
  *   dcfa_decode_box     utils/utils_bbox.py:30-40,49-58   dist2bbox(xywh) * strides, sigmoid, normalise
  *   dcfa_nms            utils/utils_bbox.py:87-168 + torchvision.ops.nms (un-vendored dependency)
+ *   dcfa_pack_detections  utils/utils_bbox.py:60-85,170-173  yolo_correct_boxes (un-letterbox) + result packing
+ *   dcfa_letterbox_u8   utils/utils.py:24-37  resize_image: PIL BICUBIC resize + grey letterbox (the caller-side pre-processing)
  *
  * Conventions
  *   - Plain pointers and sizes only; no torch types.  Every pointer is a DEVICE
@@ -221,6 +223,30 @@ int64_t dcfa_nms_workspace_bytes(int B, int A);
 int dcfa_nms(float* pred, int B, int A, int nc, float conf_thres, double nms_thres, int iou_mode,
              float* out_det, int32_t* out_idx, int32_t* out_cnt, int32_t* out_cand,
              void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * resize_image (utils/utils.py:24-37) on the device: Pillow's 8-bit `image.resize((nw, nh), Image.BICUBIC)` -- two separable
+ * fixed-point passes with an 8-bit intermediate, antialiased when shrinking -- pasted centred on a grey (128) canvas when
+ * `letterbox` is non-zero (nw = int(iw*s), nh = int(ih*s), s = min(W/iw, H/ih)), or stretched to the full canvas otherwise.
+ * Bit-exact against Pillow (an un-vendored dependency of the reference; pinned empirically, tests/test_letterbox_*.py).
+ *   src [src_h, src_w, channels] uint8 (channels = 3, or 1 for the depth plane before cvtColor replicates it);
+ *   dst [out_h, out_w, channels] uint8 (one image slot of the batch tensor the stem kernel reads);
+ *   workspace: dcfa_letterbox_workspace_bytes(...) bytes of device scratch (weight tables + the horizontal pass's output).
+ */
+int64_t dcfa_letterbox_workspace_bytes(int src_h, int src_w, int channels, int out_h, int out_w);
+int dcfa_letterbox_u8(const uint8_t* src, int src_h, int src_w, int channels, uint8_t* dst, int out_h, int out_w,
+                      int letterbox, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * The tail of DecodeBox.non_max_suppression (utils/utils_bbox.py:170-173 + yolo_correct_boxes :60-85) on the device, fused
+ * with the packing that precedes the single device->host copy of a batch:
+ *   det [B,A,6], cnt [B]: dcfa_nms outputs.  out [B, 1 + 6*K] fp32: per image (count, first K rows).
+ *   image_hw [B,2] int32 (device) = original (height, width) of every image: rows become (y1, x1, y2, x2, conf, cls) in
+ *   original-image pixels, in the reference's dtype flow (float64 intermediates, float32 `box_hw *= scale`), bit-exact
+ *   against the numpy code.  image_hw == NULL: rows are copied unchanged (x1, y1, x2, y2, conf, cls).
+ */
+int dcfa_pack_detections(const float* det, const int32_t* cnt, int B, int A, int K, const int32_t* image_hw, int in_h, int in_w,
+                         int letterbox, float* out, void* stream);
 
 #ifdef __cplusplus
 }

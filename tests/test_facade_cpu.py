@@ -55,7 +55,7 @@ def test_get_classes_and_defaults():
     import importlib.util
     here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dcfa-yolo_b200")
     names, n = get_classes(os.path.join(here, "model_data", "voc_classes.txt"))
-    assert n == 1 and names == ["cherry tomato bunch"]
+    assert n == 1 and names == ["cherry_tomato"]
     spec = importlib.util.spec_from_file_location("facade_yolo_mul", os.path.join(here, "yolo_mul.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

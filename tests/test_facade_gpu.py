@@ -61,7 +61,7 @@ def test_detect_images_batch_equals_single_and_manual(cuda, tmp_path):
     os.makedirs(tmp_path / "detection-results")
     yolo.get_map_txt("img0", rgb[0], nir[0], yolo.class_names, str(tmp_path))
     lines = open(tmp_path / "detection-results" / "img0.txt").read().strip().splitlines()
-    assert len(lines) == len(batch[0]) and lines[0].startswith("cherry tomato bunch ")
+    assert len(lines) == len(batch[0]) and lines[0].startswith("cherry_tomato ")
     assert yolo.get_FPS(rgb[0], nir[0], 3) > 0.0
     with pytest.raises(NotImplementedError):
         yolo.detect_heatmap(rgb[0], nir[0], "x.png")

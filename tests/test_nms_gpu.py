@@ -116,3 +116,36 @@ def test_nms_vs_torchvision_and_oracle(cuda, b, a, nc, kind, conf, thr, mode):
     for i in range(b):
         assert np.array_equal(idx[i, :cnt[i]], oidx[i, :cnt[i]])
         assert np.array_equal(det[i, :cnt[i]], odet[i, :cnt[i]])
+
+
+def test_pipelined_batches_on_one_decodebox_do_not_overwrite_each_other(cuda):
+    """INTEGRATION.md's pipeline on a single DecodeBox: nms_device + start_fetch of batch A, then of batch B (same shape),
+    and only then fetch_detections(A) -- A's rows must still be A's (the workspaces rotate through DecodeBox.ring)."""
+    from utils.utils_bbox import DecodeBox
+    dec = DecodeBox(2, (64, 64))
+    shape = np.array([64, 64])
+    preds = [make_pred(2, 600, 2, seed, "random") for seed in (1, 2, 3)]
+    want = [DecodeBox(2, (64, 64)).non_max_suppression(p.clone().to(cuda), 2, [64, 64], shape, True, 0.3, 0.45) for p in preds]
+    ws = []
+    for p in preds[:2]:
+        w = dec.nms_device(p.clone().to(cuda), 0.3, 0.45)
+        dec.start_fetch(w)
+        ws.append(w)
+    assert ws[0] is not ws[1]
+    got0 = dec.fetch_detections(ws[0], [64, 64], shape, True)
+    w2 = dec.nms_device(preds[2].clone().to(cuda), 0.3, 0.45)
+    dec.start_fetch(w2)
+    got1 = dec.fetch_detections(ws[1], [64, 64], shape, True)
+    got2 = dec.fetch_detections(w2, [64, 64], shape, True)
+    for got, ref in zip((got0, got1, got2), want):
+        for a, b in zip(got, ref):
+            assert (a is None) == (b is None)
+            if a is not None:
+                np.testing.assert_array_equal(a, b)
+    # more batches in flight than the ring holds is an error, not silent corruption
+    dec2 = DecodeBox(2, (64, 64))
+    dec2.ring = 2
+    for i in range(2):
+        dec2.start_fetch(dec2.nms_device(preds[i].clone().to(cuda), 0.3, 0.45))
+    with pytest.raises(RuntimeError, match="in flight"):
+        dec2.nms_device(preds[2].clone().to(cuda), 0.3, 0.45)
