@@ -722,21 +722,7 @@ int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& st
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set.mark();
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(a.n_img * CS));
-  cfg.blockDim = dim3(kFusedThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, cbam_fused_kernel, a);
+  cudaError_t le = launch_k(cbam_fused_kernel, dim3((unsigned)(a.n_img * CS)), dim3(kFusedThreads), smem, st, CS, true, a);
   if (le != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: launch (cluster %d, smem %zu): %s", CS, smem, cudaGetErrorString(le));
   count_launch();
   return 1;

@@ -4,8 +4,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
 #include <utility>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/dcfa_b200.h"
 
@@ -158,23 +160,66 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Kernel launch with the programmatic-dependent-launch attribute (see ptx::pdl_wait): EVERY kernel launched through
-// this helper executes griddepcontrol.wait before its first global access that depends on earlier work.
-// DCFA_PDL=0 in the environment falls back to plain stream-ordered launches (debugging).
+// ---------------------------------------------------------------------------------------------
+// kernel launches: immediate, or RECORDED into a plan (dcfa_plan_create) and replayed by dcfa_plan_run
+// ---------------------------------------------------------------------------------------------
+// One prepared launch: function, geometry, attributes and a private copy of every argument (tensor maps included), so
+// that replaying it costs one cudaLaunchKernelExC and nothing else -- no tensor-map encoding, no getenv, no attribute calls.
+struct LaunchRecord {
+  const void* func = nullptr;
+  dim3 grid, block;
+  size_t smem = 0;
+  int cluster = 0;      // cluster dimension x (0: no cluster attribute)
+  int pdl = 1;          // programmatic stream serialization allowed
+  int nargs = 0;
+  uint32_t off[8] = {};
+  alignas(64) unsigned char blob[1216];
+};
+struct Recorder {
+  LaunchRecord* recs;
+  int cap, n;
+  bool overflow;
+};
+Recorder*& recorder();   // thread-local; non-null while dcfa_plan_* prepares a dispatch unit (launches are recorded, not issued)
+cudaError_t launch_record(const LaunchRecord& r, cudaStream_t st);
 bool pdl_enabled();
+
+template <typename T>
+inline void pack_arg(LaunchRecord& r, uint32_t& pos, const T& v) {
+  pos = (pos + 63u) & ~63u;
+  static_assert(std::is_trivially_copyable<T>::value, "kernel arguments must be trivially copyable");
+  if (pos + sizeof(T) <= sizeof(r.blob) && r.nargs < 8) {
+    memcpy(r.blob + pos, &v, sizeof(T));
+    r.off[r.nargs++] = pos;
+  } else {
+    r.nargs = 99;   // flagged below
+  }
+  pos += (uint32_t)sizeof(T);
+}
+
+// EVERY kernel of the forward path is launched through this helper.  With pdl the kernel carries the programmatic-
+// dependent-launch attribute (see ptx::pdl_wait) and must execute griddepcontrol.wait before its first global access that
+// depends on earlier work; DCFA_PDL=0 in the environment falls back to plain stream-ordered launches (debugging).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, bool pdl,
+                            Args&&... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count mismatch");
+  LaunchRecord r;
+  r.func = reinterpret_cast<const void*>(kernel);
+  r.grid = grid; r.block = block; r.smem = smem; r.cluster = cluster; r.pdl = pdl ? 1 : 0;
+  uint32_t pos = 0;
+  (pack_arg<typename std::remove_cv<typename std::remove_reference<KArgs>::type>::type>(r, pos, args), ...);
+  if (r.nargs > 8) return cudaErrorInvalidValue;
+  if (Recorder* rec = recorder()) {
+    if (rec->n < rec->cap) rec->recs[rec->n++] = r;
+    else rec->overflow = true;
+    return cudaSuccess;
+  }
+  return launch_record(r, st);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  return launch_k(kernel, grid, block, smem, st, 0, true, std::forward<Args>(args)...);
 }
 
 // launchers implemented in the individual .cu files (host side; bufs already resolved by the caller)

@@ -424,7 +424,7 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     attr_set.mark();
   }
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
-  conv_gemm_kernel<<<grid, kThreads, smem, st>>>(a);
+  launch_k(conv_gemm_kernel, dim3(grid), dim3(kThreads), smem, st, 0, false, a);
   DCFA_CHECK_LAUNCH("conv_gemm_kernel");
   return DCFA_OK;
 }

@@ -477,7 +477,7 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   int64_t blocks = (a.total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  dwconv3x3_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  launch_k(dwconv3x3_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 0, false, a);
   DCFA_CHECK_LAUNCH("dwconv3x3_kernel");
   return DCFA_OK;
 }

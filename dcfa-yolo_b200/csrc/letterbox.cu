@@ -169,9 +169,15 @@ __global__ void pack_detections_kernel(const float* __restrict__ det, const int3
   }
   float box[4];
   for (int k = 0; k < 2; ++k) {
-    const double half = __ddiv_rn((double)hw[k], 2.0);
-    box[k] = (float)__dmul_rn(__dadd_rn(yx[k], -half), img[k]);
-    box[2 + k] = (float)__dmul_rn(__dadd_rn(yx[k], half), img[k]);
+    if (letterbox) {   // box_yx is float64 here: mins / maxes are float64
+      const double half = __ddiv_rn((double)hw[k], 2.0);
+      box[k] = (float)__dmul_rn(__dadd_rn(yx[k], -half), img[k]);
+      box[2 + k] = (float)__dmul_rn(__dadd_rn(yx[k], half), img[k]);
+    } else {           // everything stayed float32 up to the final `boxes *= image_shape` (computed in float64, stored as float32)
+      const float half = __fdiv_rn(hw[k], 2.0f);
+      box[k] = (float)__dmul_rn((double)__fsub_rn(cxy[k], half), img[k]);
+      box[2 + k] = (float)__dmul_rn((double)__fadd_rn(cxy[k], half), img[k]);
+    }
   }
   r[0] = box[0]; r[1] = box[1]; r[2] = box[2]; r[3] = box[3]; r[4] = d[4]; r[5] = d[5];
 }

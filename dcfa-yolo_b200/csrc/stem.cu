@@ -61,17 +61,33 @@ constexpr int CVT_SLOT = 2560;                // bf16 [11][28][4] = 2464 + the r
 constexpr int NCVT = 4;                       // converted-patch ring depth = converter warps
 constexpr int A_TILE_BYTES = 128 * 16 * 2;    // one (kernel row, parity) weight tile
 constexpr int A_GROUP_BYTES = 6 * A_TILE_BYTES;
-constexpr int HW = TPW / 2;                    // pooled pixels per epilogue warp (half a tile row)
-constexpr int OUT_SLAB = HW * 32 * 2;         // 384: half a pooled row of one warp, [6 pixels][32 channels] bf16
-constexpr int kEpiWarps = 16, kCvtWarps = 4;
+constexpr int OUT_SLAB = TPW * 32 * 2;        // 768: one pooled row of a warp, [12 pixels][32 channels] bf16
+constexpr int kEpiWarps = 8, kCvtWarps = 4;
 constexpr int kCvtWarp0 = kEpiWarps, kTmaWarp = kEpiWarps + kCvtWarps, kMmaWarp = kTmaWarp + 1;
-constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
+constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 448
 constexpr uint32_t kTmemCols = 512;
 static_assert(NRAW == kCvtWarps && NCVT == kCvtWarps, "converter warp w owns raw slot w and converted slot w");
 static_assert(2 * PP * 8 + (NCOL - 1) * 16 + 32 <= CVT_SLOT, "MMA over-read must stay inside the slot");
 static_assert((CH - 1) * HP + TPW + 1 <= NCOL, "tile does not fit the accumulator");
 
 enum { MODE_F32 = 0, MODE_U8 = 1, MODE_U8_C1 = 2 };   // MODE_U8_C1: group 0 uint8 NHWC, group 1 a single uint8 plane
+
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shr) : n; }
+};
+
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    const uint32_t p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
 
 struct StemArgs {
   const void* x[2];        // fp32 NCHW / uint8 NHWC / (group 1, MODE_U8_C1) uint8 [N,H,W]
@@ -80,11 +96,11 @@ struct StemArgs {
   const float* bias;       // [G][C0pad]
   View<__nv_bfloat16> y;
   int n_img, group_imgs, groups, Hi, Wi, Ho, Wo, C0, C0pad;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, total_tiles;
+  FastDiv div_img, div_row; // tiles per image / per tile row
   int use_tma;             // inputs through TMA boxes (else: plain loads with explicit zero padding)
-  int tma_out;             // output through per-warp slabs + TMA stores (else: direct 2-byte stores)
   int box_c;               // channels per output slab row (min(32, C0) rounded to 8)
-  int dbg;                 // experiments only (DCFA_STEM_DBG): 1 no stores, 2 no input loads, 4 no MMAs, 8 direct stores
+  int dbg;                 // experiments only (DCFA_STEM_DBG): 1 no stores, 2 no input loads, 4 no MMAs
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
@@ -140,33 +156,39 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint3
 // px0's first conv input column + 2; the patch starts L - 2 pixels into the box.
 __device__ __forceinline__ int u8_left(int tx) { return (tx & 1) ? 8 : 16; }
 
-// Tile coordinates advanced incrementally (tile index += step): the per-tile path has no divisions.
-// Tiles are ordered (image over both groups, tile row, tile column).
-struct TileIter {
-  int tx, ty, n;       // tile column, tile row, image index over both groups
-  int sx, sy, sn;      // mixed-radix digits of the step
-  __device__ __forceinline__ void init(int tile, int step, int tiles_x, int tiles_y) {
-    const int per_img = tiles_x * tiles_y;
-    n = tile / per_img;
-    int r = tile - n * per_img;
-    ty = r / tiles_x;
-    tx = r - ty * tiles_x;
-    sn = step / per_img;
-    r = step - sn * per_img;
-    sy = r / tiles_x;
-    sx = r - sy * tiles_x;
-  }
-  __device__ __forceinline__ void advance(int tiles_x, int tiles_y) {
-    tx += sx;
-    if (tx >= tiles_x) { tx -= tiles_x; ty += 1; }
-    ty += sy;
-    if (ty >= tiles_y) { ty -= tiles_y; n += 1; }
-    n += sn;
-  }
+// Every CTA owns a CONTIGUOUS range of tiles (ordered image, tile row, tile column): consecutive tiles share their halo
+// columns/rows through L2, and a tile's coordinates are two multiply-high divisions of the linear index.
+struct Tile {
+  int n, ty, tx;
 };
+__device__ __forceinline__ Tile tile_of(uint32_t t, const FastDiv& per_img, const FastDiv& per_row) {
+  Tile r;
+  r.n = (int)per_img.div(t);
+  const uint32_t rem = t - (uint32_t)r.n * per_img.d;
+  r.ty = (int)per_row.div(rem);
+  r.tx = (int)(rem - (uint32_t)r.ty * per_row.d);
+  return r;
+}
 
 __device__ __forceinline__ uint32_t u8x2_bf16(uint32_t lo, uint32_t hi) {   // two integers 0..255 -> packed bf16 (exact)
   return pack_bf16x2((float)lo, (float)hi);
+}
+// relu(lo), relu(hi) -> packed bf16 (one instruction)
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// lean spin on an mbarrier phase (suspend-time hint: the hardware parks the warp between polls); a pipeline bug traps
+// after ~2^24 polls instead of hanging the GPU
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait_hint(bar, parity, 100000u)) {
+    if (++spins > (1u << 24)) {
+      printf("dcfa: stem mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
 }
 
 template <int MODE>
@@ -196,7 +218,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     if (lane == 0) {
       for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(bar_raw_full + 8u * i, 1); ptx::mbar_init(bar_raw_empty + 8u * i, 1); }
       for (int i = 0; i < NCVT; ++i) { ptx::mbar_init(bar_cvt_full + 8u * i, 1); ptx::mbar_init(bar_cvt_empty + 8u * i, 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 8); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 4); }
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
       if (p.groups > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
     }
-    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_y)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_y)) : "memory");
   }
   {  // weight tiles of every group (constant parameters: no dependency on the previous kernel) and zeroed patch slots
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
@@ -226,55 +248,62 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot_ptr;
   ptx::pdl_wait();
 
+  // this CTA's tiles: [t_begin, t_end), a balanced contiguous split of the launch
+  const uint32_t t_begin = (uint32_t)(((uint64_t)p.total_tiles * blockIdx.x) / gridDim.x);
+  const uint32_t t_end = (uint32_t)(((uint64_t)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t n_tiles = t_end - t_begin;
+
   if (warp == kTmaWarp) {
-    // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0 && p.use_tma && !(p.dbg & 2)) {
-      TileIter cur;
-      cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-      uint32_t s = 0, ph = 0;
-      for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y)) {
+    // ------------------------------------------------------------------ TMA producer (whole warp runs the loop, one lane issues)
+    if (p.use_tma && !(p.dbg & 2)) {
+      const bool leader = ptx::elect_one();
+      for (uint32_t i = 0; i < n_tiles; ++i) {
+        const uint32_t s = i & (NRAW - 1), ph = (i / NRAW) & 1u;
+        const Tile t = tile_of(t_begin + i, p.div_img, p.div_row);
         const uint32_t full = bar_raw_full + 8u * s, dst = s_raw + s * (uint32_t)RAW_SLOT;
-        ptx::mbar_wait_parked(bar_raw_empty + 8u * s, ph ^ 1u);
-        const int g = cur.n >= p.group_imgs ? 1 : 0;
-        const int nl = cur.n - g * p.group_imgs;
-        const int y = 2 * cur.ty * TPH - 2;
+        wait_bar(bar_raw_empty + 8u * s, ph ^ 1u);
+        const int g = t.n >= p.group_imgs ? 1 : 0;
+        const int nl = t.n - g * p.group_imgs;
+        const int y = 2 * t.ty * TPH - 2;
         // (no pointer select between the two maps: that would copy a __grid_constant__ parameter to local memory)
-        if (MODE == MODE_F32) {
-          const int x = 2 * cur.tx * TPW - 2 - XOFF;
-          ptx::mbar_arrive_expect_tx(full, RAW_F32_BYTES);
-          if (g == 0) tma_load_4d(dst, &map0, x, y, 0, nl, full);
-          else tma_load_4d(dst, &map1, x, y, 0, nl, full);
-        } else if (MODE == MODE_U8 || g == 0) {
-          const int xb = 3 * (2 * cur.tx * TPW - u8_left(cur.tx));
-          ptx::mbar_arrive_expect_tx(full, RAW_U8_BYTES);
-          if (g == 0) tma_load_3d(dst, &map0, xb, y, nl, full);
-          else tma_load_3d(dst, &map1, xb, y, nl, full);
-        } else {
-          const int xb = 2 * cur.tx * TPW - u8_left(cur.tx);
-          ptx::mbar_arrive_expect_tx(full, RAW_C1_BYTES);
-          tma_load_3d(dst, &map1, xb, y, nl, full);
+        if (leader) {
+          if (MODE == MODE_F32) {
+            const int x = 2 * t.tx * TPW - 2 - XOFF;
+            ptx::mbar_arrive_expect_tx(full, RAW_F32_BYTES);
+            if (g == 0) tma_load_4d(dst, &map0, x, y, 0, nl, full);
+            else tma_load_4d(dst, &map1, x, y, 0, nl, full);
+          } else if (MODE == MODE_U8 || g == 0) {
+            const int xb = 3 * (2 * t.tx * TPW - u8_left(t.tx));
+            ptx::mbar_arrive_expect_tx(full, RAW_U8_BYTES);
+            if (g == 0) tma_load_3d(dst, &map0, xb, y, nl, full);
+            else tma_load_3d(dst, &map1, xb, y, nl, full);
+          } else {
+            const int xb = 2 * t.tx * TPW - u8_left(t.tx);
+            ptx::mbar_arrive_expect_tx(full, RAW_C1_BYTES);
+            tma_load_3d(dst, &map1, xb, y, nl, full);
+          }
         }
-        if (++s == NRAW) { s = 0; ph ^= 1u; }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      TileIter cur;
-      cur.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-      const uint32_t idesc = ptx::make_idesc_bf16_f32(128, NCOL);
-      // descriptors: only the 14-bit start-address field changes
-      const uint64_t bd_hi = desc_nosw(0u, 16u, 128u);    // operand rows: row n = 16 bf16 at pixel 2n (linear): LBO 16, SBO 128
-      const uint64_t ad_hi = desc_nosw(0u, 128u, 256u);   // canonical weight tiles
-      uint32_t cs = 0, cph = 0, it = 0;
-      for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), ++it) {
-        const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
-        const int g = cur.n >= p.group_imgs ? 1 : 0;
-        ptx::mbar_wait(bar_tm_empty + 8u * ab, aph ^ 1u);
-        ptx::mbar_wait(bar_cvt_full + 8u * cs, cph);
-        ptx::tc_fence_after();
-        const uint32_t b0 = ((s_cvt + cs * (uint32_t)CVT_SLOT) & 0x3FFFFu) >> 4;
-        const uint32_t a0 = ((s_a + (uint32_t)g * A_GROUP_BYTES) & 0x3FFFFu) >> 4;
+    // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop, one lane issues)
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(128, NCOL);
+    // descriptors: only the 14-bit start-address field changes
+    const uint64_t bd_hi = desc_nosw(0u, 16u, 128u);    // operand rows: row n = 16 bf16 at pixel 2n (linear): LBO 16, SBO 128
+    const uint64_t ad_hi = desc_nosw(0u, 128u, 256u);   // canonical weight tiles
+    const uint32_t a_lo0 = (s_a & 0x3FFFFu) >> 4, b_lo0 = (s_cvt & 0x3FFFFu) >> 4;
+    const uint32_t t_group1 = (uint32_t)p.group_imgs * p.div_img.d;   // first tile of the second modality
+    for (uint32_t i = 0; i < n_tiles; ++i) {
+      const uint32_t ab = i & 1u, aph = (i >> 1) & 1u, cs = i & (NCVT - 1), cph = (i / NCVT) & 1u;
+      const uint32_t g = (t_begin + i) >= t_group1 ? 1u : 0u;
+      wait_bar(bar_tm_empty + 8u * ab, aph ^ 1u);
+      wait_bar(bar_cvt_full + 8u * cs, cph);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint32_t b0 = b_lo0 + cs * (uint32_t)(CVT_SLOT / 16);
+        const uint32_t a0 = a_lo0 + g * (uint32_t)(A_GROUP_BYTES / 16);
         const uint32_t d0 = tmem_base + ab * 256u;
         if (!(p.dbg & 4)) {
 #pragma unroll
@@ -288,15 +317,13 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
         }
         ptx::umma_commit(bar_cvt_empty + 8u * cs);   // the converted patch may be overwritten
         ptx::umma_commit(bar_tm_full + 8u * ab);     // both accumulators of this tile are complete
-        if (++cs == NCVT) { cs = 0; cph ^= 1u; }
       }
+      __syncwarp();
     }
   } else if (warp >= kCvtWarp0) {
     // ------------------------------------------------------------------ converters: raw patch -> bf16 [y][x][4]
-    // Converter warp w owns the tiles blockIdx.x + (4 i + w) * gridDim.x, raw slot w and converted slot w.
+    // Converter warp w owns this CTA's tiles w, w + 4, ..., raw slot w and converted slot w.
     const int cw = warp - kCvtWarp0;
-    TileIter cur;
-    cur.init(blockIdx.x + cw * gridDim.x, kCvtWarps * gridDim.x, p.tiles_x, p.tiles_y);
     const bool tma_in = p.use_tma && !(p.dbg & 2);
     const uint8_t* raw = raw_ptr + cw * RAW_SLOT;
     uint8_t* cvt = cvt_ptr + cw * CVT_SLOT;
@@ -314,97 +341,106 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
       qq[k] = item - rr[k] * per;
     }
     uint32_t ph = 0;
-    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), ph ^= 1u) {
-      const int g = cur.n >= p.group_imgs ? 1 : 0;
-      const int nl = cur.n - g * p.group_imgs;
-      ptx::mbar_wait_parked(b_cvt_empty, ph ^ 1u);
-      if (tma_in) ptx::mbar_wait_parked(b_raw_full, ph);
-      const int iy0 = 2 * cur.ty * TPH - 2, ix0 = 2 * cur.tx * TPW - 2;   // image coordinates of patch pixel (0, 0)
-      if (MODE == MODE_F32) {
+    for (uint32_t i = (uint32_t)cw; i < n_tiles; i += kCvtWarps, ph ^= 1u) {
+      wait_bar(b_cvt_empty, ph ^ 1u);
+      if (tma_in) wait_bar(b_raw_full, ph);
+      if (MODE == MODE_F32 && p.use_tma) {
         // three 64-bit loads (one per channel plane) and one 128-bit store per item; all loads of the lane's items are
         // issued before the first convert (independent chains)
         float2 c[NI_F][3];
 #pragma unroll
         for (int k = 0; k < NI_F; ++k) {
-          if (lane + 32 * k < PH * HP) {
-            const int r = rr[k], q = qq[k];
-            if (p.use_tma) {
-              const float* src = reinterpret_cast<const float*>(raw) + r * PWB + XOFF + 2 * q;
-              c[k][0] = *reinterpret_cast<const float2*>(src);
-              c[k][1] = *reinterpret_cast<const float2*>(src + PH * PWB);
-              c[k][2] = *reinterpret_cast<const float2*>(src + 2 * PH * PWB);
-            } else {   // image rows are not 16-byte multiples: plain loads with explicit zero padding
-              const float* img = reinterpret_cast<const float*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
-              const int iy = iy0 + r, ix = ix0 + 2 * q;
-              const bool yok = iy >= 0 && iy < p.Hi, a = yok && ix >= 0 && ix < p.Wi, b = yok && ix + 1 >= 0 && ix + 1 < p.Wi;
-              const int64_t o = (int64_t)iy * p.Wi + ix, pl = (int64_t)p.Hi * p.Wi;
-              c[k][0] = make_float2(a ? __ldg(img + o) : 0.f, b ? __ldg(img + o + 1) : 0.f);
-              c[k][1] = make_float2(a ? __ldg(img + pl + o) : 0.f, b ? __ldg(img + pl + o + 1) : 0.f);
-              c[k][2] = make_float2(a ? __ldg(img + 2 * pl + o) : 0.f, b ? __ldg(img + 2 * pl + o + 1) : 0.f);
-            }
+          if (k < NI_F - 1 || lane + 32 * k < PH * HP) {
+            const float* src = reinterpret_cast<const float*>(raw) + rr[k] * PWB + XOFF + 2 * qq[k];
+            c[k][0] = *reinterpret_cast<const float2*>(src);
+            c[k][1] = *reinterpret_cast<const float2*>(src + PH * PWB);
+            c[k][2] = *reinterpret_cast<const float2*>(src + 2 * PH * PWB);
           }
         }
 #pragma unroll
         for (int k = 0; k < NI_F; ++k) {
-          if (lane + 32 * k < PH * HP) {
+          if (k < NI_F - 1 || lane + 32 * k < PH * HP) {
             const uint4 o4 = make_uint4(pack_bf16x2(c[k][0].x, c[k][1].x), pack_bf16x2(c[k][2].x, 0.f),
                                         pack_bf16x2(c[k][0].y, c[k][1].y), pack_bf16x2(c[k][2].y, 0.f));
             *reinterpret_cast<uint4*>(cvt + (rr[k] * PP + 2 * qq[k]) * 8) = o4;
           }
         }
-      } else if (MODE == MODE_U8 || g == 0) {
-        // 12 bytes -> 32 bytes per item.  0..255 are exact bf16 integers; preprocess_input's 1/255 (utils/utils.py:76-79)
-        // is folded into the BN scale.
-        const int left = 3 * (u8_left(cur.tx) - 2);
-#pragma unroll
-        for (int k = 0; k < NI_U; ++k) {
-          if (lane + 32 * k < PH * (PP / 4)) {
-            const int r = rr[k], q = qq[k];
-            uint32_t b[12];
-            if (p.use_tma) {
-              const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAWB + left + 12 * q);
-#pragma unroll
-              for (int j = 0; j < 6; ++j) { const uint32_t h = src[j]; b[2 * j] = h & 0xffu; b[2 * j + 1] = h >> 8; }
-            } else {
-              const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * p.Hi * p.Wi * 3;
-              const int iy = iy0 + r;
-#pragma unroll
-              for (int j = 0; j < 12; ++j) {
-                const int ix = ix0 + 4 * q + j / 3;
-                b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + ((int64_t)iy * p.Wi + ix) * 3 + j % 3) : 0u;
-              }
-            }
-            uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
-            dst[0] = make_uint4(u8x2_bf16(b[0], b[1]), u8x2_bf16(b[2], 0u), u8x2_bf16(b[3], b[4]), u8x2_bf16(b[5], 0u));
-            dst[1] = make_uint4(u8x2_bf16(b[6], b[7]), u8x2_bf16(b[8], 0u), u8x2_bf16(b[9], b[10]), u8x2_bf16(b[11], 0u));
-          }
-        }
       } else {
-        // single uint8 plane (the depth image before cvtColor replicates it, utils/utils.py:14-19): 4 bytes -> 32 bytes,
-        // each value written to the three channel slots -- identical to uploading the replicated image
-        const int left = u8_left(cur.tx) - 2;
+        const Tile t = tile_of(t_begin + i, p.div_img, p.div_row);
+        const int g = t.n >= p.group_imgs ? 1 : 0;
+        const int nl = t.n - g * p.group_imgs;
+        const int iy0 = 2 * t.ty * TPH - 2, ix0 = 2 * t.tx * TPW - 2;   // image coordinates of patch pixel (0, 0)
+        if (MODE == MODE_F32) {
+          // image rows are not 16-byte multiples: plain loads with explicit zero padding
+          const float* img = reinterpret_cast<const float*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * 3 * p.Hi * p.Wi;
+          const int64_t pl = (int64_t)p.Hi * p.Wi;
 #pragma unroll
-        for (int k = 0; k < NI_U; ++k) {
-          if (lane + 32 * k < PH * (PP / 4)) {
-            const int r = rr[k], q = qq[k];
-            uint32_t b[4];
-            if (p.use_tma) {
-              const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAW1B + left + 4 * q);
-              const uint32_t h0 = src[0], h1 = src[1];
-              b[0] = h0 & 0xffu; b[1] = h0 >> 8; b[2] = h1 & 0xffu; b[3] = h1 >> 8;
-            } else {
-              const uint8_t* img = reinterpret_cast<const uint8_t*>(p.x[1]) + (int64_t)nl * p.Hi * p.Wi;
-              const int iy = iy0 + r;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int ix = ix0 + 4 * q + j;
-                b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + (int64_t)iy * p.Wi + ix) : 0u;
-              }
+          for (int k = 0; k < NI_F; ++k) {
+            if (lane + 32 * k < PH * HP) {
+              const int iy = iy0 + rr[k], ix = ix0 + 2 * qq[k];
+              const bool yok = iy >= 0 && iy < p.Hi, a = yok && ix >= 0 && ix < p.Wi, b = yok && ix + 1 >= 0 && ix + 1 < p.Wi;
+              const int64_t o = (int64_t)iy * p.Wi + ix;
+              const float2 c0 = make_float2(a ? __ldg(img + o) : 0.f, b ? __ldg(img + o + 1) : 0.f);
+              const float2 c1 = make_float2(a ? __ldg(img + pl + o) : 0.f, b ? __ldg(img + pl + o + 1) : 0.f);
+              const float2 c2 = make_float2(a ? __ldg(img + 2 * pl + o) : 0.f, b ? __ldg(img + 2 * pl + o + 1) : 0.f);
+              const uint4 o4 = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f));
+              *reinterpret_cast<uint4*>(cvt + (rr[k] * PP + 2 * qq[k]) * 8) = o4;
             }
-            uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
-            const uint32_t p0 = u8x2_bf16(b[0], b[0]), p1 = u8x2_bf16(b[1], b[1]), p2 = u8x2_bf16(b[2], b[2]), p3 = u8x2_bf16(b[3], b[3]);
-            dst[0] = make_uint4(p0, p0 & 0xffffu, p1, p1 & 0xffffu);
-            dst[1] = make_uint4(p2, p2 & 0xffffu, p3, p3 & 0xffffu);
+          }
+        } else if (MODE == MODE_U8 || g == 0) {
+          // 12 bytes -> 32 bytes per item.  0..255 are exact bf16 integers; preprocess_input's 1/255 (utils/utils.py:76-79)
+          // is folded into the BN scale.
+          const int left = 3 * (u8_left(t.tx) - 2);
+#pragma unroll
+          for (int k = 0; k < NI_U; ++k) {
+            if (lane + 32 * k < PH * (PP / 4)) {
+              const int r = rr[k], q = qq[k];
+              uint32_t b[12];
+              if (p.use_tma) {
+                const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAWB + left + 12 * q);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { const uint32_t h = src[j]; b[2 * j] = h & 0xffu; b[2 * j + 1] = h >> 8; }
+              } else {
+                const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? p.x[0] : p.x[1]) + (int64_t)nl * p.Hi * p.Wi * 3;
+                const int iy = iy0 + r;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                  const int ix = ix0 + 4 * q + j / 3;
+                  b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + ((int64_t)iy * p.Wi + ix) * 3 + j % 3) : 0u;
+                }
+              }
+              uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
+              dst[0] = make_uint4(u8x2_bf16(b[0], b[1]), u8x2_bf16(b[2], 0u), u8x2_bf16(b[3], b[4]), u8x2_bf16(b[5], 0u));
+              dst[1] = make_uint4(u8x2_bf16(b[6], b[7]), u8x2_bf16(b[8], 0u), u8x2_bf16(b[9], b[10]), u8x2_bf16(b[11], 0u));
+            }
+          }
+        } else {
+          // single uint8 plane (the depth image before cvtColor replicates it, utils/utils.py:14-19): 4 bytes -> 32 bytes,
+          // each value written to the three channel slots -- identical to uploading the replicated image
+          const int left = u8_left(t.tx) - 2;
+#pragma unroll
+          for (int k = 0; k < NI_U; ++k) {
+            if (lane + 32 * k < PH * (PP / 4)) {
+              const int r = rr[k], q = qq[k];
+              uint32_t b[4];
+              if (p.use_tma) {
+                const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + r * RAW1B + left + 4 * q);
+                const uint32_t h0 = src[0], h1 = src[1];
+                b[0] = h0 & 0xffu; b[1] = h0 >> 8; b[2] = h1 & 0xffu; b[3] = h1 >> 8;
+              } else {
+                const uint8_t* img = reinterpret_cast<const uint8_t*>(p.x[1]) + (int64_t)nl * p.Hi * p.Wi;
+                const int iy = iy0 + r;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int ix = ix0 + 4 * q + j;
+                  b[j] = (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? (uint32_t)__ldg(img + (int64_t)iy * p.Wi + ix) : 0u;
+                }
+              }
+              uint4* dst = reinterpret_cast<uint4*>(cvt + (r * PP + 4 * q) * 8);
+              const uint32_t p0 = u8x2_bf16(b[0], b[0]), p1 = u8x2_bf16(b[1], b[1]), p2 = u8x2_bf16(b[2], b[2]), p3 = u8x2_bf16(b[3], b[3]);
+              dst[0] = make_uint4(p0, p0 & 0xffffu, p1, p1 & 0xffffu);
+              dst[1] = make_uint4(p2, p2 & 0xffffu, p3, p3 & 0xffffu);
+            }
           }
         }
       }
@@ -417,7 +453,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue: group = tile parity, warp & 3 = TMEM lane quarter
-    const int q4 = warp & 3, grp = (warp >> 2) & 1, half = warp >> 3;
+    const int q4 = warp & 3, grp = warp >> 2;
     const int mrow = q4 * 32 + lane;              // accumulator row (TMEM lane)
     const int ch = mrow & (p.C0pad - 1);          // C0pad is 32, 64 or 128
     const int rep = mrow / p.C0pad;               // replica: handles the pooled rows rep, rep + nrep, ...
@@ -425,90 +461,95 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     const int chan0 = ch - lane;                  // first channel of this warp (multiple of 32)
     const bool ch_valid = ch < p.C0;
     const bool warp_valid = chan0 < p.C0;
+    const bool leader = ptx::elect_one();
     float sc[2], bi[2];
     sc[0] = __ldg(p.scale + ch); bi[0] = __ldg(p.bias + ch);
     sc[1] = p.groups > 1 ? __ldg(p.scale + p.C0pad + ch) : sc[0];
     bi[1] = p.groups > 1 ? __ldg(p.bias + p.C0pad + ch) : bi[0];
     const uint32_t slab0 = s_out + (uint32_t)(warp * 2 * OUT_SLAB);
-    uint8_t* slab_ptr0 = out_ptr + warp * 2 * OUT_SLAB;
-    const int pitch = p.box_c * 2;                // slab row pitch in bytes (channels of one pixel)
-    const bool tma_out = p.tma_out && !(p.dbg & 8);
-    uint32_t slab_sel = 0;
-    TileIter cur;                                 // this group's tiles: blockIdx.x + (2 i + grp) * gridDim.x
-    cur.init(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, p.tiles_x, p.tiles_y);
-    uint32_t aph = 0;
-    for (; cur.n < p.n_img; cur.advance(p.tiles_x, p.tiles_y), aph ^= 1u) {
-      const int g = cur.n >= p.group_imgs ? 1 : 0;
+    uint8_t* slab_ptr0 = out_ptr + warp * 2 * OUT_SLAB + lane * 2;
+    const bool dense32 = p.box_c == 32;           // slab row pitch 64 bytes: compile-time store offsets
+    const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)grp * 256u;
+    const uint32_t b_full = bar_tm_full + 8u * grp, b_empty = bar_tm_empty + 8u * grp;
+    uint32_t slab_sel = 0, aph = 0;
+    for (uint32_t i = (uint32_t)grp; i < n_tiles; i += 2, aph ^= 1u) {
+      const Tile t = tile_of(t_begin + i, p.div_img, p.div_row);
+      const int g = t.n >= p.group_imgs ? 1 : 0;
       const float s = g ? sc[1] : sc[0], b = g ? bi[1] : bi[0];
-      const int py0 = cur.ty * TPH, px0 = cur.tx * TPW + HW * half;
-      const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // image coordinates of this warp's first conv pixel
-      const bool border = cy0 < 0 || cx0 < 0 || cy0 + CH > p.Hi || cx0 + 2 * HW + 1 > p.Wi;
-      ptx::mbar_wait_parked(bar_tm_full + 8u * grp, aph);
+      const int py0 = t.ty * TPH, px0 = t.tx * TPW;
+      const bool border = t.ty == 0 || t.tx == 0 || 2 * py0 - 1 + CH > p.Hi || 2 * px0 - 1 + CW > p.Wi;
+      wait_bar(b_full, aph);
       ptx::tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)grp * 256u + (uint32_t)(HW * half);
       for (int r = rep; r < TPH; r += nrep) {
-        // pooled row r, pooled columns 6*half .. 6*half+5 = conv rows 2r..2r+2 x conv columns 12*half .. 12*half+12: per conv
-        // row 7 even columns (accumulator 0, TMEM columns 14*(2r+j) + 6*half + 0..6) and 6 odd ones (accumulator 1)
-        uint32_t E[3][8], O[3][8];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          tmem_ld_x8(t0 + (uint32_t)(HP * (2 * r + j)), E[j]);
-          tmem_ld_x8(t0 + (uint32_t)(NCOL + HP * (2 * r + j)), O[j]);
-        }
+        // pooled row r = conv rows 2r..2r+2 = TMEM columns 28r .. 28r+41 of the even accumulator (conv columns 0,2,..,24
+        // in the first 13 of every 14) and of the odd accumulator (conv columns 1,3,..,23 in the first 12 of every 14)
+        uint32_t E[3 * HP], O[3 * HP];
+        const uint32_t te = t0 + (uint32_t)(2 * HP * r), to = te + (uint32_t)NCOL;
+        tmem_ld_x32(te, E); tmem_ld_x8(te + 32u, E + 32); tmem_ld_x2(te + 40u, E + 40);
+        tmem_ld_x32(to, O); tmem_ld_x8(to + 32u, O + 32);
+        O[40] = O[41] = 0u;
         ptx::tmem_ld_wait();
         if (r + nrep >= TPH) {   // last row of this thread: the accumulators may be overwritten by the next tile
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_tm_empty + 8u * grp);
+          if (leader) ptx::mbar_arrive(b_empty);
         }
         if (border) {   // exclude out-of-image conv positions from the max (reference: -inf pool padding)
+          const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // image coordinates of conv pixel (0, 0) of the tile
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const bool yok = cy0 + 2 * r + j >= 0 && cy0 + 2 * r + j < p.Hi;
 #pragma unroll
-            for (int i = 0; i < HW + 1; ++i)
-              if (!(yok && cx0 + 2 * i >= 0 && cx0 + 2 * i < p.Wi)) E[j][i] = 0xff800000u;
+            for (int k = 0; k < TPW + 1; ++k)
+              if (!(yok && cx0 + 2 * k >= 0 && cx0 + 2 * k < p.Wi)) E[j * HP + k] = 0xff800000u;
 #pragma unroll
-            for (int i = 0; i < HW; ++i)
-              if (!(yok && cx0 + 2 * i + 1 < p.Wi)) O[j][i] = 0xff800000u;
+            for (int k = 0; k < TPW; ++k)
+              if (!(yok && cx0 + 2 * k + 1 < p.Wi)) O[j * HP + k] = 0xff800000u;
           }
         }
         // vertical 3-max per conv column, then horizontal 3-max at stride 2
-        float ve[HW + 1], vo[HW];
+        float ve[TPW + 1], vo[TPW];
 #pragma unroll
-        for (int i = 0; i < HW + 1; ++i) ve[i] = max3(__uint_as_float(E[0][i]), __uint_as_float(E[1][i]), __uint_as_float(E[2][i]));
+        for (int k = 0; k < TPW + 1; ++k)
+          ve[k] = max3(__uint_as_float(E[k]), __uint_as_float(E[HP + k]), __uint_as_float(E[2 * HP + k]));
 #pragma unroll
-        for (int i = 0; i < HW; ++i) vo[i] = max3(__uint_as_float(O[0][i]), __uint_as_float(O[1][i]), __uint_as_float(O[2][i]));
-        float o[HW];
+        for (int k = 0; k < TPW; ++k)
+          vo[k] = max3(__uint_as_float(O[k]), __uint_as_float(O[HP + k]), __uint_as_float(O[2 * HP + k]));
+        float o[TPW];
 #pragma unroll
-        for (int pc = 0; pc < HW; ++pc) o[pc] = fmaxf(fmaf(max3(ve[pc], vo[pc], ve[pc + 1]), s, b), 0.0f);
+        for (int pc = 0; pc < TPW; ++pc) o[pc] = fmaf(max3(ve[pc], vo[pc], ve[pc + 1]), s, b);   // ReLU is fused into the convert
         const int py = py0 + r;
-        if (tma_out) {
-          // [6 pixels][box_c channels] slab -> one TMA store (clipped at the image edge and at C0 by the tensor map)
+        {
+          // [12 pixels][box_c channels] slab -> one TMA store (clipped at the image edge and at C0 by the tensor map)
           const uint32_t slab = slab0 + slab_sel * (uint32_t)OUT_SLAB;
-          uint8_t* sp = slab_ptr0 + slab_sel * OUT_SLAB + lane * 2;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this slab
+          uint8_t* sp = slab_ptr0 + slab_sel * OUT_SLAB;
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this slab
           __syncwarp();
           if (ch_valid) {
+            if (dense32) {
 #pragma unroll
-            for (int pc = 0; pc < HW; ++pc) *reinterpret_cast<__nv_bfloat16*>(sp + pc * pitch) = __float2bfloat16_rn(o[pc]);
+              for (int pc = 0; pc < TPW; pc += 2) {
+                const uint32_t w = relu_pack_bf16x2(o[pc], o[pc + 1]);
+                *reinterpret_cast<uint16_t*>(sp + pc * 64) = (uint16_t)(w & 0xffffu);
+                *reinterpret_cast<uint16_t*>(sp + (pc + 1) * 64) = (uint16_t)(w >> 16);
+              }
+            } else {
+              const int pitch = p.box_c * 2;
+#pragma unroll
+              for (int pc = 0; pc < TPW; ++pc) *reinterpret_cast<__nv_bfloat16*>(sp + pc * pitch) = __float2bfloat16_rn(fmaxf(o[pc], 0.0f));
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            if (warp_valid && py < p.Ho && px0 < p.Wo && !(p.dbg & 1)) tma_store_4d(&map_y, slab, chan0, px0, py, cur.n);
+          if (leader) {
+            if (warp_valid && py < p.Ho && !(p.dbg & 1)) tma_store_4d(&map_y, slab, chan0, px0, py, t.n);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           slab_sel ^= 1u;
-        } else if (ch_valid && py < p.Ho && !(p.dbg & 1)) {
-          __nv_bfloat16* yrow = p.y.p + p.y.img_off(cur.n) + (int64_t)(py * p.Wo + px0) * p.y.ld + ch;
-#pragma unroll
-          for (int pc = 0; pc < HW; ++pc)
-            if (px0 + pc < p.Wo) yrow[pc * p.y.ld] = __float2bfloat16_rn(o[pc]);
         }
       }
     }
-    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs must outlive their stores
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs must outlive their stores
   }
 
   ptx::tc_fence_before();
@@ -572,6 +613,9 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.tiles_y = ceil_div(a.Ho, TPH);
   const int64_t total = (int64_t)a.n_img * a.tiles_x * a.tiles_y;
   DCFA_REQUIRE(total < (1ll << 31), "stem: too many tiles");
+  a.total_tiles = (int)total;
+  a.div_img = make_fastdiv((uint32_t)(a.tiles_x * a.tiles_y));
+  a.div_row = make_fastdiv((uint32_t)a.tiles_x);
 
   // ---- tensor maps, zero fill outside the image:
   //      fp32 NCHW : dims (W, H, C, N), box (PWB, 9, 3, 1)      uint8 NHWC : dims (3W bytes, H, N), box (RAWB, 9, 1)
@@ -617,14 +661,15 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   alignas(64) CUtensorMap map_y;
   memset(&map_y, 0, sizeof(map_y));
   a.box_c = a.C0 >= 32 ? 32 : (a.C0 + 7) / 8 * 8;
-  a.tma_out = (a.C0 % 8 == 0 && ((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 &&
-               (a.y.gi <= 0 || a.y.gstride == (int64_t)a.y.gi * a.y.img_stride)) ? 1 : 0;
-  if (a.tma_out) {
+  DCFA_REQUIRE(a.C0 % 8 == 0 && ((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 &&
+                   (a.y.gi <= 0 || a.y.gstride == (int64_t)a.y.gi * a.y.img_stride),
+               "stem: the output view must be 16-byte aligned with C0 %% 8 == 0 and a uniform image stride (TMA store)");
+  {
     EncodeTiledFn enc = stem_encode_fn();
     DCFA_REQUIRE(enc != nullptr, "stem: cuTensorMapEncodeTiled entry point unavailable");
     const cuuint64_t ydim[4] = {(cuuint64_t)a.C0, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.n_img};
     const cuuint64_t ystr[3] = {(cuuint64_t)a.y.ld * 2, (cuuint64_t)a.Wo * a.y.ld * 2, (cuuint64_t)a.y.img_stride * 2};
-    const cuuint32_t ybox[4] = {(cuuint32_t)a.box_c, (cuuint32_t)HW, 1u, 1u};
+    const cuuint32_t ybox[4] = {(cuuint32_t)a.box_c, (cuuint32_t)TPW, 1u, 1u};
     const cuuint32_t yes[4] = {1u, 1u, 1u, 1u};
     CUresult cr = enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.y.p, ydim, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

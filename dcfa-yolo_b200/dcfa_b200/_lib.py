@@ -11,7 +11,9 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdcfa_b200.so")
 # every symbol include/dcfa_b200.h declares
 SYMBOLS = ("dcfa_abi_version", "dcfa_sizeof_view", "dcfa_sizeof_op", "dcfa_last_error", "dcfa_device_check",
            "dcfa_launch_count", "dcfa_run_ops", "dcfa_decode_box", "dcfa_nms_workspace_bytes", "dcfa_nms",
-           "dcfa_letterbox_workspace_bytes", "dcfa_letterbox_u8", "dcfa_pack_detections")
+           "dcfa_letterbox_workspace_bytes", "dcfa_letterbox_u8", "dcfa_pack_detections",
+           "dcfa_plan_create", "dcfa_plan_run", "dcfa_plan_num_launches", "dcfa_plan_destroy", "dcfa_plan_load",
+           "dcfa_plan_get_info", "dcfa_plan_forward")
 
 
 class DcfaError(RuntimeError):
@@ -42,6 +44,14 @@ def _load():
                                       C.c_void_p, C.c_int64, C.c_void_p]
     lib.dcfa_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p]
+    lib.dcfa_plan_create.argtypes = [C.POINTER(abi.Op), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+    lib.dcfa_plan_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    lib.dcfa_plan_num_launches.argtypes = [C.c_void_p]
+    lib.dcfa_plan_destroy.argtypes = [C.c_void_p]
+    lib.dcfa_plan_destroy.restype = None
+    lib.dcfa_plan_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.dcfa_plan_get_info.argtypes = [C.c_void_p, C.POINTER(abi.PlanInfo)]
+    lib.dcfa_plan_forward.argtypes = [C.c_void_p] * 9
     if lib.dcfa_abi_version() != abi.ABI_VERSION:
         raise ImportError("dcfa_b200: ABI version %d != %d" % (lib.dcfa_abi_version(), abi.ABI_VERSION))
     if lib.dcfa_sizeof_view() != C.sizeof(abi.View) or lib.dcfa_sizeof_op() != C.sizeof(abi.Op):

@@ -53,3 +53,16 @@ def new_op(kind, **kw):
             raise AttributeError("dcfa_op has no field %r" % k)
         setattr(op, k, v)
     return op
+
+
+class PlanInfo(C.Structure):
+    """dcfa_plan_info"""
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_classes", C.c_int32),
+                ("anchors", C.c_int32), ("no", C.c_int32), ("level_hw", (C.c_int32 * 2) * 3), ("input_u8", C.c_int32),
+                ("depth_plane", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class PlanFileHeader(C.Structure):
+    """dcfa_plan_file_header"""
+    _fields_ = [("magic", C.c_char * 8), ("abi_version", C.c_int32), ("sizeof_op", C.c_int32), ("n_ops", C.c_int32),
+                ("nbufs", C.c_int32), ("blob_bytes", C.c_int64), ("arena_bytes", C.c_int64), ("info", PlanInfo)]

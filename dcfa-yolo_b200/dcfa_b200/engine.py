@@ -29,7 +29,17 @@ class Engine:
         self._bufs = (C.c_void_p * P.NUM_BUFS)()
         self._bufs[P.BUF_BLOB] = self.blob.data_ptr()
         self._bufs[P.BUF_ARENA] = self.arena.data_ptr()
+        # the C-side plan object: blob and arena bound, inputs / outputs supplied per run; every launch prepared once
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.dcfa_plan_create(self.plan.op_array, self.n_ops, self._bufs, P.NUM_BUFS, C.byref(self._plan)))
         self.anchors, self.strides = self._make_anchors()
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan:
+            _lib.lib.dcfa_plan_destroy(plan)
+            self._plan = None
 
     def _make_anchors(self):
         """make_anchors (reference utils/utils_bbox.py:16-28), always fp32; returned as (2,A) and (1,A)."""
@@ -68,7 +78,7 @@ class Engine:
             b[P.BUF_X0], b[P.BUF_X1], b[P.BUF_X2] = x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr()
             b[P.BUF_DBOX], b[P.BUF_CLS] = dbox.data_ptr(), cls.data_ptr()
             st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(_lib.lib.dcfa_run_ops(self.plan.op_array, self.n_ops, b, P.NUM_BUFS, C.c_void_p(st)))
+            _lib.check(_lib.lib.dcfa_plan_run(self._plan, b, P.NUM_BUFS, C.c_void_p(st)))
         self.last_bufs = b   # the pointer table of the latest call (profiling tools replay single ops with it)
         return dbox, cls, x
 

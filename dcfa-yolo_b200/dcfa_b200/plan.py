@@ -87,6 +87,29 @@ class Plan:
         self.op_array = (abi.Op * len(self.ops))(*self.ops)
         del self.sd
 
+    def info(self):
+        """dcfa_plan_info of this plan (what a plan file records)."""
+        pi = abi.PlanInfo()
+        pi.batch, pi.height, pi.width, pi.num_classes, pi.anchors, pi.no = self.B, self.H, self.W, self.nc, self.A, self.no
+        for i, (h, w) in enumerate(self.level_shapes):
+            pi.level_hw[i][0], pi.level_hw[i][1] = h, w
+        pi.input_u8, pi.depth_plane = int(self.input_u8), int(self.depth_plane)
+        return pi
+
+    def save(self, path):
+        """Write the plan file dcfa_plan_load reads (include/dcfa_b200.h: dcfa_plan_file_header, the op records, the
+        parameter blob): everything a caller without Python needs to run this forward pass."""
+        import ctypes as C
+        h = abi.PlanFileHeader()
+        h.magic = b"DCFAPLN1"
+        h.abi_version, h.sizeof_op, h.n_ops, h.nbufs = abi.ABI_VERSION, C.sizeof(abi.Op), len(self.ops), NUM_BUFS
+        h.blob_bytes, h.arena_bytes = int(self.blob_tensor.numel()), int(self.arena_bytes)
+        h.info = self.info()
+        with open(path, "wb") as f:
+            f.write(bytes(h))
+            f.write(bytes(self.op_array))
+            f.write(self.blob_tensor.numpy().tobytes())
+
     # ------------------------------------------------------------------------------------------ helpers
     def _alloc_bytes(self, nbytes):
         off = (self.arena_bytes + 255) // 256 * 256

@@ -190,6 +190,67 @@ int64_t dcfa_launch_count(void);
 int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, void* stream);
 
 /*
+ * The same op list as a PLAN object: prepared once (kernel variants chosen, TMA tensor maps encoded, launch geometry and
+ * arguments fixed), then replayed with one launch call per kernel -- what a long-lived caller should use.
+ *   bufs[i] != NULL at creation: bound for the plan's lifetime (the parameter blob and the activation arena);
+ *   bufs[i] == NULL: supplied at every dcfa_plan_run (inputs / outputs); the few ops that touch such a buffer are
+ *   re-prepared only when its pointer differs from the previous run.
+ * A plan belongs to the device that was current at creation and is not thread-safe; runs on one stream at a time share
+ * its arena.  dcfa_plan_run enqueues asynchronously and is CUDA-graph capturable.
+ */
+typedef struct dcfa_plan dcfa_plan;
+int dcfa_plan_create(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, dcfa_plan** out);
+int dcfa_plan_run(dcfa_plan* plan, void* const* bufs, int nbufs, void* stream);
+int dcfa_plan_num_launches(const dcfa_plan* plan);   /* kernels per run (0 for parts not prepared yet) */
+void dcfa_plan_destroy(dcfa_plan* plan);
+
+/*
+ * Buffer indices of the plans the host-side compiler emits for YoloBody.forward (nets/yolo_mul.py:397-462):
+ * what the views of its ops reference.
+ */
+enum {
+  DCFA_BUF_BLOB = 0,   /* packed parameters (folded BN, pre-tiled bf16 weights) */
+  DCFA_BUF_ARENA = 1,  /* activations */
+  DCFA_BUF_RGB = 2,    /* input: fp32 [B,3,H,W], or uint8 [B,H,W,3] (plans compiled for uint8 input) */
+  DCFA_BUF_NIR = 3,    /* input: second modality; uint8 [B,H,W] for depth-plane plans */
+  DCFA_BUF_X0 = 4,     /* outputs: head maps fp32 [B,64+nc,H/8,W/8], [.., H/16, W/16], [.., H/32, W/32] */
+  DCFA_BUF_X1 = 5,
+  DCFA_BUF_X2 = 6,
+  DCFA_BUF_DBOX = 7,   /* output: fp32 [B,4,A] */
+  DCFA_BUF_CLS = 8,    /* output: fp32 [B,nc,A] */
+  DCFA_NUM_BUFS = 9
+};
+
+/* Facts about a compiled forward plan, stored in plan files. */
+typedef struct dcfa_plan_info {
+  int32_t batch, height, width, num_classes;
+  int32_t anchors;          /* A = sum of the three level sizes */
+  int32_t no;               /* 64 + num_classes */
+  int32_t level_hw[3][2];   /* (H_l, W_l) of the three head levels */
+  int32_t input_u8;         /* inputs are uint8 NHWC images */
+  int32_t depth_plane;      /* the second input is a single uint8 plane */
+  int32_t reserved[3];
+} dcfa_plan_info;
+
+/* Plan file = this header, n_ops dcfa_op records, blob_bytes of parameters (written by dcfa_b200.plan.Plan.save). */
+typedef struct dcfa_plan_file_header {
+  char magic[8];            /* "DCFAPLN1" */
+  int32_t abi_version, sizeof_op, n_ops, nbufs;
+  int64_t blob_bytes, arena_bytes;
+  dcfa_plan_info info;
+} dcfa_plan_file_header;
+
+/*
+ * For callers without the Python plan compiler: load a plan file, upload its parameters and allocate its arena (the
+ * library owns both until dcfa_plan_destroy), then run YoloBody.forward on device pointers.
+ *   rgb/depth: inputs as the plan was compiled for (see dcfa_plan_get_info); x0..x2, dbox, cls: outputs as above.
+ */
+int dcfa_plan_load(const char* path, dcfa_plan** out);
+int dcfa_plan_get_info(const dcfa_plan* plan, dcfa_plan_info* info);
+int dcfa_plan_forward(dcfa_plan* plan, const void* rgb, const void* depth, float* x0, float* x1, float* x2, float* dbox,
+                      float* cls, void* stream);
+
+/*
  * DecodeBox.decode_box (utils/utils_bbox.py:49-58).
  *   dbox [B,4,A] fp32 (l,t,r,b distances), cls [B,nc,A] fp32 logits (batch stride cls_bstride
  *   elements, row stride A), anchors [2,A] fp32 with element (k,a) at anchors[k*anc_s0 + a*anc_s1],
