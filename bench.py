@@ -271,7 +271,7 @@ class Pipeline:
         self.graph.replay()
 
 
-def algorithmic_bytes(kind, op, cnt_ops, batch, plan, fp32_input=True):
+def algorithmic_bytes(kind, op, cnt_ops, batch, plan, fp32_input=True, extra_res=False):
     """HBM bytes a kernel must move at the very least: each input read once, each output written once."""
     n, hw_in, hw_out = op.n_img, op.Hi * op.Wi, op.Ho * op.Wo
     if kind == "stem":
@@ -280,6 +280,8 @@ def algorithmic_bytes(kind, op, cnt_ops, batch, plan, fp32_input=True):
         return n * hw_in * op.Cin * 2 * (3 if op.x2.buf >= 0 else 2)
     if kind in ("cbam", "maxpool5", "chain"):
         return 2 * n * hw_in * op.Cin * 2
+    if kind == "ghost":   # module input + output (+ the bottleneck's residual on the second module)
+        return n * hw_in * op.Cin * 2 * (3 if extra_res else 2)
     if kind == "upsample":
         return n * hw_in * op.Cin * 2 * (2 if op.x2.buf >= 0 else 1) + n * hw_out * op.Cin * 2
     if kind == "dfl":
@@ -315,6 +317,10 @@ def profile_ops(net, batch, size, device, iters=5):
               ops[i + 1].kind == abi.OP_DWCONV and ops[i + 2].kind == abi.OP_CONV):
             groups.append((i, 3, "chain", names[i].rsplit(".", 1)[0]))
             i += 3
+        elif (k == abi.OP_CONV and (ops[i].flags & abi.CONV_FLAG_GHOST_HEAD) and i + 1 < len(ops) and
+              ops[i + 1].kind == abi.OP_DWCONV):
+            groups.append((i, 2, "ghost", names[i].rsplit(".", 1)[0]))
+            i += 2
         else:
             groups.append((i, 1, abi.OP_NAMES[k], names[i]))
             i += 1
@@ -337,7 +343,8 @@ def profile_ops(net, batch, size, device, iters=5):
         if kind == "conv":
             flops = 2 * op.n_img * op.Ho * op.Wo * op.Cout * op.K_real
         rows.append({"i": i0, "name": name, "kind": kind, "ms": float(ms[gi]), "flops": flops,
-                     "bytes": int(algorithmic_bytes(kind, op, cnt, batch, eng.plan)),
+                     "bytes": int(algorithmic_bytes(kind, op, cnt, batch, eng.plan,
+                                                    extra_res=(kind == "ghost" and ops[i0 + 1].x2.buf >= 0))),
                      "shape": [op.n_img, op.Hi, op.Wi, op.Cin, op.Cout, op.ksize, op.stride]})
     n = len(ops)
     # decode_box and NMS (outside the op list: separate C-ABI entry points)

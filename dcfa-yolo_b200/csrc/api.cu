@@ -127,6 +127,8 @@ int unit_span(const dcfa_op* ops, int i, int n_ops) {
   if (op.kind == DCFA_OP_CONV && (op.flags & DCFA_CONV_FLAG_CHAIN_HEAD) && i + 2 < n_ops && ops[i + 1].kind == DCFA_OP_DWCONV &&
       ops[i + 2].kind == DCFA_OP_CONV)
     return 3;
+  if (op.kind == DCFA_OP_CONV && (op.flags & DCFA_CONV_FLAG_GHOST_HEAD) && i + 1 < n_ops && ops[i + 1].kind == DCFA_OP_DWCONV)
+    return 2;
   return 1;
 }
 
@@ -173,6 +175,14 @@ int dispatch_unit(const dcfa_op* ops, int i, int span, void* const* bufs, int nb
       char tmp[400];
       snprintf(tmp, sizeof(tmp), "%s", dcfa_last_error());
       return fail(rc, "op %d (fused chain): %s", i, tmp);
+    }
+    if (rc == 1) return DCFA_OK;
+  } else if (span == 2) {
+    const int rc = launch_ghost(ops[i], ops[i + 1], bufs, st);
+    if (rc < 0) {
+      char tmp[400];
+      snprintf(tmp, sizeof(tmp), "%s", dcfa_last_error());
+      return fail(rc, "op %d (fused ghost module): %s", i, tmp);
     }
     if (rc == 1) return DCFA_OK;
   }

@@ -13,6 +13,11 @@
 // Both weight matrices, the depthwise taps and the BN vectors stay resident in shared memory; the halo of the next
 // tile is requested as soon as GEMM 1 has consumed the current one.  Intermediates are rounded to bf16 exactly where
 // the three-kernel path stores them, so both paths produce the same values.
+//
+// The same kernel in GHOST mode runs a RepGhostModule in deploy algebra (nets/repghost.py:98-123): 1x1 conv + BN (+SiLU)
+// -> depthwise 3x3 (identity-BN branch folded into the centre tap) (+SiLU) (+ the bottleneck's residual, :279) --
+// steps 1-3, with the depthwise result stored straight to global memory instead of feeding a second GEMM.  The plan
+// holds the two records (CONV with DCFA_CONV_FLAG_GHOST_HEAD, DWCONV); launch_ghost falls back to the two kernels.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,6 +53,8 @@ struct ChainArgs {
   uint32_t tmem_cols;
   uint32_t off_a2, off_w1, off_w2, off_t1, off_par, off_bar;   // shared-memory offsets from the 1024-aligned base
   uint32_t t1_pitch;         // bytes per row of the GEMM-1 result tile
+  int ghost;                 // 1: no second GEMM -- the depthwise result (+ residual) is the output
+  View<const __nv_bfloat16> res;   // ghost mode: optional residual, added after the depthwise activation
 };
 
 // v[e] = act(acc[e] * scale[e] + bias[e]) for 16 consecutive channels: 128-bit shared-memory loads of the BN vectors,
@@ -82,9 +89,17 @@ __device__ __forceinline__ void chain_tma_load(uint32_t dst, const CUtensorMap* 
 // Depthwise 3x3 over the GEMM-1 tile (same register tiling as dw_tile_compute in dwconv.cu): one thread = one
 // 8-channel chunk of one tile column and R consecutive output rows, for the 2R chunks starting at c8_base; the bf16
 // results go straight into the swizzled K-major A tile of GEMM 2.
+// Tile of the output tensor in ghost mode: pointer to pixel (0, 0) of the tile (channel 0), rows / columns inside the image
+struct GhostTile {
+  __nv_bfloat16* y;
+  const __nv_bfloat16* res;
+  int rows, cols;
+  int64_t y_row, res_row;   // elements per image row
+};
+
 template <int R, int CT>
 __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, uint32_t s_a2, const float* wd_s, const float* bd_s,
-                                         int c8_base, int tid) {
+                                         int c8_base, int tid, const GhostTile& gt) {
   constexpr int C8N = 2 * R;                 // chunks handled per pass: 4 (R = 2) or 8 (R = 4)
   const int c8 = c8_base + tid % C8N;
   const int col = (tid / C8N) % TW;
@@ -134,6 +149,18 @@ __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, 
     if (p.actd != DCFA_ACT_NONE) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = apply_act(f[e], p.actd);
+    }
+    if (p.ghost) {   // the module's output: (+ residual) -> 16 bytes of one pixel, neighbouring threads cover the neighbouring chunks
+      if (oy0 + o < gt.rows && col < gt.cols) {
+        if (gt.res) {
+          float rr[8];
+          unpack8(ldg128(gt.res + (int64_t)(oy0 + o) * gt.res_row + (int64_t)col * p.res.ld + c8 * 8), rr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += rr[e];
+        }
+        stg128(gt.y + (int64_t)(oy0 + o) * gt.y_row + (int64_t)col * p.y.ld + c8 * 8, pack8(f));
+      }
+      continue;
     }
     const uint4 v = pack8(f);
     const uint32_t pp = (uint32_t)((oy0 + o) * TW + col);
@@ -213,14 +240,18 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
       uint4* d1 = reinterpret_cast<uint4*>(gb + p.off_w1);
       uint4* d2 = reinterpret_cast<uint4*>(gb + p.off_w2);
       const int n16 = C * C * 2 / 16;
-      for (int i = tid; i < n16; i += kChainThreads) { d1[i] = __ldg(src1 + i); d2[i] = __ldg(src2 + i); }
+      for (int i = tid; i < n16; i += kChainThreads) d1[i] = __ldg(src1 + i);
+      if (!p.ghost)
+        for (int i = tid; i < n16; i += kChainThreads) d2[i] = __ldg(src2 + i);
       for (int i = tid; i < 9 * C; i += kChainThreads) wd_s[i] = __ldg(p.wd + (int64_t)g * 9 * C + i);
       for (int i = tid; i < C; i += kChainThreads) {
         bd_s[i] = __ldg(p.bd + (int64_t)g * C + i);
         s1_s[i] = __ldg(p.s1 + (int64_t)g * p.sb1_gstride + i);
         b1_s[i] = __ldg(p.b1 + (int64_t)g * p.sb1_gstride + i);
-        s2_s[i] = __ldg(p.s2 + (int64_t)g * p.sb2_gstride + i);
-        b2_s[i] = __ldg(p.b2 + (int64_t)g * p.sb2_gstride + i);
+        if (!p.ghost) {
+          s2_s[i] = __ldg(p.s2 + (int64_t)g * p.sb2_gstride + i);
+          b2_s[i] = __ldg(p.b2 + (int64_t)g * p.sb2_gstride + i);
+        }
       }
       cur_g = g;
       __syncthreads();
@@ -276,14 +307,27 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
     ptx::tc_fence_before();
     __syncthreads();   // T1 complete; the GEMM-1 accumulators have been read
 
-    // ---- depthwise 3x3 -> A tile of GEMM 2
+    // ---- depthwise 3x3 -> A tile of GEMM 2 (ghost mode: -> global memory, the module's output)
+    GhostTile gt;
+    gt.y = nullptr; gt.res = nullptr; gt.rows = gt.cols = 0; gt.y_row = gt.res_row = 0;
+    if (p.ghost) {
+      gt.y_row = (int64_t)p.W * p.y.ld;
+      gt.y = p.y.p + p.y.img_off(n) + (int64_t)(ty * TH) * gt.y_row + (int64_t)(tx * TW) * p.y.ld;
+      gt.rows = p.H - ty * TH;
+      gt.cols = p.W - tx * TW;
+      if (p.res.p) {
+        gt.res_row = (int64_t)p.W * p.res.ld;
+        gt.res = p.res.p + p.res.img_off(n) + (int64_t)(ty * TH) * gt.res_row + (int64_t)(tx * TW) * p.res.ld;
+      }
+    }
     if (C == 32) {
-      chain_dw<2, CT>(p, t1, s_a2, wd_s, bd_s, 0, tid);
+      chain_dw<2, CT>(p, t1, s_a2, wd_s, bd_s, 0, tid, gt);
     } else {
 #pragma unroll
-      for (int cb = 0; cb < (C >> 3); cb += 8) chain_dw<4, CT>(p, t1, s_a2, wd_s, bd_s, cb, tid);
+      for (int cb = 0; cb < (C >> 3); cb += 8) chain_dw<4, CT>(p, t1, s_a2, wd_s, bd_s, cb, tid, gt);
     }
     __syncthreads();
+    if (p.ghost) continue;   // T1 may be rewritten by the next tile's epilogue 1
 
     // ---- GEMM 2: [128 pixels, C] x W2^T -> TMEM columns [0, C)
     if (tid == 0) {
@@ -358,39 +402,59 @@ bool same_view(const dcfa_view& a, const dcfa_view& b) {
 
 }  // namespace
 
+namespace {
+int launch_chain_impl(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op* pw2p, void* const* bufs, cudaStream_t st);
+}
+
 // pw1 (CONV 1x1), dw (DWCONV), pw2 (CONV 1x1): returns 1 if the fused kernel was launched, 0 if the chain is left to
 // the three kernels, < 0 on error.  Only called for chains the plan marked as private (DCFA_CONV_FLAG_CHAIN_HEAD).
 int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void* const* bufs, cudaStream_t st) {
+  return launch_chain_impl(pw1, dw, &pw2, bufs, st);
+}
+
+// RepGhostModule: pw (CONV 1x1 with DCFA_CONV_FLAG_GHOST_HEAD), dw (DWCONV, optional residual): 1 = fused kernel launched,
+// 0 = left to the two kernels, < 0 on error.
+int launch_ghost(const dcfa_op& pw, const dcfa_op& dw, void* const* bufs, cudaStream_t st) {
+  return launch_chain_impl(pw, dw, nullptr, bufs, st);
+}
+
+namespace {
+int launch_chain_impl(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op* pw2p, void* const* bufs, cudaStream_t st) {
+  const bool ghost = pw2p == nullptr;
+  const dcfa_op& pw2 = ghost ? pw1 : *pw2p;   // ghost mode: the checks on the second conv degenerate to the first
   {
-    const char* e = getenv("DCFA_CHAIN");   // debug: DCFA_CHAIN=0 keeps the three-kernel path
+    const char* e = getenv(ghost ? "DCFA_GHOST" : "DCFA_CHAIN");   // debug: =0 keeps the separate kernels
     if (e && atoi(e) == 0) return 0;
   }
   bool force = false;
   {
-    const char* e = getenv("DCFA_CHAIN");
-    force = e && atoi(e) == 2;   // tests: also take the shapes the heuristic below leaves to the three kernels
+    const char* e = getenv(ghost ? "DCFA_GHOST" : "DCFA_CHAIN");
+    force = e && atoi(e) == 2;   // tests: also take the shapes the heuristic below leaves to the separate kernels
   }
   const int C = pw1.Cin;
   if (!(C == 32 || C == 64 || C == 128)) return 0;
   // measured (s, B=32): 0.172 vs 0.188 ms at C=32/160^2, 0.074 vs 0.090 at C=64/80^2, but 0.065 vs 0.062 at C=128/40^2,
   // where one CTA per SM (217 KB of shared memory) no longer hides the phase latencies
-  if (C == 128 && !force) return 0;
+  if (!ghost && C == 128 && !force) return 0;
   if (pw1.ksize != 1 || pw2.ksize != 1 || pw1.stride != 1 || pw2.stride != 1 || pw1.Cout != C || pw2.Cin != C || pw2.Cout != C ||
       dw.Cin != C || pw1.n_tiles != 1 || pw2.n_tiles != 1 || pw1.BN != C || pw2.BN != C)
     return 0;
   const int bk = pw1.flags & 0xff;
   if (bk != (pw2.flags & 0xff) || (bk != 64 && bk != 32) || C % bk != 0 || pw1.k_blocks != C / bk || pw2.k_blocks != C / bk) return 0;
   if (pw1.out_mode != DCFA_OUT_BF16_NHWC || pw2.out_mode != DCFA_OUT_BF16_NHWC || pw1.x2.buf >= 0 || pw2.x2.buf >= 0 ||
-      dw.x2.buf >= 0 || pw1.parts != 0 || pw2.parts != 0 || pw1.f0 != 1.0f || pw2.f0 != 1.0f)
+      (!ghost && dw.x2.buf >= 0) || pw1.parts != 0 || pw2.parts != 0 || pw1.f0 != 1.0f || pw2.f0 != 1.0f)
     return 0;
-  if (!same_view(pw1.y, dw.x) || !same_view(dw.y, pw2.x)) return 0;
+  if (!same_view(pw1.y, dw.x) || (!ghost && !same_view(dw.y, pw2.x))) return 0;
   if (pw1.n_img != dw.n_img || pw1.n_img != pw2.n_img || pw1.Hi != dw.Hi || pw1.Wi != dw.Wi || pw2.Hi != dw.Hi || pw2.Wi != dw.Wi ||
       pw1.group_imgs != dw.group_imgs || pw1.group_imgs != pw2.group_imgs)
     return 0;
 
   ChainArgs a;
   View<const __nv_bfloat16> x = resolve<const __nv_bfloat16>(pw1.x, bufs);
-  a.y = resolve<__nv_bfloat16>(pw2.y, bufs);
+  a.y = resolve<__nv_bfloat16>(ghost ? dw.y : pw2.y, bufs);
+  a.ghost = ghost ? 1 : 0;
+  a.res = resolve<const __nv_bfloat16>(dw.x2, bufs);
+  if (!ghost) a.res.p = nullptr;
   a.w1 = resolve_ptr<const __nv_bfloat16>(pw1.w, bufs);
   a.w2 = resolve_ptr<const __nv_bfloat16>(pw2.w, bufs);
   a.w1_gstride = pw1.w_gstride; a.w2_gstride = pw2.w_gstride;
@@ -407,6 +471,7 @@ int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void
   if (x.gi > 0 && x.gstride != (int64_t)x.gi * x.img_stride) return 0;   // grouped input views: not through one tensor map
   if (((uintptr_t)x.p % 16) != 0 || x.ld % 8 != 0 || x.img_stride % 8 != 0) return 0;
   if (((uintptr_t)a.y.p % 32) != 0 || a.y.ld % 16 != 0 || a.y.img_stride % 16 != 0 || a.y.gstride % 16 != 0) return 0;
+  if (a.res.p && (((uintptr_t)a.res.p % 16) != 0 || a.res.ld % 8 != 0 || a.res.img_stride % 8 != 0 || a.res.gstride % 8 != 0)) return 0;
   if (((uintptr_t)a.w1 % 16) != 0 || ((uintptr_t)a.w2 % 16) != 0 || a.w1_gstride % 8 != 0 || a.w2_gstride % 8 != 0) return 0;
 
   a.bk = bk;
@@ -424,9 +489,9 @@ int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void
 
   // shared memory: XA | A2 | W1 | W2 | T1 | parameters | barriers
   uint32_t off = (uint32_t)a.katoms * 256u * a.row_bytes;
-  a.off_a2 = off; off += (uint32_t)a.katoms * 128u * a.row_bytes;
+  a.off_a2 = off; off += ghost ? 0u : (uint32_t)a.katoms * 128u * a.row_bytes;
   a.off_w1 = off; off += (uint32_t)C * C * 2u;
-  a.off_w2 = off; off += (uint32_t)C * C * 2u;
+  a.off_w2 = off; off += ghost ? 0u : (uint32_t)C * C * 2u;
   a.t1_pitch = (uint32_t)C * 2u + 16u;
   a.off_t1 = off; off += ((uint32_t)NHALO * a.t1_pitch + 127u) & ~127u;
   a.off_par = off; off += (uint32_t)(9 * C + 5 * C) * 4u;
@@ -470,5 +535,6 @@ int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void
   count_launch();
   return 1;
 }
+}  // namespace
 
 }  // namespace dcfa

@@ -228,6 +228,7 @@ int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void* const* bufs, cudaStream_t st);
+int launch_ghost(const dcfa_op& pw, const dcfa_op& dw, void* const* bufs, cudaStream_t st);
 int launch_cbam_pool(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_mlp(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_stats(const dcfa_op& op, void* const* bufs, cudaStream_t st);

@@ -294,9 +294,12 @@ class Plan:
 
         pw1, dw1 = module(p + '.ghost1')
         pw2, dw2 = module(p + '.ghost2')
+        # u1 / v1 are private and no module output aliases its input: each (1x1 conv, depthwise) pair may run fused
         self.conv(name + '.g1.pw', x, u1, [pw1], 1, 1, abi.ACT_SILU)
+        self.ops[-1].flags |= abi.CONV_FLAG_GHOST_HEAD
         self.dwconv(name + '.g1.dw', u1, u2, [dw1], abi.ACT_SILU)
         self.conv(name + '.g2.pw', u2, v1, [pw2], 1, 1, abi.ACT_NONE)
+        self.ops[-1].flags |= abi.CONV_FLAG_GHOST_HEAD
         self.dwconv(name + '.g2.dw', v1, dst, [dw2], abi.ACT_NONE, res=x)
 
     def _c2f(self, name, p, src, dst, depth, col_scale=None):

@@ -89,7 +89,10 @@ enum {
   DCFA_CONV_FLAG_CHAIN_HEAD = 0x400,
   /* 3x3 stride-2 conv, Cin = 32, dense even-width input: w holds SIX k-blocks of 64 per n-tile, one per (kernel row,
    * pixel pair): [0 | w(dy,0)] applied to input pair ox-1 and [w(dy,1) | w(dy,2)] applied to pair ox */
-  DCFA_CONV_FLAG_PAIR = 0x800
+  DCFA_CONV_FLAG_PAIR = 0x800,
+  /* this 1x1 conv and the DWCONV after it are a RepGhostModule (nets/repghost.py:70-123) whose intermediate tensor nobody
+   * else reads and whose output does not alias its input -- dcfa_run_ops may run the two records as one fused kernel */
+  DCFA_CONV_FLAG_GHOST_HEAD = 0x1000
 };
 
 /* DCFA_OP_CONV output modes */
@@ -185,7 +188,7 @@ int64_t dcfa_launch_count(void);
  * Consecutive records may run as ONE kernel when their shapes allow: CBAM_POOL, CBAM_MLP, CBAM_STATS, CBAM_APPLY of one
  * tensor (a thread-block cluster per image; the partial-sum / gate / stats scratch views are then not written), and
  * CONV(1x1) -> DWCONV -> CONV(1x1) chains whose head carries DCFA_CONV_FLAG_CHAIN_HEAD (the two intermediate tensors
- * are then not written).  Results are the same either way.
+ * are then not written), and CONV(1x1, DCFA_CONV_FLAG_GHOST_HEAD) -> DWCONV pairs.  Results are the same either way.
  */
 int dcfa_run_ops(const dcfa_op* ops, int n_ops, void* const* bufs, int nbufs, void* stream);
 

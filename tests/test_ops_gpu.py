@@ -361,6 +361,54 @@ def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w,
     _bf16_close(outs[0], torch.cat(refs).permute(0, 2, 3, 1), "chain")
 
 
+@pytest.mark.parametrize("n,h,w,c,act,use_res", [(2, 16, 32, 64, 2, False), (3, 21, 37, 64, 0, True), (2, 40, 40, 128, 2, False),
+                                                 (2, 40, 40, 128, 0, True), (1, 8, 16, 32, 2, True), (2, 80, 80, 64, 0, True)])
+def test_repghost_module_fused_vs_two_kernels(cuda, monkeypatch, n, h, w, c, act, use_res):
+    """RepGhostModule in deploy algebra (nets/repghost.py:98-123, :263-279): 1x1 conv + BN (+SiLU) -> depthwise 3x3 (+SiLU)
+    (+ residual).  The fused kernel (DCFA_CONV_FLAG_GHOST_HEAD) against the two-kernel path and against torch; input,
+    output and residual are channel slots of wider tensors, as in C2f_repghost's concat buffer."""
+    from dcfa_b200 import abi, pack
+    g = torch.Generator().manual_seed(41 + c + h)
+    cat = bf16_round(torch.randn(n, h, w, 3 * c, generator=g))       # [other | module input / residual | output slot]
+    w1 = bf16_round(torch.randn(c, c, 1, 1, generator=g) / c ** 0.5)
+    wd = torch.randn(c, 1, 3, 3, generator=g) * 0.3
+    bd = torch.randn(c, generator=g) * 0.2
+    s1 = torch.rand(c, generator=g) + 0.5
+    b1 = torch.randn(c, generator=g) * 0.2
+    pk, m1 = pack.pack_conv_weight(w1)
+    W1, S1, B1 = pk.to(cuda), s1.to(cuda), b1.to(cuda)
+    WD, BD = wd.reshape(c, 9).t().contiguous().to(cuda), bd.to(cuda)
+    outs = []
+    for fused in ("2", "0"):
+        monkeypatch.setenv("DCFA_GHOST", fused)
+        xg = cat.to(torch.bfloat16).to(cuda)
+        t1 = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+        bufs = [xg, W1, S1, B1, t1, WD, BD]
+        common = dict(n_img=n, group_imgs=n, Hi=h, Wi=w, Ho=h, Wo=w, Cin=c, Cout=c)
+        dw = abi.new_op(abi.OP_DWCONV, act=act, x=nhwc_view(t1, 4), w=flat_view(5), bias=flat_view(6), y=nhwc_view(xg, 0, 2 * c),
+                        n_img=n, group_imgs=n, Hi=h, Wi=w, Cin=c)
+        if use_res:
+            dw.x2 = nhwc_view(xg, 0, c)
+        ops = [abi.new_op(abi.OP_CONV, act=abi.ACT_SILU if act else abi.ACT_NONE, x=nhwc_view(xg, 0, c), w=flat_view(1),
+                          scale=flat_view(2), bias=flat_view(3), y=nhwc_view(t1, 4), ksize=1, stride=1, BN=m1["BN"],
+                          n_tiles=m1["n_tiles"], k_blocks=m1["k_blocks"], K_real=m1["K_real"], w_gstride=pk.numel(), sb_gstride=c,
+                          flags=m1["bk"] | abi.CONV_FLAG_GHOST_HEAD, **common), dw]
+        _run(ops, bufs)
+        if fused == "2":
+            assert float(t1.float().abs().max()) == 0.0, "fused path not taken"
+        assert torch.equal(xg[..., :2 * c].float().cpu(), cat[..., :2 * c]), "module wrote outside its output slot"
+        outs.append(xg[..., 2 * c:].float().cpu())
+    _bf16_close(outs[0], outs[1], "ghost fused vs two kernels")
+    x = cat[..., c:2 * c].permute(0, 3, 1, 2)
+    t = F.conv2d(x, w1) * s1.view(1, -1, 1, 1) + b1.view(1, -1, 1, 1)
+    t = bf16_round(F.silu(t) if act else t)
+    t = F.conv2d(t, wd, bd, 1, 1, groups=c)
+    t = F.silu(t) if act else t
+    if use_res:
+        t = t + x
+    _bf16_close(outs[0], t.permute(0, 2, 3, 1), "ghost module")
+
+
 def _cbam_ref(x, fc1, fc2, w7):
     """CBAM restated with plain torch ops (nets/yolo_mul.py:56-102); x NCHW fp32."""
     avg, mx = x.mean((2, 3), keepdim=True), x.amax((2, 3), keepdim=True)
