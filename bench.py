@@ -342,6 +342,8 @@ def profile_ops(net, batch, size, device, iters=5):
         flops = 0
         if kind == "conv":
             flops = 2 * op.n_img * op.Ho * op.Wo * op.Cout * op.K_real
+            if op.flags & abi.CONV_FLAG_DFL:   # block-diagonal merge of the two final head convs: count the real blocks only
+                flops = 2 * op.n_img * op.Ho * op.Wo * (64 * 64 + op.nc * (op.Cin - 64))
         rows.append({"i": i0, "name": name, "kind": kind, "ms": float(ms[gi]), "flops": flops,
                      "bytes": int(algorithmic_bytes(kind, op, cnt, batch, eng.plan,
                                                     extra_res=(kind == "ghost" and ops[i0 + 1].x2.buf >= 0))),

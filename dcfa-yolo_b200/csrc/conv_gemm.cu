@@ -334,6 +334,7 @@ bool pixel_linear(const View<T>& v, int64_t hw) {
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   if ((op.flags & 0xff) != 0) return launch_conv_tma(op, bufs, st);  // packed per (tap, channel block): TMA path
   DCFA_REQUIRE(op.parts == 0, "conv(gather): split outputs need the TMA path");
+  DCFA_REQUIRE(!(op.flags & DCFA_CONV_FLAG_DFL), "conv(gather): the fused DFL epilogue needs the TMA path");
   ConvArgs a;
   a.x = resolve<const __nv_bfloat16>(op.x, bufs);
   a.res = resolve<const __nv_bfloat16>(op.x2, bufs);

@@ -81,6 +81,10 @@ struct TmaConvArgs {
   uint32_t out_stage_bytes;  // 128 rows * cbox * 2
   uint32_t tmem_cols;
   uint32_t acc_stages;   // TMEM accumulator stages (2 or 4): the MMA issuer runs this many tiles ahead of the epilogues
+  // DCFA_CONV_FLAG_DFL (fp32 NCHW head map [box 64 | cls nc]): the epilogue also emits DFL(box) and the class logits
+  float* dfl_dbox;       // [n_img, 4, A] (nullptr: off)
+  float* dfl_cls;        // [n_img, nc, A]
+  int dfl_A, dfl_aoff, dfl_nc;   // total anchors, first anchor of this level, classes
   int epi_split;         // 1: BOTH epilogue groups work on every tile, each on every other 16-channel chunk (wide
                          // tiles: halves the epilogue latency of a tile, which is exposed at the tail of every launch
                          // and is all there is when a CTA gets one tile); 0: the groups alternate tiles
@@ -426,6 +430,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if (c0 + e < cvalid) yf[(int64_t)(c0 + e) * HoWo] = v[e];
+            if (p.dfl_dbox) {
+              // DFL (nets/yolo_mul.py:312-322) straight from the fp32 accumulators: a 16-channel chunk of the box part is
+              // one side's 16 bins -- softmax expectation in registers; the class logits are gathered into (B, nc, A)
+              // (:459-460).  The thread's row is one anchor of this level.
+              const int cg0 = nt * p.BN + c0;
+              const int64_t a = (int64_t)p.dfl_aoff + pix;
+              if (cg0 < 64) {
+                float mx = v[0];
+#pragma unroll
+                for (int e = 1; e < 16; ++e) mx = fmaxf(mx, v[e]);
+                float den = 0.0f, num = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float ex = __expf(v[e] - mx);
+                  den += ex;
+                  num = fmaf((float)e, ex, num);
+                }
+                p.dfl_dbox[((int64_t)n * 4 + (cg0 >> 4)) * p.dfl_A + a] = __fdividef(num, den);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const int c = cg0 + e - 64;
+                  if (c < p.dfl_nc) p.dfl_cls[((int64_t)n * p.dfl_nc + c) * p.dfl_A + a] = v[e];
+                }
+              }
+            }
           }
         }
       };
@@ -525,6 +555,15 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.pair = (op.flags & DCFA_CONV_FLAG_PAIR) ? 1 : 0;
   a.act = op.act; a.out_mode = op.out_mode; a.out_ctot = op.out_ctot; a.out_coff = op.out_coff;
   a.post_scale = op.f0;
+  a.dfl_dbox = nullptr; a.dfl_cls = nullptr; a.dfl_A = a.dfl_aoff = a.dfl_nc = 0;
+  if (op.flags & DCFA_CONV_FLAG_DFL) {
+    a.dfl_dbox = resolve_ptr<float>(op.a1, bufs);
+    a.dfl_cls = resolve_ptr<float>(op.a2, bufs);
+    a.dfl_A = op.A; a.dfl_aoff = op.hidden; a.dfl_nc = op.nc;
+    DCFA_REQUIRE(a.dfl_dbox && a.dfl_cls && op.out_mode == DCFA_OUT_F32_NCHW && op.out_coff == 0 && op.Cout == 64 + op.nc &&
+                     op.nc >= 1 && op.act == DCFA_ACT_NONE && op.hidden >= 0 && op.hidden + op.Ho * op.Wo <= op.A,
+                 "conv(tma): DCFA_CONV_FLAG_DFL needs the fp32 NCHW head map [64 box | nc cls] and its dbox / cls outputs");
+  }
 
   DCFA_REQUIRE(x.p && a.y.p && a.w && a.scale && a.bias, "conv(tma): missing tensor");
   DCFA_REQUIRE(a.bk == 64 || a.bk == 32 || a.bk == 16, "conv(tma): bk %d unsupported", a.bk);

@@ -10,6 +10,7 @@ STEM_FLAG_X2_PLANE = 0x200   # DCFA_STEM_FLAG_X2_PLANE
 CONV_FLAG_CHAIN_HEAD = 0x400   # DCFA_CONV_FLAG_CHAIN_HEAD
 CONV_FLAG_PAIR = 0x800         # DCFA_CONV_FLAG_PAIR
 CONV_FLAG_GHOST_HEAD = 0x1000  # DCFA_CONV_FLAG_GHOST_HEAD
+CONV_FLAG_DFL = 0x2000         # DCFA_CONV_FLAG_DFL
 OP_NAMES = {OP_STEM: "stem", OP_CONV: "conv", OP_DWCONV: "dwconv", OP_CBAM_POOL: "cbam_pool", OP_CBAM_MLP: "cbam_mlp",
             OP_CBAM_STATS: "cbam_stats", OP_CBAM_APPLY: "cbam_apply", OP_MAXPOOL5: "maxpool5", OP_UPSAMPLE: "upsample",
             OP_DFL: "dfl"}

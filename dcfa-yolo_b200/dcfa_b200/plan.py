@@ -141,7 +141,7 @@ class Plan:
         out[:, src.perm_tensor()] = w
         return out
 
-    def conv(self, name, src, dst, groups, k, stride, act, res=None, f32_out=None, post_scale=1.0, split=None):
+    def conv(self, name, src, dst, groups, k, stride, act, res=None, f32_out=None, post_scale=1.0, split=None, macs_per_pixel=None):
         """groups: list (1 or 2 entries) of (weight [Cout,Cin,k,k] logical order, scale [Cout], bias [Cout],
         col_scale or None).  dst: TRef (bf16 NHWC) or None with f32_out = (buf, ctot, coff).
         split = (c, TRef): output channels from c on go to that second tensor instead of dst[..., c:]."""
@@ -186,7 +186,8 @@ class Plan:
             op.out_ctot, op.out_coff = ctot, coff
         if res is not None:
             op.x2 = res.view()
-        self.conv_flops += 2 * src.n * ho * wo * meta['Cout'] * meta['K_real']
+        # algorithmic FLOPs of the reference's convolutions (a block-diagonal merge does not count its zero blocks)
+        self.conv_flops += 2 * src.n * ho * wo * (macs_per_pixel if macs_per_pixel is not None else meta['Cout'] * meta['K_real'])
         self._emit(name, op)
 
     def dwconv(self, name, src, dst, groups, act, res=None):
@@ -421,29 +422,41 @@ class Plan:
         c2h = max(16, c3 // 4, 64)
         c3h = max(c3, nc)
         no = 64 + nc
-        self.level_shapes = []
+        self.level_shapes = [(p.h, p.w) for p in (p3, p4, p5)]
+        self.A = sum(h * w for h, w in self.level_shapes)
+        assert self.level_shapes[1] == (down2(h3), down2(w3)) and self.level_shapes[2] == (down2(h4), down2(w4))
+        assert torch.equal(s['dfl.conv.weight'].reshape(-1), torch.arange(16.0)), \
+            "dfl.conv.weight must be arange(16) (frozen in the reference, nets/yolo_mul.py:315-317)"
+        a_off = 0
         for i, (p, buf) in enumerate(((p3, BUF_X0), (p4, BUF_X1), (p5, BUF_X2))):
             a = self._conv_group('cv2.%d.0' % i, 1e-3)
             b = self._conv_group('cv3.%d.0' % i, 1e-3)
             merged = (torch.cat([a[0], b[0]]), torch.cat([a[1], b[1]]), torch.cat([a[2], b[2]]), None)
             h1t = self._tensor(B, p.h, p.w, c2h + c3h)
             self.conv('head%d.0' % i, p, h1t, [merged], 3, 1, abi.ACT_SILU)
-            hb = self._tensor(B, p.h, p.w, c2h)
-            hc = self._tensor(B, p.h, p.w, c3h)
-            self.conv('head%d.box1' % i, h1t.sub(0, c2h), hb, [self._conv_group('cv2.%d.1' % i, 1e-3)], 3, 1, abi.ACT_SILU)
-            self.conv('head%d.cls1' % i, h1t.sub(c2h, c3h), hc, [self._conv_group('cv3.%d.1' % i, 1e-3)], 3, 1, abi.ACT_SILU)
-            one = torch.ones(64)
-            self.conv('head%d.box2' % i, hb, None, [(s['cv2.%d.2.weight' % i], one, s['cv2.%d.2.bias' % i], None)], 1, 1,
-                      abi.ACT_NONE, f32_out=(buf, no, 0))
-            self.conv('head%d.cls2' % i, hc, None, [(s['cv3.%d.2.weight' % i], torch.ones(nc), s['cv3.%d.2.bias' % i], None)],
-                      1, 1, abi.ACT_NONE, f32_out=(buf, no, 64))
-            self.level_shapes.append((p.h, p.w))
-        self.A = sum(h * w for h, w in self.level_shapes)
-        assert self.level_shapes[1] == (down2(h3), down2(w3)) and self.level_shapes[2] == (down2(h4), down2(w4))
-
-        # ---- DFL (+ the level gather of :459-460)
-        assert torch.equal(s['dfl.conv.weight'].reshape(-1), torch.arange(16.0)), \
-            "dfl.conv.weight must be arange(16) (frozen in the reference, nets/yolo_mul.py:315-317)"
-        self._emit('dfl', abi.new_op(abi.OP_DFL, a0=_flat(BUF_X0, 0), a1=_flat(BUF_X1, 0), a2=_flat(BUF_X2, 0),
-                                     y=_flat(BUF_DBOX, 0), x2=_flat(BUF_CLS, 0), n_img=B, Hi=h3, Wi=w3, nc=nc, A=self.A))
+            # second convs of both branches write the two channel slots of ONE tensor, so that the two final biased 1x1
+            # convs (:389, :391) run as a single block-diagonal GEMM (K = c2h + c3h, N = 64 + nc) whose epilogue writes
+            # x[i] = cat(box, cls) (:453), DFL(box) (:461) and the gathered class logits (:459-460)
+            hbc = self._tensor(B, p.h, p.w, c2h + c3h)
+            self.conv('head%d.box1' % i, h1t.sub(0, c2h), hbc.sub(0, c2h), [self._conv_group('cv2.%d.1' % i, 1e-3)], 3, 1, abi.ACT_SILU)
+            self.conv('head%d.cls1' % i, h1t.sub(c2h, c3h), hbc.sub(c2h, c3h), [self._conv_group('cv3.%d.1' % i, 1e-3)], 3, 1, abi.ACT_SILU)
+            wout = torch.zeros(no, c2h + c3h, 1, 1)
+            wout[:64, :c2h] = s['cv2.%d.2.weight' % i]
+            wout[64:, c2h:] = s['cv3.%d.2.weight' % i]
+            bout = torch.cat([s['cv2.%d.2.bias' % i], s['cv3.%d.2.bias' % i]])
+            self.conv('head%d.out' % i, hbc, None, [(wout, torch.ones(no), bout, None)], 1, 1, abi.ACT_NONE, f32_out=(buf, no, 0),
+                      macs_per_pixel=64 * c2h + nc * c3h)
+            op = self.ops[-1]
+            if (op.flags & 0xff) != 0:   # TMA packing: fused DFL epilogue; else (odd widths) a separate DFL pass below
+                op.flags |= abi.CONV_FLAG_DFL
+                op.a1, op.a2 = _flat(BUF_DBOX, 0), _flat(BUF_CLS, 0)
+                op.A, op.nc, op.hidden = self.A, nc, a_off
+            a_off += p.h * p.w
+        if not all(o.flags & abi.CONV_FLAG_DFL for o, n in zip(self.ops, self.op_names) if n.endswith('.out')):
+            for o, n in zip(self.ops, self.op_names):
+                if n.endswith('.out'):
+                    o.flags &= ~abi.CONV_FLAG_DFL
+            # ---- DFL (+ the level gather of :459-460) as its own pass
+            self._emit('dfl', abi.new_op(abi.OP_DFL, a0=_flat(BUF_X0, 0), a1=_flat(BUF_X1, 0), a2=_flat(BUF_X2, 0),
+                                         y=_flat(BUF_DBOX, 0), x2=_flat(BUF_CLS, 0), n_img=B, Hi=h3, Wi=w3, nc=nc, A=self.A))
         self.no = no

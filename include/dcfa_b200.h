@@ -92,7 +92,12 @@ enum {
   DCFA_CONV_FLAG_PAIR = 0x800,
   /* this 1x1 conv and the DWCONV after it are a RepGhostModule (nets/repghost.py:70-123) whose intermediate tensor nobody
    * else reads and whose output does not alias its input -- dcfa_run_ops may run the two records as one fused kernel */
-  DCFA_CONV_FLAG_GHOST_HEAD = 0x1000
+  DCFA_CONV_FLAG_GHOST_HEAD = 0x1000,
+  /* the last conv of a head level (nets/yolo_mul.py:388-391 merged: Cout = 64 box + nc class channels, fp32 NCHW map
+   * x[i]): the epilogue ALSO applies DFL (:312-322) to the box channels and gathers the level into the (B, 4, A) /
+   * (B, nc, A) tensors of :459-461 -- a1 = dbox fp32 [n_img,4,A], a2 = cls fp32 [n_img,nc,A], A = total anchors,
+   * hidden = first anchor of this level, nc = classes.  Replaces a separate DCFA_OP_DFL pass over the maps. */
+  DCFA_CONV_FLAG_DFL = 0x2000
 };
 
 /* DCFA_OP_CONV output modes */

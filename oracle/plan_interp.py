@@ -133,6 +133,13 @@ def run_ops(ops, bufs):
             else:
                 dst = bufs[op.y.buf].view(torch.float32).view(n, op.out_ctot, op.Ho, op.Wo)
                 dst[:, op.out_coff:op.out_coff + op.Cout] = y
+                if op.flags & 0x2000:   # DCFA_CONV_FLAG_DFL: DFL of the box channels + class gather for this level's anchors
+                    hw = op.Ho * op.Wo
+                    box = y[:, :64].reshape(n, 4, 16, hw)
+                    dbox = (torch.softmax(box, 2) * torch.arange(16.0).view(1, 1, 16, 1)).sum(2)
+                    bufs[op.a1.buf].view(torch.float32).view(n, 4, op.A)[:, :, op.hidden:op.hidden + hw] = dbox
+                    bufs[op.a2.buf].view(torch.float32).view(n, op.nc, op.A)[:, :, op.hidden:op.hidden + hw] = \
+                        y[:, 64:64 + op.nc].reshape(n, op.nc, hw)
         elif k == 3:  # DWCONV
             c = op.Cin
             x = read_nhwc(bufs, op.x, n, op.Hi, op.Wi, c).permute(0, 3, 1, 2)
