@@ -708,6 +708,13 @@ int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& st
   // cluster size: as many CTAs per image as keep the whole grid within one wave, bands of at least 3 rows
   int CS = 8;
   while (CS > 1 && ((int64_t)a.n_img * CS > sm_count() || ceil_div(a.H, CS) < 3)) CS >>= 1;
+  {
+    const char* e = getenv("DCFA_CBAM_CS");   // experiments: force the cluster size (more CTAs per image, several waves)
+    if (e && atoi(e) >= 1) {
+      CS = atoi(e);
+      while (CS > 1 && ceil_div(a.H, CS) < 3) CS >>= 1;
+    }
+  }
   if (!force && (int64_t)a.n_img * CS < sm_count() / 4) return 0;   // too few CTAs to fill the GPU: keep the wide kernels
   a.rows_per = ceil_div(a.H, CS);
   const int c8n = a.C >> 3, planes = kFusedThreads / c8n, round_px = planes * kU;

@@ -11,23 +11,27 @@
 //   * the tcgen05 shared-memory descriptor does the im2col: NO-SWIZZLE K-major layout with LBO = 16 B (next K chunk =
 //     next pixel pair) and SBO = 128 B (next 8 rows), i.e. operand row n = the 16 bf16 starting at pixel 2n of the
 //     LINEAR patch (pitch 28): four consecutive pixels x 4 channels.  Rows overlap in memory; the hardware only
-//     computes addresses (tools/umma_overlap_test.cu proves it on a B200).  One K=16 MMA per kernel row and per pixel
-//     PARITY: the even conv pixel 2n uses weights [w(ky,0) | w(ky,1) | w(ky,2) | 0], the odd conv pixel 2n+1 uses
-//     [0 | w(ky,0) | w(ky,1) | w(ky,2)] over the SAME operand rows, into a second accumulator;
-//   * the GEMM is turned so that CHANNELS are the 128 MMA rows (C0 replicated 128/C0pad times) and pixels are TMEM
-//     columns: replica r of a channel owns POOLED ROW r of the tile (three conv rows, 14 TMEM columns per row and
-//     accumulator); the 3x3/2 max-pool is pure register arithmetic with three-input max; BN + ReLU after pooling
+//     computes addresses (tools/umma_overlap_test.cu proves it on a B200).  The even conv pixel 2n uses weights
+//     [w(ky,0) | w(ky,1) | w(ky,2) | 0], the odd conv pixel 2n+1 uses [0 | w(ky,0) | w(ky,1) | w(ky,2)] over the SAME
+//     operand rows, so both PARITIES are stacked on the M dimension of ONE K=16 MMA per kernel row: in every TMEM lane
+//     quarter, lanes 0..15 hold the even conv columns of 16 channels and lanes 16..31 the odd ones (measured: the
+//     stem's time is linear in its MMA count, 0.317 / 0.373 / 0.461 ms for 0 / 3 / 6 MMAs per tile);
+//   * the GEMM is turned so that CHANNELS are MMA rows and pixels are TMEM columns: a thread holds three conv rows
+//     (14 TMEM columns each) of ONE channel and one column parity; the vertical 3-max is pure register arithmetic
+//     with three-input max, the two lanes of a parity pair (16 apart in the same warp) swap half of their column
+//     maxima with seven shuffles and each finishes six pooled pixels (a first version that paired two WARPS through
+//     shared memory and a named barrier per row was 0.1 ms slower than not stacking at all); BN + ReLU after pooling
 //     (exact: the sign of the BN scale is folded into the weights, so the pooled quantity is monotone in the
-//     accumulator); the 6 pooled pixels x 32 channels of a warp leave through a 384-byte shared-memory slab and ONE
+//     accumulator); the 12 pooled pixels x 16 channels of a warp leave through a 384-byte shared-memory slab and ONE
 //     TMA store (no global address arithmetic, edges clipped by the tensor map);
-//   * warp-specialised pipeline, one CTA per SM, all of TMEM (2 tiles x 2 parities x 128 columns):
+//   * warp-specialised pipeline, one CTA per SM, all of TMEM (4 accumulator stages x 128 columns):
 //       warp 20      TMA producer: raw patch ring (fp32 NCHW planes, uint8 NHWC rows or a uint8 depth plane)
 //       warps 16-19  converters, ONE TILE PER WARP (four tiles in flight: the dependent LDS -> convert -> STS chain and the
 //                    proxy fence of one tile overlap the other three): raw -> bf16 [y][x][4], fence.proxy.async, arrive
-//       warp 21      MMA issuer: 6 x (M128 N128 K16) per tile, commits free the converted slot / publish the accumulators
-//       warps 0-15   two epilogue groups alternating tiles; per group two warps per TMEM lane quarter, each taking half of
-//                    the tile's pooled columns (ncu: one warp per quarter spent ~1 800 cycles per tile in dependent
-//                    tcgen05.ld -> max -> convert -> st.shared -> proxy fence -> TMA store chains).
+//       warp 21      MMA issuer: 3 x (M128 N128 K16) per tile, commits free the converted slot / publish the accumulators
+//       warps 0-15   four epilogue groups, one per accumulator stage, taking every fourth tile (ncu: an epilogue warp
+//                    spends ~1 500 cycles per tile in dependent tcgen05.ld -> max -> shuffle -> convert -> st.shared ->
+//                    proxy fence -> TMA store chains; four tiles in flight hide them).
 // Tile: 4 x 12 pooled pixels = 9 x 25 conv pixels (linear index L = cy*28 + cx, parity = cx & 1, TMEM column L >> 1).
 // Out-of-image conv positions are excluded from the max (reference: -inf pool padding); zero padding of the conv comes
 // from the TMA's out-of-bounds fill.
@@ -59,12 +63,15 @@ constexpr int RAW_SLOT = 4224;                // bytes per raw ring slot (multip
 constexpr int NRAW = 4;                       // raw ring depth = converter warps (warp w owns slot w)
 constexpr int CVT_SLOT = 2560;                // bf16 [11][28][4] = 2464 + the rows the last MMA over-reads (columns 126, 127)
 constexpr int NCVT = 4;                       // converted-patch ring depth = converter warps
-constexpr int A_TILE_BYTES = 128 * 16 * 2;    // one (kernel row, parity) weight tile
-constexpr int A_GROUP_BYTES = 6 * A_TILE_BYTES;
-constexpr int OUT_SLAB = TPW * 32 * 2;        // 768: one pooled row of a warp, [12 pixels][32 channels] bf16
-constexpr int kEpiWarps = 8, kCvtWarps = 4;
+constexpr int A_TILE_BYTES = 128 * 16 * 2;    // one kernel row's weight tile (both parities stacked on the rows)
+constexpr int A_GROUP_BYTES = 3 * A_TILE_BYTES;
+constexpr int HW6 = TPW / 2;                   // pooled pixels one lane finishes per tile row
+constexpr int OUT_SLAB = 2 * TPW * 16 * 2;    // 768: two pooled rows of a warp, [2][12 pixels][16 channels] bf16
+constexpr int NACC = 4;                       // TMEM accumulator stages (128 columns each)
+constexpr int XCH_BYTES = 0;
+constexpr int kEpiWarps = 16, kCvtWarps = 4;
 constexpr int kCvtWarp0 = kEpiWarps, kTmaWarp = kEpiWarps + kCvtWarps, kMmaWarp = kTmaWarp + 1;
-constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 448
+constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
 constexpr uint32_t kTmemCols = 512;
 static_assert(NRAW == kCvtWarps && NCVT == kCvtWarps, "converter warp w owns raw slot w and converted slot w");
 static_assert(2 * PP * 8 + (NCOL - 1) * 16 + 32 <= CVT_SLOT, "MMA over-read must stay inside the slot");
@@ -91,7 +98,10 @@ FastDiv make_fastdiv(uint32_t d) {
 
 struct StemArgs {
   const void* x[2];        // fp32 NCHW / uint8 NHWC / (group 1, MODE_U8_C1) uint8 [N,H,W]
-  const __nv_bfloat16* w;  // [G][3][2][128 x 16] canonical no-swizzle K-major tiles (pack.pack_stem)
+  const __nv_bfloat16* w;  // [G] x (this channel block's [3][128 x 16] canonical no-swizzle K-major tiles, pack.pack_stem)
+  int64_t w_gstride;       // elements between the groups' tiles
+  int chan_base;           // first channel of this launch's block (0, or 64 for the second block of C0 > 64)
+  int cb;                  // row slots per parity that hold distinct channels: min(C0pad, 64) -> 32 (two replicas) or 64
   const float* scale;      // [G][C0pad]  (>= 0, sign folded into the weights)
   const float* bias;       // [G][C0pad]
   View<__nv_bfloat16> y;
@@ -99,8 +109,8 @@ struct StemArgs {
   int tiles_x, tiles_y, total_tiles;
   FastDiv div_img, div_row; // tiles per image / per tile row
   int use_tma;             // inputs through TMA boxes (else: plain loads with explicit zero padding)
-  int box_c;               // channels per output slab row (min(32, C0) rounded to 8)
-  int dbg;                 // experiments only (DCFA_STEM_DBG): 1 no stores, 2 no input loads, 4 no MMAs
+  int box_c;               // channels per output slab row (min(16, C0) rounded to 8)
+  int dbg;                 // experiments only (DCFA_STEM_DBG): 1 no stores, 2 no input loads, 4 no MMAs, 16 half the MMAs
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
@@ -136,6 +146,12 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4s(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr)
                : "memory");
 }
@@ -203,22 +219,23 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   const uint32_t s_raw = s_a + 2u * A_GROUP_BYTES;
   const uint32_t s_cvt = s_raw + (uint32_t)(NRAW * RAW_SLOT);
   const uint32_t s_out = s_cvt + (uint32_t)(NCVT * CVT_SLOT);
-  const uint32_t bars = s_out + (uint32_t)(kEpiWarps * 2 * OUT_SLAB);
+  const uint32_t s_xch = s_out + (uint32_t)(kEpiWarps * 2 * OUT_SLAB);
+  const uint32_t bars = s_xch + (uint32_t)(4 * XCH_BYTES);
   const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8u * NRAW;
   const uint32_t bar_cvt_full = bars + 16u * NRAW, bar_cvt_empty = bar_cvt_full + 8u * NCVT;
-  const uint32_t bar_tm_full = bar_cvt_empty + 8u * NCVT, bar_tm_empty = bar_tm_full + 16u;
-  const uint32_t tmem_slot = bar_tm_empty + 16u;
+  const uint32_t bar_tm_full = bar_cvt_empty + 8u * NCVT, bar_tm_empty = bar_tm_full + 8u * NACC;
+  const uint32_t tmem_slot = bar_tm_empty + 8u * NACC;
   uint8_t* raw_ptr = gbase + 2 * A_GROUP_BYTES;
   uint8_t* cvt_ptr = raw_ptr + NRAW * RAW_SLOT;
   uint8_t* out_ptr = cvt_ptr + NCVT * CVT_SLOT;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(out_ptr + kEpiWarps * 2 * OUT_SLAB + (tmem_slot - bars));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(out_ptr + kEpiWarps * 2 * OUT_SLAB + 4 * XCH_BYTES + (tmem_slot - bars));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(bar_raw_full + 8u * i, 1); ptx::mbar_init(bar_raw_empty + 8u * i, 1); }
       for (int i = 0; i < NCVT; ++i) { ptx::mbar_init(bar_cvt_full + 8u * i, 1); ptx::mbar_init(bar_cvt_empty + 8u * i, 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 4); }
+      for (int i = 0; i < NACC; ++i) { ptx::mbar_init(bar_tm_full + 8u * i, 1); ptx::mbar_init(bar_tm_empty + 8u * i, 4); }
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -233,10 +250,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_y)) : "memory");
   }
   {  // weight tiles of every group (constant parameters: no dependency on the previous kernel) and zeroed patch slots
-    const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(gbase);
-    const int n16 = p.groups * (A_GROUP_BYTES / 16);
-    for (int i = tid; i < n16; i += kStemThreads) dst[i] = __ldg(src + i);
+    for (int g = 0; g < p.groups; ++g) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.w + (int64_t)g * p.w_gstride);
+      for (int i = tid; i < A_GROUP_BYTES / 16; i += kStemThreads) dst[g * (A_GROUP_BYTES / 16) + i] = __ldg(src + i);
+    }
     uint4* cz = reinterpret_cast<uint4*>(cvt_ptr);
     for (int i = tid; i < NCVT * CVT_SLOT / 16; i += kStemThreads) cz[i] = make_uint4(0u, 0u, 0u, 0u);
     ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's operand reads
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     const uint32_t a_lo0 = (s_a & 0x3FFFFu) >> 4, b_lo0 = (s_cvt & 0x3FFFFu) >> 4;
     const uint32_t t_group1 = (uint32_t)p.group_imgs * p.div_img.d;   // first tile of the second modality
     for (uint32_t i = 0; i < n_tiles; ++i) {
-      const uint32_t ab = i & 1u, aph = (i >> 1) & 1u, cs = i & (NCVT - 1), cph = (i / NCVT) & 1u;
+      const uint32_t ab = i & (NACC - 1), aph = (i / NACC) & 1u, cs = i & (NCVT - 1), cph = (i / NCVT) & 1u;
       const uint32_t g = (t_begin + i) >= t_group1 ? 1u : 0u;
       wait_bar(bar_tm_empty + 8u * ab, aph ^ 1u);
       wait_bar(bar_cvt_full + 8u * cs, cph);
@@ -304,19 +322,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
       if (leader) {
         const uint32_t b0 = b_lo0 + cs * (uint32_t)(CVT_SLOT / 16);
         const uint32_t a0 = a_lo0 + g * (uint32_t)(A_GROUP_BYTES / 16);
-        const uint32_t d0 = tmem_base + ab * 256u;
+        const uint32_t d0 = tmem_base + ab * (uint32_t)NCOL;
         if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t bd = bd_hi | (uint64_t)(b0 + (uint32_t)(ky * PP * 8 / 16));
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              ptx::umma_bf16(d0 + (uint32_t)(e * NCOL), ad_hi | (uint64_t)(a0 + (uint32_t)((ky * 2 + e) * A_TILE_BYTES / 16)), bd, idesc,
-                             ky > 0 ? 1u : 0u);
-          }
+          for (int ky = 0; ky < 3; ++ky)
+            ptx::umma_bf16(d0, ad_hi | (uint64_t)(a0 + (uint32_t)(ky * A_TILE_BYTES / 16)),
+                           bd_hi | (uint64_t)(b0 + (uint32_t)(ky * PP * 8 / 16)), idesc, ky > 0 ? 1u : 0u);
         }
         ptx::umma_commit(bar_cvt_empty + 8u * cs);   // the converted patch may be overwritten
-        ptx::umma_commit(bar_tm_full + 8u * ab);     // both accumulators of this tile are complete
+        ptx::umma_commit(bar_tm_full + 8u * ab);     // the accumulator of this tile is complete
       }
       __syncwarp();
     }
@@ -453,12 +467,14 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue: group = tile parity, warp & 3 = TMEM lane quarter
+    // Lane l of quarter q: column parity e = l >> 4, channel lane cl = l & 15, row slot j = 16 q + cl.  cb = 64: slot = channel
+    // (all four pooled rows per warp); cb = 32: slots 32..63 are a replica that owns the other two pooled rows.
     const int q4 = warp & 3, grp = warp >> 2;
-    const int mrow = q4 * 32 + lane;              // accumulator row (TMEM lane)
-    const int ch = mrow & (p.C0pad - 1);          // C0pad is 32, 64 or 128
-    const int rep = mrow / p.C0pad;               // replica: handles the pooled rows rep, rep + nrep, ...
-    const int nrep = 128 / p.C0pad;
-    const int chan0 = ch - lane;                  // first channel of this warp (multiple of 32)
+    const int e = lane >> 4, cl = lane & 15;
+    const int slot0 = q4 * 16;
+    const int chan0 = p.chan_base + (p.cb == 64 ? slot0 : (slot0 & 31));   // first channel of this warp (multiple of 16)
+    const int rep = p.cb == 64 ? 0 : (q4 >> 1), nrep = p.cb == 64 ? 1 : 2;   // replica rep owns the pooled row pairs rep, rep + nrep
+    const int ch = chan0 + cl;
     const bool ch_valid = ch < p.C0;
     const bool warp_valid = chan0 < p.C0;
     const bool leader = ptx::elect_one();
@@ -467,86 +483,114 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     sc[1] = p.groups > 1 ? __ldg(p.scale + p.C0pad + ch) : sc[0];
     bi[1] = p.groups > 1 ? __ldg(p.bias + p.C0pad + ch) : bi[0];
     const uint32_t slab0 = s_out + (uint32_t)(warp * 2 * OUT_SLAB);
-    uint8_t* slab_ptr0 = out_ptr + warp * 2 * OUT_SLAB + lane * 2;
-    const bool dense32 = p.box_c == 32;           // slab row pitch 64 bytes: compile-time store offsets
-    const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)grp * 256u;
-    const uint32_t b_full = bar_tm_full + 8u * grp, b_empty = bar_tm_empty + 8u * grp;
-    uint32_t slab_sel = 0, aph = 0;
-    for (uint32_t i = (uint32_t)grp; i < n_tiles; i += 2, aph ^= 1u) {
+    const bool dense16 = p.box_c == 16;           // slab row pitch 32 bytes: compile-time store offsets
+    uint8_t* slab_ptr0 = out_ptr + warp * 2 * OUT_SLAB + cl * 2 + HW6 * e * (p.box_c * 2);   // this lane's first pixel: 6 e
+    const uint32_t b_full0 = bar_tm_full, b_empty0 = bar_tm_empty;
+    uint32_t slab_sel = 0;
+    for (uint32_t i = (uint32_t)grp; i < n_tiles; i += NACC) {   // group grp owns accumulator stage grp
+      const uint32_t ab = i & (NACC - 1), aph = (i / NACC) & 1u;
       const Tile t = tile_of(t_begin + i, p.div_img, p.div_row);
       const int g = t.n >= p.group_imgs ? 1 : 0;
       const float s = g ? sc[1] : sc[0], b = g ? bi[1] : bi[0];
       const int py0 = t.ty * TPH, px0 = t.tx * TPW;
       const bool border = t.ty == 0 || t.tx == 0 || 2 * py0 - 1 + CH > p.Hi || 2 * px0 - 1 + CW > p.Wi;
-      wait_bar(b_full, aph);
+      wait_bar(b_full0 + 8u * ab, aph);
       ptx::tc_fence_after();
-      for (int r = rep; r < TPH; r += nrep) {
-        // pooled row r = conv rows 2r..2r+2 = TMEM columns 28r .. 28r+41 of the even accumulator (conv columns 0,2,..,24
-        // in the first 13 of every 14) and of the odd accumulator (conv columns 1,3,..,23 in the first 12 of every 14)
-        uint32_t E[3 * HP], O[3 * HP];
-        const uint32_t te = t0 + (uint32_t)(2 * HP * r), to = te + (uint32_t)NCOL;
-        tmem_ld_x32(te, E); tmem_ld_x8(te + 32u, E + 32); tmem_ld_x2(te + 40u, E + 40);
-        tmem_ld_x32(to, O); tmem_ld_x8(to + 32u, O + 32);
-        O[40] = O[41] = 0u;
-        ptx::tmem_ld_wait();
-        if (r + nrep >= TPH) {   // last row of this thread: the accumulators may be overwritten by the next tile
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (leader) ptx::mbar_arrive(b_empty);
-        }
-        if (border) {   // exclude out-of-image conv positions from the max (reference: -inf pool padding)
-          const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // image coordinates of conv pixel (0, 0) of the tile
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + ab * (uint32_t)NCOL;
+      for (int rp = rep; rp < TPH / 2; rp += nrep) {
+        // pooled rows 2rp, 2rp+1 = conv rows 4rp .. 4rp+4 = 70 consecutive TMEM columns (56 rp ..); this lane's parity:
+        // conv columns 2k + e.  Both rows leave through ONE slab and ONE TMA store (the per-store proxy fence and bulk-group
+        // bookkeeping were ~15 % of the epilogue's time).
+        const uint32_t tr = t0 + (uint32_t)(4 * HP * rp);
+        const uint32_t slab = slab0 + slab_sel * (uint32_t)OUT_SLAB;
+        uint8_t* sp = slab_ptr0 + slab_sel * OUT_SLAB;
+        int cy0 = 2 * py0 - 1 + 4 * rp, cx0 = 2 * px0 - 1 + e;   // image coordinates of this lane's first conv pixel
+        // the column maxima of one pooled row -> swap with the lane of the other parity -> pool, BN, ReLU -> slab row h.
+        // The even lane finishes pooled pixels 0..5 (needs the odd maxima 0..5), the odd lane pixels 6..11 (needs the even
+        // maxima 6..12): with P = the even maxima and Q = the odd ones of the lane's six pixels, out = max3(P[pc], P[pc+1], Q[pc]).
+        auto finish_row = [&](const float (&v)[TPW + 1], int h) {
+          float rcv[7];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const bool yok = cy0 + 2 * r + j >= 0 && cy0 + 2 * r + j < p.Hi;
+          for (int k = 0; k < 7; ++k) rcv[k] = __shfl_xor_sync(0xffffffffu, e ? v[k] : v[6 + k], 16);
+          float o[HW6];
 #pragma unroll
-            for (int k = 0; k < TPW + 1; ++k)
-              if (!(yok && cx0 + 2 * k >= 0 && cx0 + 2 * k < p.Wi)) E[j * HP + k] = 0xff800000u;
-#pragma unroll
-            for (int k = 0; k < TPW; ++k)
-              if (!(yok && cx0 + 2 * k + 1 < p.Wi)) O[j * HP + k] = 0xff800000u;
+          for (int pc = 0; pc < HW6; ++pc) {
+            const float p0 = e ? rcv[pc] : v[pc], p1 = e ? rcv[pc + 1] : v[pc + 1], q0 = e ? v[6 + pc] : rcv[pc];
+            o[pc] = fmaf(max3(p0, p1, q0), s, b);
           }
-        }
-        // vertical 3-max per conv column, then horizontal 3-max at stride 2
-        float ve[TPW + 1], vo[TPW];
-#pragma unroll
-        for (int k = 0; k < TPW + 1; ++k)
-          ve[k] = max3(__uint_as_float(E[k]), __uint_as_float(E[HP + k]), __uint_as_float(E[2 * HP + k]));
-#pragma unroll
-        for (int k = 0; k < TPW; ++k)
-          vo[k] = max3(__uint_as_float(O[k]), __uint_as_float(O[HP + k]), __uint_as_float(O[2 * HP + k]));
-        float o[TPW];
-#pragma unroll
-        for (int pc = 0; pc < TPW; ++pc) o[pc] = fmaf(max3(ve[pc], vo[pc], ve[pc + 1]), s, b);   // ReLU is fused into the convert
-        const int py = py0 + r;
-        {
-          // [12 pixels][box_c channels] slab -> one TMA store (clipped at the image edge and at C0 by the tensor map)
-          const uint32_t slab = slab0 + slab_sel * (uint32_t)OUT_SLAB;
-          uint8_t* sp = slab_ptr0 + slab_sel * OUT_SLAB;
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this slab
-          __syncwarp();
           if (ch_valid) {
-            if (dense32) {
+            if (dense16) {
 #pragma unroll
-              for (int pc = 0; pc < TPW; pc += 2) {
-                const uint32_t w = relu_pack_bf16x2(o[pc], o[pc + 1]);
-                *reinterpret_cast<uint16_t*>(sp + pc * 64) = (uint16_t)(w & 0xffffu);
-                *reinterpret_cast<uint16_t*>(sp + (pc + 1) * 64) = (uint16_t)(w >> 16);
+              for (int pc = 0; pc < HW6; pc += 2) {
+                const uint32_t w = relu_pack_bf16x2(o[pc], o[pc + 1]);   // ReLU fused into the convert
+                *reinterpret_cast<uint16_t*>(sp + h * (TPW * 32) + pc * 32) = (uint16_t)(w & 0xffffu);
+                *reinterpret_cast<uint16_t*>(sp + h * (TPW * 32) + (pc + 1) * 32) = (uint16_t)(w >> 16);
               }
             } else {
               const int pitch = p.box_c * 2;
 #pragma unroll
-              for (int pc = 0; pc < TPW; ++pc) *reinterpret_cast<__nv_bfloat16*>(sp + pc * pitch) = __float2bfloat16_rn(fmaxf(o[pc], 0.0f));
+              for (int pc = 0; pc < HW6; ++pc)
+                *reinterpret_cast<__nv_bfloat16*>(sp + h * (TPW * pitch) + pc * pitch) = __float2bfloat16_rn(fmaxf(o[pc], 0.0f));
             }
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (leader) {
-            if (warp_valid && py < p.Ho && !(p.dbg & 1)) tma_store_4d(&map_y, slab, chan0, px0, py, t.n);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        };
+        // out-of-image conv positions are excluded from the max below (reference: -inf pool padding); border tiles only
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this slab
+        __syncwarp();
+        float mid[TPW + 1];   // conv row 4rp + 2 belongs to both pooled rows
+        {
+          uint32_t V[3 * HP];   // conv rows 4rp .. 4rp+2
+          tmem_ld_x32(tr, V); tmem_ld_x8(tr + 32u, V + 32); tmem_ld_x2(tr + 40u, V + 40);
+          ptx::tmem_ld_wait();
+          if (border) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const bool yok = cy0 + j >= 0 && cy0 + j < p.Hi;
+#pragma unroll
+              for (int k = 0; k < TPW + 1; ++k)
+                if (!(yok && cx0 + 2 * k >= 0 && cx0 + 2 * k < p.Wi)) V[j * HP + k] = 0xff800000u;
+            }
           }
-          slab_sel ^= 1u;
+          float v[TPW + 1];
+#pragma unroll
+          for (int k = 0; k < TPW + 1; ++k) {
+            mid[k] = __uint_as_float(V[2 * HP + k]);
+            v[k] = max3(__uint_as_float(V[k]), __uint_as_float(V[HP + k]), mid[k]);
+          }
+          finish_row(v, 0);
         }
+        {
+          uint32_t V[2 * HP];   // conv rows 4rp+3, 4rp+4
+          ptx::tmem_ld_x16(tr + 42u, V); tmem_ld_x8(tr + 58u, V + 16); tmem_ld_x4s(tr + 66u, V + 24);
+          ptx::tmem_ld_wait();
+          if (rp + nrep >= TPH / 2) {   // last rows of this thread: the accumulator may be overwritten by a later tile
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (leader) ptx::mbar_arrive(b_empty0 + 8u * ab);
+          }
+          if (border) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const bool yok = cy0 + 3 + j >= 0 && cy0 + 3 + j < p.Hi;
+#pragma unroll
+              for (int k = 0; k < TPW + 1; ++k)
+                if (!(yok && cx0 + 2 * k >= 0 && cx0 + 2 * k < p.Wi)) V[j * HP + k] = 0xff800000u;
+            }
+          }
+          float v[TPW + 1];
+#pragma unroll
+          for (int k = 0; k < TPW + 1; ++k) v[k] = max3(mid[k], __uint_as_float(V[k]), __uint_as_float(V[HP + k]));
+          finish_row(v, 1);
+        }
+        // [2 rows][12 pixels][box_c channels] slab -> one TMA store (clipped at the image edges and at C0 by the tensor map)
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (leader) {
+          const int py = py0 + 2 * rp;
+          if (warp_valid && py < p.Ho && !(p.dbg & 1)) tma_store_4d(&map_y, slab, chan0, px0, py, t.n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        slab_sel ^= 1u;
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs must outlive their stores
@@ -600,7 +644,11 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   DCFA_REQUIRE(a.C0 >= 1 && a.C0 <= 128, "stem: C0 %d unsupported", a.C0);
   DCFA_REQUIRE((a.C0pad == 32 || a.C0pad == 64 || a.C0pad == 128) && a.C0pad >= a.C0 && op.K_real == 27,
                "stem: weight packing mismatch (C0pad %d, C0 %d)", a.C0pad, a.C0);
-  DCFA_REQUIRE(op.w_gstride == 6 * 128 * 16 && op.sb_gstride == a.C0pad, "stem: weight tiles must be [G][3][2][128x16]");
+  const int nblk = a.C0pad > 64 ? a.C0pad / 64 : 1;   // channel blocks of 64 (one launch each)
+  DCFA_REQUIRE(op.w_gstride == (int64_t)nblk * 3 * 128 * 16 && op.sb_gstride == a.C0pad,
+               "stem: weight tiles must be [G][%d][3][128x16]", nblk);
+  a.w_gstride = op.w_gstride;
+  a.cb = a.C0pad < 64 ? 32 : 64;
   DCFA_REQUIRE(((uintptr_t)a.w % 16) == 0, "stem: weights must be 16-byte aligned");
   a.groups = a.n_img / a.group_imgs;
   DCFA_REQUIRE(!c1 || (u8 && a.groups == 2), "stem: the single-plane flag needs uint8 inputs and two groups");
@@ -660,7 +708,7 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   // ---- output tensor map: dims (C0, Wo, Ho, N) over the NHWC view, box (box_c channels, 12 pixels, 1, 1)
   alignas(64) CUtensorMap map_y;
   memset(&map_y, 0, sizeof(map_y));
-  a.box_c = a.C0 >= 32 ? 32 : (a.C0 + 7) / 8 * 8;
+  a.box_c = a.C0 >= 16 ? 16 : (a.C0 + 7) / 8 * 8;   // channels per epilogue warp (16 channel lanes x 2 parities)
   DCFA_REQUIRE(a.C0 % 8 == 0 && ((uintptr_t)a.y.p % 16) == 0 && a.y.ld % 8 == 0 && a.y.img_stride % 8 == 0 &&
                    (a.y.gi <= 0 || a.y.gstride == (int64_t)a.y.gi * a.y.img_stride),
                "stem: the output view must be 16-byte aligned with C0 %% 8 == 0 and a uniform image stride (TMA store)");
@@ -669,13 +717,13 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     DCFA_REQUIRE(enc != nullptr, "stem: cuTensorMapEncodeTiled entry point unavailable");
     const cuuint64_t ydim[4] = {(cuuint64_t)a.C0, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.n_img};
     const cuuint64_t ystr[3] = {(cuuint64_t)a.y.ld * 2, (cuuint64_t)a.Wo * a.y.ld * 2, (cuuint64_t)a.y.img_stride * 2};
-    const cuuint32_t ybox[4] = {(cuuint32_t)a.box_c, (cuuint32_t)TPW, 1u, 1u};
+    const cuuint32_t ybox[4] = {(cuuint32_t)a.box_c, (cuuint32_t)TPW, 2u, 1u};
     const cuuint32_t yes[4] = {1u, 1u, 1u, 1u};
     CUresult cr = enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.y.p, ydim, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
   }
-  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + kEpiWarps * 2 * OUT_SLAB + 256;
+  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + kEpiWarps * 2 * OUT_SLAB + 4 * XCH_BYTES + 256;
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(stem_kernel<MODE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -686,9 +734,15 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   }
   int64_t grid = sm_count();   // one CTA per SM: the kernel owns all 512 TMEM columns
   if (grid > total) grid = total;
-  if (!u8) launch_pdl(stem_kernel<MODE_F32>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
-  else if (!c1) launch_pdl(stem_kernel<MODE_U8>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
-  else launch_pdl(stem_kernel<MODE_U8_C1>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+  const __nv_bfloat16* w0 = a.w;
+  for (int blk = 0; blk < nblk; ++blk) {
+    a.w = w0 + (int64_t)blk * 3 * 128 * 16;
+    a.chan_base = 64 * blk;
+    if (!u8) launch_pdl(stem_kernel<MODE_F32>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+    else if (!c1) launch_pdl(stem_kernel<MODE_U8>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+    else launch_pdl(stem_kernel<MODE_U8_C1>, dim3((unsigned)grid), dim3(kStemThreads), smem, st, maps[0], maps[1], map_y, a);
+    if (blk + 1 < nblk) DCFA_CHECK_LAUNCH("stem_kernel");
+  }
   DCFA_CHECK_LAUNCH("stem_kernel");
   return DCFA_OK;
 }

@@ -87,53 +87,61 @@ def pack_conv_weight(w, bk=None):
     return packed, meta
 
 
-STEM_W_ELEMS = 6 * 128 * 16   # bf16 elements of one group's stem weight tiles: [ky 3][parity 2][128 rows x 16 K]
-
-
 def pack_stem(w, scale, bias, u8=False):
-    """Stem conv [C0,3,3,3] + folded BN -> (weight tiles bf16 [3*2*128*16], scale [C0pad], bias [C0pad], C0pad).
+    """Stem conv [C0,3,3,3] + folded BN -> (weight tiles bf16 [nblk*3*128*16], scale [C0pad], bias [C0pad], C0pad).
 
     The stem kernel never builds an im2col: its B operand is the bf16 [y][x][4 channel] input patch itself, read through a
     no-swizzle K-major descriptor whose row n is the 16 values starting at pixel 2n (four pixels x 4 channel slots).
-    So per kernel row ky there are two K=16 weight tiles: parity 0 (conv pixel 2n: taps on pixels 2n, 2n+1, 2n+2) has
-    K = kx*4 + ci, parity 1 (conv pixel 2n+1: taps on pixels 2n+1..2n+3) has K = (kx+1)*4 + ci; unused slots are zero.
+    A conv pixel of even column 2n taps pixels 2n..2n+2 (K = kx*4 + ci), one of odd column 2n+1 taps pixels 2n+1..2n+3
+    (K = (kx+1)*4 + ci); unused slots are zero.  Both PARITIES share the operand rows, so they are stacked on the 128 MMA
+    rows of ONE weight tile per kernel row ky.  Row m = 32*q + 16*e + cl: TMEM lane quarter q (one epilogue warp), column
+    parity e, channel lane cl -- the two parities of a channel sit 16 lanes apart in the SAME warp, which swaps its
+    column maxima with one shuffle.  Row slot j = 16*q + cl holds channel 64*blk + j % min(C0pad, 64)  (C0pad = 32: two
+    replicas of the 32 channels, each pooling other tile rows; C0pad = 128: two blocks of 64 channels, one launch each).
     Tiles are stored in the canonical no-swizzle layout of the tcgen05 descriptor: element (m, k) at
     (m//8)*128 + (k//8)*64 + (m%8)*8 + k%8  (8 rows x 16 bytes core matrices; LBO = 128 B, SBO = 256 B).
 
     u8=True: the scale carries preprocess_input's 1/255 (utils/utils.py:76-79) -- the kernel multiplies exact integer
     pixels.
 
-    CHANNELS sit on the 128 MMA rows (replicated C0pad-periodically so every TMEM lane quarter holds a copy) and the
-    kernel pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative BN scale
+    The kernel pools BEFORE applying scale/bias/ReLU, which needs a non-negative scale: channels with a negative BN scale
     get negated weights and |scale| (scale * conv(w) == |scale| * conv(sign * w))."""
     c0 = w.shape[0]
     c0pad = 32 if c0 <= 32 else (64 if c0 <= 64 else 128)
+    nblk, cb = max(1, c0pad // 64), min(c0pad, 64)
     sgn = torch.where(scale < 0, -torch.ones_like(scale), torch.ones_like(scale))
     ws = (w * sgn.view(-1, 1, 1, 1)).float()                      # [c, ci, ky, kx]
-    tiles = torch.zeros(3, 2, 128, 16, dtype=torch.float32)
+    tiles = torch.zeros(nblk, 3, 128, 16, dtype=torch.float32)
     rows = torch.arange(128)
-    src = rows % c0pad
-    valid = src < c0
-    for ky in range(3):
+    e_of = (rows % 32) // 16
+    slot = (rows // 32) * 16 + rows % 16
+    for blk in range(nblk):
+        src = 64 * blk + slot % cb
         for e in range(2):
-            for kx in range(3):
-                for ci in range(3):
-                    tiles[ky, e, rows[valid], (kx + e) * 4 + ci] = ws[src[valid], ci, ky, kx]
-    t = tiles.reshape(3, 2, 16, 8, 2, 8).permute(0, 1, 2, 4, 3, 5)   # [ky, e, m/8, k/8, m%8, k%8]
+            sel = (e_of == e) & (src < c0)
+            for ky in range(3):
+                for kx in range(3):
+                    for ci in range(3):
+                        tiles[blk, ky, rows[sel], (kx + e) * 4 + ci] = ws[src[sel], ci, ky, kx]
+    t = tiles.reshape(nblk, 3, 16, 8, 2, 8).permute(0, 1, 2, 4, 3, 5)   # [blk, ky, m/8, k/8, m%8, k%8]
     packed = t.reshape(-1).to(torch.bfloat16)
     sc = scale.abs() / 255.0 if u8 else scale.abs()
     return packed, pad_channels(sc, c0pad), pad_channels(bias, c0pad), c0pad
 
 
 def unpack_stem(packed, c0):
-    """Inverse of pack_stem's weight layout (test infrastructure uses it): bf16 [3*2*128*16] -> fp32 [c0,3,3,3] (sign-folded)."""
-    t = packed.float().reshape(3, 2, 16, 2, 8, 8).permute(0, 1, 2, 4, 3, 5).reshape(3, 2, 128, 16)
+    """Inverse of pack_stem's weight layout (test infrastructure uses it): bf16 [nblk*3*128*16] -> fp32 [c0,3,3,3] (sign-folded)."""
+    nblk = packed.numel() // (3 * 128 * 16)
+    t = packed.float().reshape(nblk, 3, 16, 2, 8, 8).permute(0, 1, 2, 4, 3, 5).reshape(nblk, 3, 128, 16)
     w = torch.zeros(c0, 3, 3, 3)
-    for ky in range(3):
-        for kx in range(3):
-            for ci in range(3):
-                w[:, ci, ky, kx] = t[ky, 0, :c0, kx * 4 + ci]
-                assert torch.equal(t[ky, 1, :c0, (kx + 1) * 4 + ci], w[:, ci, ky, kx])
+    for c in range(c0):
+        blk, j = c // 64, c % 64
+        m = (j // 16) * 32 + j % 16          # even-parity row of slot j; the odd-parity row is 16 further
+        for ky in range(3):
+            for kx in range(3):
+                for ci in range(3):
+                    w[c, ci, ky, kx] = t[blk, ky, m, kx * 4 + ci]
+                    assert t[blk, ky, m + 16, (kx + 1) * 4 + ci] == w[c, ci, ky, kx]
     return w
 
 

@@ -335,7 +335,7 @@ class Plan:
         self._emit('stem', abi.new_op(abi.OP_STEM, x=_flat(BUF_RGB, 0), x2=_flat(BUF_NIR, 0), w=_flat(BUF_BLOB, w_off),
                                       scale=_flat(BUF_BLOB, sc_off), bias=_flat(BUF_BLOB, b_off), y=x.view(), n_img=N2,
                                       group_imgs=B, Hi=H, Wi=W, Ho=h1, Wo=w1, Cout=bc, Cin=3, ksize=3, stride=1,
-                                      BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad,
+                                      BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=packed[0].numel(), sb_gstride=c0pad,
                                       flags=(abi.STEM_FLAG_U8 if self.input_u8 else 0) |
                                       (abi.STEM_FLAG_X2_PLANE if self.depth_plane else 0)))
         self.conv_flops += 2 * N2 * H * W * bc * 27

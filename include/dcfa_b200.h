@@ -126,12 +126,13 @@ typedef struct dcfa_view {
 /*
  * One op of the flat execution plan.  Field use per kind:
  *
- * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 [G][3][2][128*16]: per group,
- *        kernel row ky and pixel parity e one K-major tile in the canonical NO-SWIZZLE layout (element (m,k) at
- *        (m/8)*128 + (k/8)*64 + (m%8)*8 + k%8) whose 128 rows are the Cout channels repeated with period BN (= Cout
- *        rounded up to 32/64/128), K = (kx+e)*4 + ci (four consecutive pixels x 4 channel slots; unused slots zero),
- *        rows of channels with a negative BN scale negated; w_gstride = 6*128*16;
- *        scale (>= 0), bias = fp32 [G][BN]; y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise.
+ * STEM   x,x2 = fp32 NCHW inputs of group 0 / group 1 [group_imgs,3,Hi,Wi]; w = bf16 [G][nblk][3][128*16]: per group,
+ *        64-channel block (nblk = max(1, BN/64)) and kernel row ky one K-major tile in the canonical NO-SWIZZLE layout
+ *        (element (m,k) at (m/8)*128 + (k/8)*64 + (m%8)*8 + k%8).  Row m = 32*q + 16*e + cl: e = 0 rows carry the weights
+ *        for EVEN conv columns (K = kx*4 + ci: four consecutive pixels x 4 channel slots, unused slots zero), e = 1 rows
+ *        those for ODD conv columns (K = (kx+1)*4 + ci); row slot j = 16*q + cl holds channel 64*blk + j % min(BN, 64),
+ *        BN = Cout rounded up to 32/64/128; rows of channels with a negative BN scale are negated; w_gstride = nblk*3*128*16;
+ *        scale (>= 0), bias = fp32 [G][BN]; y = bf16 NHWC [n_img,Ho,Wo,Cout], Ho = (Hi-1)/2+1, Wo likewise; Cout % 8 == 0.
  *        With flags & DCFA_STEM_FLAG_U8: x,x2 = uint8 NHWC [group_imgs,Hi,Wi,3] (x2 a single plane [group_imgs,Hi,Wi]
  *        with DCFA_STEM_FLAG_X2_PLANE), scale already divided by 255.
  * CONV   x = bf16 NHWC input view (Cin channels starting at the view's offset); w = bf16 packed

@@ -80,7 +80,7 @@ def run_ops(ops, bufs):
         gi = n // G
         if k == 1:  # STEM: bf16 inputs and weights, fp32 accumulate, fp32 scale/bias, ReLU, pool, bf16 store
             c0 = op.Cout
-            # weight tiles [G][3][2][128 x 16] in the canonical no-swizzle K-major layout (pack.pack_stem); sign-folded
+            # weight tiles [G][nblk][3][128 x 16] in the canonical no-swizzle K-major layout (pack.pack_stem); sign-folded
             from dcfa_b200 import pack as _pack
             wraw = bufs[op.w.buf][op.w.off:op.w.off + 2 * G * op.w_gstride].view(torch.bfloat16).view(G, -1)
             sc = _f32(bufs[op.scale.buf], op.scale.off, G * op.sb_gstride).view(G, -1)

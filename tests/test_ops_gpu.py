@@ -200,7 +200,7 @@ def test_stem(cuda, b, h, w, c0, groups):
     bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
     op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
                     bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
-                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad)
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=packed[0].numel(), sb_gstride=c0pad)
     _run([op], bufs)
     bs = [bs[i] for i in range(groups)]
     ws = [ws[i] * 1.0 for i in range(groups)]
@@ -232,7 +232,7 @@ def test_stem_uint8_depth_plane(cuda, b, h, w, c0):
         bufs = [rgb.to(cuda), x2.to(cuda), wk, bk, y, sk]
         op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1), w=flat_view(2), bias=flat_view(3), scale=flat_view(5),
                         y=nhwc_view(y, 4), n_img=2 * b, group_imgs=b, Hi=h, Wi=w, Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1,
-                        k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad, flags=abi.STEM_FLAG_U8 | flag)
+                        k_blocks=1, K_real=27, w_gstride=packed[0].numel(), sb_gstride=c0pad, flags=abi.STEM_FLAG_U8 | flag)
         _run([op], bufs)
         outs.append(y.cpu())
     assert torch.equal(outs[0], outs[1])
@@ -263,7 +263,7 @@ def test_stem_uint8_nhwc(cuda, b, h, w, c0, groups):
     bufs = [xg[0], xg[1] if groups == 2 else None, wk, bk, y, sk]
     op = abi.new_op(abi.OP_STEM, x=flat_view(0), x2=flat_view(1) if groups == 2 else abi.no_view(), w=flat_view(2),
                     bias=flat_view(3), scale=flat_view(5), y=nhwc_view(y, 4), n_img=groups * b, group_imgs=b, Hi=h, Wi=w,
-                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=pack.STEM_W_ELEMS, sb_gstride=c0pad,
+                    Ho=ho, Wo=wo, Cout=c0, BN=c0pad, n_tiles=1, k_blocks=1, K_real=27, w_gstride=packed[0].numel(), sb_gstride=c0pad,
                     flags=abi.STEM_FLAG_U8)
     _run([op], bufs)
     ref = torch.cat([F.max_pool2d(F.relu(F.conv2d(xs[i].permute(0, 3, 1, 2).float() / 255.0, ws[i], None, 1, 1)
