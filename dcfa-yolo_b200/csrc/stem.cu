@@ -60,7 +60,8 @@ constexpr int RAW_U8_BYTES = RAWB * PH;       // 1408
 constexpr int RAW1B = 48;                     // uint8 single plane raw row bytes: 14 + 28 = 42, rounded to 16
 constexpr int RAW_C1_BYTES = RAW1B * PH;      // 528
 constexpr int RAW_SLOT = 4224;                // bytes per raw ring slot (multiple of 128)
-constexpr int NRAW = 4;                       // raw ring depth = converter warps (warp w owns slot w)
+constexpr int NRAW = 8;                       // raw ring depth: the TMA producer runs 8 tiles ahead (34 KB in flight per SM --
+                                              // with 4 the input stream sat near 1 TB/s: bytes in flight = bandwidth x latency)
 constexpr int CVT_SLOT = 2560;                // bf16 [11][28][4] = 2464 + the rows the last MMA over-reads (columns 126, 127)
 constexpr int NCVT = 4;                       // converted-patch ring depth = converter warps
 constexpr int A_TILE_BYTES = 128 * 16 * 2;    // one kernel row's weight tile (both parities stacked on the rows)
@@ -73,7 +74,8 @@ constexpr int kEpiWarps = 16, kCvtWarps = 4;
 constexpr int kCvtWarp0 = kEpiWarps, kTmaWarp = kEpiWarps + kCvtWarps, kMmaWarp = kTmaWarp + 1;
 constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
 constexpr uint32_t kTmemCols = 512;
-static_assert(NRAW == kCvtWarps && NCVT == kCvtWarps, "converter warp w owns raw slot w and converted slot w");
+static_assert(NCVT == kCvtWarps && NRAW % kCvtWarps == 0 && (NRAW & (NRAW - 1)) == 0,
+              "converter warp w owns converted slot w and the raw slots w, w + 4, ...");
 static_assert(2 * PP * 8 + (NCOL - 1) * 16 + 32 <= CVT_SLOT, "MMA over-read must stay inside the slot");
 static_assert((CH - 1) * HP + TPW + 1 <= NCOL, "tile does not fit the accumulator");
 
@@ -336,12 +338,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
   } else if (warp >= kCvtWarp0) {
     // ------------------------------------------------------------------ converters: raw patch -> bf16 [y][x][4]
-    // Converter warp w owns this CTA's tiles w, w + 4, ..., raw slot w and converted slot w.
+    // Converter warp w owns this CTA's tiles w, w + 4, ... and converted slot w; tile i arrives in raw slot i % NRAW.
     const int cw = warp - kCvtWarp0;
     const bool tma_in = p.use_tma && !(p.dbg & 2);
-    const uint8_t* raw = raw_ptr + cw * RAW_SLOT;
     uint8_t* cvt = cvt_ptr + cw * CVT_SLOT;
-    const uint32_t b_raw_full = bar_raw_full + 8u * cw, b_raw_empty = bar_raw_empty + 8u * cw;
     const uint32_t b_cvt_full = bar_cvt_full + 8u * cw, b_cvt_empty = bar_cvt_empty + 8u * cw;
     // tile-invariant item geometry of this lane.  fp32: item = (patch row r, pixel pair q), 154 items = 5 per lane;
     // uint8: item = (patch row r, 4 pixels q), 77 items = 3 per lane
@@ -356,8 +356,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
     uint32_t ph = 0;
     for (uint32_t i = (uint32_t)cw; i < n_tiles; i += kCvtWarps, ph ^= 1u) {
+      const uint32_t rs = i & (NRAW - 1), rph = (i / NRAW) & 1u;   // raw slot of tile i and its use parity
+      const uint8_t* raw = raw_ptr + rs * RAW_SLOT;
+      const uint32_t b_raw_full = bar_raw_full + 8u * rs, b_raw_empty = bar_raw_empty + 8u * rs;
       wait_bar(b_cvt_empty, ph ^ 1u);
-      if (tma_in) wait_bar(b_raw_full, ph);
+      if (tma_in) wait_bar(b_raw_full, rph);
       if (MODE == MODE_F32 && p.use_tma) {
         // three 64-bit loads (one per channel plane) and one 128-bit store per item; all loads of the lane's items are
         // issued before the first convert (independent chains)
