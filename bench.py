@@ -291,21 +291,12 @@ def algorithmic_bytes(kind, op, cnt_ops, batch, plan, fp32_input=True, extra_res
     return 0
 
 
-def profile_ops(net, batch, size, device, iters=5):
-    """Per-op CUDA-event timings of the forward plan (one dcfa_run_ops call per op)."""
-    import ctypes as C
-    from dcfa_b200 import _lib, abi
-    from dcfa_b200 import plan as P
-    eng = net._engine(batch, size, size, device)
-    rgb = torch.rand(batch, 3, size, size, device=device)
-    nir = torch.rand(batch, 3, size, size, device=device)
-    eng.run(rgb, nir)
-    torch.cuda.synchronize()
-    st = torch.cuda.current_stream(device)
-    # Records the dispatcher runs as ONE kernel are timed together: the four records of a CBAM, and a 1x1 conv ->
-    # depthwise -> 1x1 conv chain the plan marked as private (if the shape falls back to separate kernels the group
-    # is still what one dcfa_run_ops call executes).
-    ops, names = eng.plan.ops, eng.plan.op_names
+def plan_units(plan):
+    """(first op, op count, kind, name) of every unit the dispatcher runs from ONE dcfa_run_ops call: the four records
+    of a CBAM, a 1x1 conv -> depthwise -> 1x1 conv chain the plan marked as private, a RepGhost 1x1 -> depthwise pair
+    (if the shape falls back to separate kernels the unit is still what one call executes), else the single op."""
+    from dcfa_b200 import abi
+    ops, names = plan.ops, plan.op_names
     groups, i = [], 0
     while i < len(ops):
         k = ops[i].kind
@@ -324,6 +315,22 @@ def profile_ops(net, batch, size, device, iters=5):
         else:
             groups.append((i, 1, abi.OP_NAMES[k], names[i]))
             i += 1
+    return groups
+
+
+def profile_ops(net, batch, size, device, iters=5):
+    """Per-op CUDA-event timings of the forward plan (one dcfa_run_ops call per op)."""
+    import ctypes as C
+    from dcfa_b200 import _lib, abi
+    from dcfa_b200 import plan as P
+    eng = net._engine(batch, size, size, device)
+    rgb = torch.rand(batch, 3, size, size, device=device)
+    nir = torch.rand(batch, 3, size, size, device=device)
+    eng.run(rgb, nir)
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream(device)
+    ops = eng.plan.ops
+    groups = plan_units(eng.plan)
     n = len(groups)
     arrays = [(abi.Op * cnt)(*ops[i0:i0 + cnt]) for (i0, cnt, _, _) in groups]
     tot = np.zeros(n)

@@ -69,7 +69,6 @@ constexpr int A_GROUP_BYTES = 3 * A_TILE_BYTES;
 constexpr int HW6 = TPW / 2;                   // pooled pixels one lane finishes per tile row
 constexpr int OUT_SLAB = 2 * TPW * 16 * 2;    // 768: two pooled rows of a warp, [2][12 pixels][16 channels] bf16
 constexpr int NACC = 4;                       // TMEM accumulator stages (128 columns each)
-constexpr int XCH_BYTES = 0;
 constexpr int kEpiWarps = 16, kCvtWarps = 4;
 constexpr int kCvtWarp0 = kEpiWarps, kTmaWarp = kEpiWarps + kCvtWarps, kMmaWarp = kTmaWarp + 1;
 constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
@@ -216,13 +215,12 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: A weight tiles (2 groups x 24 KB) | raw ring | converted ring | output slabs (8 warps x 2) | barriers | tmem slot
+  // layout: A weight tiles (2 groups x 24 KB) | raw ring | converted ring | output slabs (16 warps x 2) | barriers | tmem slot
   const uint32_t s_a = base;
   const uint32_t s_raw = s_a + 2u * A_GROUP_BYTES;
   const uint32_t s_cvt = s_raw + (uint32_t)(NRAW * RAW_SLOT);
   const uint32_t s_out = s_cvt + (uint32_t)(NCVT * CVT_SLOT);
-  const uint32_t s_xch = s_out + (uint32_t)(kEpiWarps * 2 * OUT_SLAB);
-  const uint32_t bars = s_xch + (uint32_t)(4 * XCH_BYTES);
+  const uint32_t bars = s_out + (uint32_t)(kEpiWarps * 2 * OUT_SLAB);
   const uint32_t bar_raw_full = bars, bar_raw_empty = bars + 8u * NRAW;
   const uint32_t bar_cvt_full = bars + 16u * NRAW, bar_cvt_empty = bar_cvt_full + 8u * NCVT;
   const uint32_t bar_tm_full = bar_cvt_empty + 8u * NCVT, bar_tm_empty = bar_tm_full + 8u * NACC;
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   uint8_t* raw_ptr = gbase + 2 * A_GROUP_BYTES;
   uint8_t* cvt_ptr = raw_ptr + NRAW * RAW_SLOT;
   uint8_t* out_ptr = cvt_ptr + NCVT * CVT_SLOT;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(out_ptr + kEpiWarps * 2 * OUT_SLAB + 4 * XCH_BYTES + (tmem_slot - bars));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(out_ptr + kEpiWarps * 2 * OUT_SLAB + (tmem_slot - bars));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == kMmaWarp) {
@@ -726,7 +724,7 @@ int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "stem: cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
   }
-  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + kEpiWarps * 2 * OUT_SLAB + 4 * XCH_BYTES + 256;
+  const size_t smem = 1024 + 2 * A_GROUP_BYTES + NRAW * RAW_SLOT + NCVT * CVT_SLOT + kEpiWarps * 2 * OUT_SLAB + 256;
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(stem_kernel<MODE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -68,7 +68,7 @@ def _flat(buf, off):
 
 
 class Plan:
-    def __init__(self, sd, phi, num_classes, batch, height, width, input_u8=False, depth_plane=False):
+    def __init__(self, sd, phi, num_classes, batch, height, width, input_u8=False, depth_plane=False, reuse_arena=True):
         """input_u8: the two inputs are uint8 NHWC images [B,H,W,3] (pre-`preprocess_input`, utils/utils.py:76-79)
         instead of fp32 NCHW tensors in [0,1]; the stem folds the /255.  depth_plane (with input_u8): the second input
         is the single uint8 plane [B,H,W] that cvtColor would replicate to three channels (utils/utils.py:14-19)."""
@@ -81,8 +81,12 @@ class Plan:
         self.ops = []
         self.op_names = []
         self.arena_bytes = 0
+        self._allocs = []    # (bump offset, bytes) of every arena allocation, in program order
         self.conv_flops = 0  # 2*MAC over every convolution, per forward of this batch
         self._build()
+        self.arena_bytes_bump = self.arena_bytes
+        if reuse_arena:
+            self._assign_arena_by_liveness()
         self.blob_tensor = self.blob.finish()
         self.op_array = (abi.Op * len(self.ops))(*self.ops)
         del self.sd
@@ -114,7 +118,55 @@ class Plan:
     def _alloc_bytes(self, nbytes):
         off = (self.arena_bytes + 255) // 256 * 256
         self.arena_bytes = off + nbytes
+        self._allocs.append((off, nbytes))
         return off
+
+    _VIEW_FIELDS = ("x", "x2", "y", "w", "scale", "bias", "a0", "a1", "a2")
+    # The library may run up to 4 consecutive ops as ONE kernel (a CBAM, a ShuffleNet branch, a RepGhost module); that
+    # kernel reads the first op's input while it writes the last op's output, so a tensor stays reserved this many ops
+    # past its last reference.
+    _FUSION_SPAN = 3
+
+    def _assign_arena_by_liveness(self):
+        """Replace the bump offsets by addresses shared between tensors whose lifetimes (first .. last op that
+        references them) do not overlap: the arena shrinks ~3x and a consumer's output lands on lines a dead tensor
+        left in L2.  Offsets inside the op list are patched in place; the op list stays relocatable."""
+        import bisect
+        starts = [a[0] for a in self._allocs]
+        first = [None] * len(starts)
+        last = [None] * len(starts)
+        refs = []                                   # (op, field, allocation index)
+        for i, op in enumerate(self.ops):
+            for f in self._VIEW_FIELDS:
+                v = getattr(op, f)
+                if v.buf != BUF_ARENA:
+                    continue
+                a = bisect.bisect_right(starts, v.off) - 1
+                assert a >= 0 and v.off < starts[a] + max(self._allocs[a][1], 1), (self.op_names[i], f)
+                refs.append((op, f, a))
+                first[a] = i if first[a] is None else first[a]
+                last[a] = i
+        placed = []                                 # (new offset, bytes, first, last)
+        new_off = [0] * len(starts)
+        total = 0
+        order = sorted((a for a in range(len(starts)) if first[a] is not None), key=lambda a: (first[a], -self._allocs[a][1]))
+        for a in order:
+            nbytes = (self._allocs[a][1] + 255) // 256 * 256
+            lo, hi = first[a], last[a] + self._FUSION_SPAN
+            busy = sorted((o, o + b) for (o, b, f0, l0) in placed if not (l0 < lo or f0 > hi))
+            off = 0
+            for (o, e) in busy:                     # first fit among the tensors alive at the same time
+                if off + nbytes <= o:
+                    break
+                off = max(off, e)
+            placed.append((off, nbytes, lo, hi))
+            new_off[a] = off
+            total = max(total, off + nbytes)
+        for (op, f, a) in refs:
+            v = getattr(op, f)
+            v.off = v.off - starts[a] + new_off[a]
+            setattr(op, f, v)
+        self.arena_bytes = total
 
     def _tensor(self, n, h, w, c, gi=0):
         off = self._alloc_bytes(n * h * w * c * 2)
