@@ -280,6 +280,8 @@ def algorithmic_bytes(kind, op, cnt_ops, batch, plan, fp32_input=True, extra_res
         return n * hw_in * op.Cin * 2 * (3 if op.x2.buf >= 0 else 2)
     if kind in ("cbam", "maxpool5", "chain"):
         return 2 * n * hw_in * op.Cin * 2
+    if kind == "sppf":    # the input once, the four concat slots once (pooled intermediates never leave the SM)
+        return 5 * n * hw_in * op.Cin * 2
     if kind == "ghost":   # module input + output (+ the bottleneck's residual on the second module)
         return n * hw_in * op.Cin * 2 * (3 if extra_res else 2)
     if kind == "upsample":
@@ -298,9 +300,16 @@ def plan_units(plan):
     from dcfa_b200 import abi
     ops, names = plan.ops, plan.op_names
     groups, i = [], 0
+    def is_cbam(j):
+        return j + 3 < len(ops) and [o.kind for o in ops[j:j + 4]] == [abi.OP_CBAM_POOL, abi.OP_CBAM_MLP, abi.OP_CBAM_STATS,
+                                                                       abi.OP_CBAM_APPLY]
     while i < len(ops):
         k = ops[i].kind
-        if (k == abi.OP_CBAM_POOL and i + 3 < len(ops) and
+        if (is_cbam(i) and i + 19 <= len(ops) and
+                all(ops[i + 5 * s - 1].kind == abi.OP_MAXPOOL5 and is_cbam(i + 5 * s) for s in (1, 2, 3))):
+            groups.append((i, 19, "sppf", names[i].rsplit(".", 1)[0].rsplit(".", 1)[0] + ".attn"))   # SPPF_CBAM: CBAM, (pool, CBAM) x 3
+            i += 19
+        elif (k == abi.OP_CBAM_POOL and i + 3 < len(ops) and
                 [o.kind for o in ops[i + 1:i + 4]] == [abi.OP_CBAM_MLP, abi.OP_CBAM_STATS, abi.OP_CBAM_APPLY]):
             groups.append((i, 4, "cbam", names[i].rsplit(".", 1)[0]))
             i += 4

@@ -119,8 +119,21 @@ bool views_ok(const dcfa_op& o, void* const* bufs, int nbufs) {
 }
 
 // Number of consecutive records the dispatcher treats as one unit at index i (the fusion candidates), 1 otherwise.
+bool is_cbam(const dcfa_op* ops, int i, int n_ops) {
+  return i + 3 < n_ops && ops[i].kind == DCFA_OP_CBAM_POOL && ops[i + 1].kind == DCFA_OP_CBAM_MLP &&
+         ops[i + 2].kind == DCFA_OP_CBAM_STATS && ops[i + 3].kind == DCFA_OP_CBAM_APPLY;
+}
+
+constexpr int kSppfSpan = 19;   // CBAM, (MAXPOOL5, CBAM) x 3: SPPF_CBAM's attention / pooling sequence
+
 int unit_span(const dcfa_op* ops, int i, int n_ops) {
   const dcfa_op& op = ops[i];
+  if (is_cbam(ops, i, n_ops) && i + kSppfSpan <= n_ops) {
+    bool sppf = true;
+    for (int s = 1; s < 4 && sppf; ++s)
+      sppf = ops[i + 5 * s - 1].kind == DCFA_OP_MAXPOOL5 && is_cbam(ops, i + 5 * s, n_ops);
+    if (sppf) return kSppfSpan;
+  }
   if (op.kind == DCFA_OP_CBAM_POOL && i + 3 < n_ops && ops[i + 1].kind == DCFA_OP_CBAM_MLP &&
       ops[i + 2].kind == DCFA_OP_CBAM_STATS && ops[i + 3].kind == DCFA_OP_CBAM_APPLY)
     return 4;
@@ -161,6 +174,24 @@ int dispatch_unit(const dcfa_op* ops, int i, int span, void* const* bufs, int nb
   for (int j = 0; j < span; ++j)
     if (!views_ok(ops[i + j], bufs, nbufs))
       return fail(DCFA_E_INVALID, "run_ops: op %d (kind %d) references a missing buffer (nbufs %d)", i + j, ops[i + j].kind, nbufs);
+  if (span == kSppfSpan) {
+    const int rc = launch_sppf_fused(ops + i, bufs, st);
+    if (rc < 0) {
+      char tmp[400];
+      snprintf(tmp, sizeof(tmp), "%s", dcfa_last_error());
+      return fail(rc, "op %d (fused SPPF_CBAM): %s", i, tmp);
+    }
+    if (rc == 1) return DCFA_OK;
+    for (int s = 0; s < 4; ++s) {   // its units one by one
+      if (s > 0) {
+        const int r1 = dispatch_unit(ops, i + 5 * s - 1, 1, bufs, nbufs, st);
+        if (r1 != DCFA_OK) return r1;
+      }
+      const int r4 = dispatch_unit(ops, i + 5 * s, 4, bufs, nbufs, st);
+      if (r4 != DCFA_OK) return r4;
+    }
+    return DCFA_OK;
+  }
   if (span == 4) {
     const int rc = launch_cbam_fused(ops[i], ops[i + 1], ops[i + 2], ops[i + 3], bufs, st);
     if (rc < 0) {
@@ -242,8 +273,8 @@ bool unit_pointers_changed(const dcfa_plan& p, const dcfa_plan::Unit& u, void* c
 }
 
 int prepare_unit(dcfa_plan& p, dcfa_plan::Unit& u, void* const* bufs) {
-  LaunchRecord tmp[8];
-  Recorder rec{tmp, 8, 0, false};
+  LaunchRecord tmp[24];   // the largest unit (SPPF_CBAM, 19 records) run as separate kernels
+  Recorder rec{tmp, 24, 0, false};
   recorder() = &rec;
   const int rc = dispatch_unit(p.ops.data(), u.first, u.span, bufs, (int)p.bound.size(), nullptr);
   recorder() = nullptr;

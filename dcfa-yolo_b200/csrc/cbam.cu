@@ -9,6 +9,7 @@
 // result is deterministic.
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <cstdio>
 
 #include <algorithm>
 
@@ -583,6 +584,358 @@ __global__ void __launch_bounds__(kFusedThreads) cbam_fused_kernel(const FusedAr
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused SPPF_CBAM
+// SPPF_CBAM (nets/yolo_mul.py:18-31) after its first conv:  x1 = cbam1(t), x2 = cbam2(pool(x1)), x3 = cbam3(pool(x2)),
+// x4 = cbam4(pool(x3)), each written to its slot of the concat buffer.  As separate launches that is 4 fused CBAMs and
+// 3 max-pools on a per-image tensor of a few hundred KB -- seven launches of 14-21 us that are all fill and drain.
+// Here one thread-block cluster per image keeps the image RESIDENT in shared memory for the whole sequence: CTA r owns
+// a band of rows ([rows][W][C] bf16), a stage runs the CBAM phases of cbam_fused_kernel on the band in shared memory
+// (channel sums and the stats halo cross the cluster through DSMEM), stores y = x * gate * s to the stage's concat
+// slot AND back into the band, and the band is then max-pooled 5x5 in place: a horizontal 1x5 pass, the two edge rows
+// of each neighbouring band fetched through DSMEM, a vertical 5x1 pass.  bf16 maxima are exact, so the values equal
+// the separate-kernel path wherever the CBAM sums are associated in the same order.
+constexpr int kSppfStages = 4;
+
+struct SppfArgs {
+  View<const __nv_bfloat16> x;
+  View<__nv_bfloat16> y[kSppfStages];
+  const float* fc1[kSppfStages];   // [G][hidden][C]
+  const float* fc2[kSppfStages];   // [G][C][hidden]
+  const float* w7[kSppfStages];    // [G][2][7][7]
+  int n_img, group_imgs, H, W, C, hidden, rows_per, stages;
+};
+
+__device__ __forceinline__ uint4 bf16x8_max(const uint4& a, const uint4& b) {
+  uint4 r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r.x) : "r"(a.x), "r"(b.x));
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r.y) : "r"(a.y), "r"(b.y));
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r.z) : "r"(a.z), "r"(b.z));
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r.w) : "r"(a.w), "r"(b.w));
+  return r;
+}
+
+// NT threads per CTA: 1024 (one CTA per SM) or 512 (two CTAs per SM: one works while the other waits at a cluster barrier)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) sppf_cbam_kernel(const SppfArgs p) {
+  constexpr int kSppfThreads = NT;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  namespace cg = cooperative_groups;
+  ptx::pdl_launch_dependents();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CS;
+  const int g = n / p.group_imgs;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int C = p.C, W = p.W, rows = p.rows_per;       // H == CS * rows (checked by the launcher)
+  const int c8n = C >> 3;                              // 8, 16 or 32: a pixel's chunks live in one warp
+  const int planes = kSppfThreads / c8n;
+  const int c8 = tid % c8n, plane = tid / c8n;
+  const int y0 = crank * rows, y1 = y0 + rows;
+  const int npix = rows * W;
+  const int SW = W + 6, SR = rows + 6;
+  const int planesA = min(planes, W);                  // phase-A partials live in the halo buffer: W planes of 2 * C floats fit
+  const uint4 neg_inf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  const size_t row_bytes = (size_t)W * C * 2;
+
+  uint8_t* X = s_raw;                                  // [rows][W][C] bf16: the band
+  uint8_t* HALO = X + (size_t)rows * row_bytes;        // [4][W][C] bf16: rows y0-2, y0-1, y1, y1+1 (horizontally pooled)
+  float* part_sum = reinterpret_cast<float*>(HALO + 4 * row_bytes);
+  float* part_max = part_sum + C;
+  float* s_avg = part_max + C;
+  float* s_max = s_avg + C;
+  float* s_gate = s_max + C;
+  float* s_hid = s_gate + C;
+  float* s_w4 = s_hid + ((p.hidden + 3) & ~3);         // [stages][100]: the 7x7 taps of every stage
+  float* s_st = s_w4 + 100 * kSppfStages;              // [SR][SW][2] stats tile, zero border
+  float* s_sig = s_st + SR * SW * 2;                   // [rows * W]
+  float* scratch = reinterpret_cast<float*>(HALO);     // phase A: [planesA][2][C]
+
+#ifdef DCFA_SPPF_TIMING
+  long long ts[96];
+  int nts = 0;
+#define SPPF_TS() do { if (tid == 0 && blockIdx.x == 0 && nts < 96) ts[nts++] = clock64(); } while (0)
+#else
+#define SPPF_TS() do {} while (0)
+#endif
+  // parameters do not depend on the previous kernel: the 7x7 taps of all stages into shared memory, the MLP weights of
+  // all stages pulled into L2 (each stage reads them once, right on its critical path)
+  for (int i = tid; i < 98 * p.stages; i += kSppfThreads) {
+    const int st = i / 98, j = i - st * 98;
+    s_w4[st * 100 + j] = __ldg(p.w7[st] + (int64_t)g * 98 + j);
+  }
+  {
+    const int lines = (C * p.hidden * 4 + 127) / 128;
+    for (int i = tid; i < 2 * p.stages * lines; i += kSppfThreads) {
+      const int st = i / (2 * lines), r = i - st * 2 * lines;
+      const float* w = (r < lines ? p.fc1[st] : p.fc2[st]) + (int64_t)g * C * p.hidden;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(w) + (size_t)(r % lines) * 128));
+    }
+  }
+  ptx::pdl_wait();
+  SPPF_TS();
+  {
+    const __nv_bfloat16* xin = p.x.p + p.x.img_off(n) + (int64_t)y0 * W * p.x.ld + c8 * 8;
+    for (int px = plane; px < npix; px += planes * kU) {   // kU independent 128-bit loads in flight
+      uint4 r[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (px + u * planes < npix) r[u] = ldg128(xin + (int64_t)(px + u * planes) * p.x.ld);
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (px + u * planes < npix) *reinterpret_cast<uint4*>(X + (size_t)(px + u * planes) * C * 2 + c8 * 16) = r[u];
+    }
+  }
+  __syncthreads();
+  SPPF_TS();   // 1: band loaded
+
+  for (int s = 0; s < p.stages; ++s) {
+    // ---- A: channel sums / maxima of the band
+    if (plane < planesA) {
+      float sm[8], mx[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sm[e] = 0.0f; mx[e] = -INFINITY; }
+      for (int px = plane; px < npix; px += planesA) {
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(X + (size_t)px * C * 2 + c8 * 16), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sm[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
+      }
+      float4* ds = reinterpret_cast<float4*>(scratch + (plane * 2 + 0) * C + c8 * 8);
+      float4* dm = reinterpret_cast<float4*>(scratch + (plane * 2 + 1) * C + c8 * 8);
+      ds[0] = make_float4(sm[0], sm[1], sm[2], sm[3]); ds[1] = make_float4(sm[4], sm[5], sm[6], sm[7]);
+      dm[0] = make_float4(mx[0], mx[1], mx[2], mx[3]); dm[1] = make_float4(mx[4], mx[5], mx[6], mx[7]);
+    }
+    SPPF_TS();   // A1 accumulate
+    __syncthreads();
+    SPPF_TS();   // A2 barrier
+    for (int c = tid; c < C; c += kSppfThreads) {
+      float ss = 0.0f, mm = -INFINITY;
+#pragma unroll 4
+      for (int q = 0; q < planesA; ++q) {
+        ss += scratch[(q * 2 + 0) * C + c];
+        mm = fmaxf(mm, scratch[(q * 2 + 1) * C + c]);
+      }
+      part_sum[c] = ss;
+      part_max[c] = mm;
+    }
+    for (int i = tid; i < SR * SW * 2; i += kSppfThreads) s_st[i] = 0.0f;
+    SPPF_TS();   // A done
+    cluster.sync();
+    SPPF_TS();   // cluster sync
+    {
+      const float inv_hw = 1.0f / (float)(p.H * W);
+      for (int c = tid; c < C; c += kSppfThreads) {
+        float ss = 0.0f, mm = -INFINITY;
+        for (int r = 0; r < CS; ++r) {             // fixed order over the cluster: deterministic
+          ss += cluster.map_shared_rank(part_sum, r)[c];
+          mm = fmaxf(mm, cluster.map_shared_rank(part_max, r)[c]);
+        }
+        s_avg[c] = ss * inv_hw;
+        s_max[c] = mm;
+      }
+    }
+    __syncthreads();
+
+    SPPF_TS();   // combine
+    // ---- B: fc1 -> ReLU -> fc2 on both vectors, add, sigmoid
+    {
+      const int warp = tid >> 5, nwarps = kSppfThreads >> 5;
+      for (int h = warp; h < p.hidden; h += nwarps) {
+        const float* w1 = p.fc1[s] + ((int64_t)g * p.hidden + h) * C;
+        float da = 0.0f, dm = 0.0f;
+        float w[8];                                   // C <= 256: all of a lane's weights in flight at once
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (lane + u * 32 < C) w[u] = __ldg(w1 + lane + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (lane + u * 32 < C) {
+            da = fmaf(w[u], s_avg[lane + u * 32], da);
+            dm = fmaf(w[u], s_max[lane + u * 32], dm);
+          }
+        da = warp_sum(da);
+        dm = warp_sum(dm);
+        if (lane == 0) s_hid[h] = fmaxf(da, 0.0f) + fmaxf(dm, 0.0f);
+      }
+      __syncthreads();
+      for (int c = tid; c < C; c += kSppfThreads) {
+        const float* w2 = p.fc2[s] + ((int64_t)g * C + c) * p.hidden;
+        float o = 0.0f;
+        for (int h0 = 0; h0 < p.hidden; h0 += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (h0 + u < p.hidden) w[u] = __ldg(w2 + h0 + u);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (h0 + u < p.hidden) o = fmaf(w[u], s_hid[h0 + u], o);
+        }
+        s_gate[c] = 1.0f / (1.0f + expf(-o));
+      }
+    }
+    __syncthreads();
+    SPPF_TS();   // B (MLP)
+    const float* s_w = s_w4 + s * 100;
+    float g8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g8[e] = s_gate[c8 * 8 + e];
+
+    // ---- C: per-pixel mean / max over channels of x * gate -> interior of the stats tile (shuffles inside a pixel's lanes)
+    {
+      const float inv_c = 1.0f / (float)C;
+      // A thread first forms the partials of up to 8 pixels (its chunk's 8 channels each), then the lanes of a pixel group
+      // reduce them TRANSPOSED: in each of three rounds a lane hands half of its pixels to its partner and keeps the other
+      // half (4 + 2 + 1 shuffles per value instead of 3 x 8), the remaining rounds are plain butterflies on one pixel.
+      constexpr int PI = 8;
+      for (int base = 0; base < npix; base += planes * PI) {
+        float sm[PI], mx[PI];
+#pragma unroll
+        for (int u = 0; u < PI; ++u) {
+          const int px = base + u * planes + plane;
+          sm[u] = 0.0f; mx[u] = -INFINITY;
+          if (px < npix) {
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4*>(X + (size_t)px * C * 2 + c8 * 16), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = v[e] * g8[e];
+              sm[u] += t;
+              mx[u] = fmaxf(mx[u], t);
+            }
+          }
+        }
+        int o = c8n >> 1, sel = 0;
+#pragma unroll
+        for (int half = PI / 2; half >= 1; half >>= 1) {
+          const bool upper = (c8 & o) != 0;
+#pragma unroll
+          for (int u = 0; u < half; ++u) {
+            const float s_send = upper ? sm[u] : sm[u + half], s_keep = upper ? sm[u + half] : sm[u];
+            const float m_send = upper ? mx[u] : mx[u + half], m_keep = upper ? mx[u + half] : mx[u];
+            sm[u] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, o);
+            mx[u] = fmaxf(m_keep, __shfl_xor_sync(0xffffffffu, m_send, o));
+          }
+          if (upper) sel += half;
+          o >>= 1;
+        }
+        for (; o > 0; o >>= 1) {
+          sm[0] += __shfl_xor_sync(0xffffffffu, sm[0], o);
+          mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
+        }
+        const int px = base + sel * planes + plane;
+        if ((c8 & ((c8n >> 3) - 1)) == 0 && px < npix) {
+          const int ry = px / W, rx = px - ry * W;
+          *reinterpret_cast<float2*>(s_st + ((ry + 3) * SW + rx + 3) * 2) = make_float2(sm[0] * inv_c, mx[0]);
+        }
+      }
+    }
+    SPPF_TS();   // C (stats)
+    cluster.sync();
+    // stats halo rows: the last 3 rows of the band above, the first 3 rows of the band below (zero outside the image)
+    for (int i = tid; i < 6 * W; i += kSppfThreads) {
+      const int hr = i / W, rx = i - hr * W;
+      const int gy = hr < 3 ? y0 - 3 + hr : y1 + hr - 3;
+      if (gy >= 0 && gy < p.H) {
+        const int owner = gy / rows;
+        const int ly = gy - owner * rows;
+        const float2 v = *reinterpret_cast<const float2*>(cluster.map_shared_rank(s_st, owner) + ((ly + 3) * SW + rx + 3) * 2);
+        const int dr = hr < 3 ? hr : rows + hr;
+        *reinterpret_cast<float2*>(s_st + (dr * SW + rx + 3) * 2) = v;
+      }
+    }
+    cluster.sync();
+    SPPF_TS();   // stats halo (2 cluster syncs)
+
+    // ---- D: 7x7 conv over (mean, max), sigmoid
+    for (int i = tid; i < npix; i += kSppfThreads) {
+      const int r = i / W, q = i - r * W;
+      float acc = 0.0f;
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float2 sp = *reinterpret_cast<const float2*>(s_st + ((r + ky) * SW + q + kx) * 2);
+          acc = fmaf(s_w[ky * 7 + kx], sp.x, acc);
+          acc = fmaf(s_w[49 + ky * 7 + kx], sp.y, acc);
+        }
+      s_sig[i] = 1.0f / (1.0f + __expf(-acc));
+    }
+    __syncthreads();
+    SPPF_TS();   // D (7x7)
+
+    // ---- E: y = x * gate * s -> the stage's concat slot and, in place, the band
+    {
+      __nv_bfloat16* yout = p.y[s].p + p.y[s].img_off(n) + (int64_t)y0 * W * p.y[s].ld + c8 * 8;
+      for (int px = plane; px < npix; px += planes) {
+        uint4* xp = reinterpret_cast<uint4*>(X + (size_t)px * C * 2 + c8 * 16);
+        float v[8];
+        unpack8(*xp, v);
+        const float sp = s_sig[px];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= g8[e] * sp;
+        const uint4 o = pack8(v);
+        stg128(yout + (int64_t)px * p.y[s].ld, o);
+        *xp = o;
+      }
+    }
+    SPPF_TS();   // E (apply)
+    if (s + 1 == p.stages) break;
+    __syncthreads();
+
+    // ---- 5x5 max-pool of the band, in place: horizontal pass (one thread = one row x one chunk, window in registers)
+    for (int i = tid; i < rows * c8n; i += kSppfThreads) {
+      const int r = i / c8n, cc = i - r * c8n;
+      uint4* rowp = reinterpret_cast<uint4*>(X + (size_t)r * row_bytes + cc * 16);
+      const int pitch = C * 2 / 16;   // uint4 per pixel
+      uint4 a = neg_inf, b = neg_inf, c = rowp[0], d = W > 1 ? rowp[pitch] : neg_inf;
+      for (int x = 0; x < W; ++x) {
+        const uint4 e = x + 2 < W ? rowp[(x + 2) * pitch] : neg_inf;
+        rowp[x * pitch] = bf16x8_max(bf16x8_max(bf16x8_max(a, b), bf16x8_max(c, d)), e);
+        a = b; b = c; c = d; d = e;
+      }
+    }
+    SPPF_TS();   // pool H
+    cluster.sync();
+    // the two edge rows of each neighbouring band (horizontally pooled), -inf outside the image
+    for (int i = tid; i < 4 * W * c8n; i += kSppfThreads) {
+      const int hr = i / (W * c8n), rem = i - hr * (W * c8n);
+      const int gy = hr < 2 ? y0 - 2 + hr : y1 + hr - 2;
+      uint4 v = neg_inf;
+      if (gy >= 0 && gy < p.H) {
+        const int owner = gy / rows, ly = gy - owner * rows;
+        v = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(X, owner) + (size_t)ly * row_bytes + (size_t)rem * 16);
+      }
+      *reinterpret_cast<uint4*>(HALO + (size_t)hr * row_bytes + (size_t)rem * 16) = v;
+    }
+    cluster.sync();   // every neighbour has its copy: the band may be overwritten
+    SPPF_TS();   // pool halo (2 cluster syncs)
+    // vertical pass (one thread = one column x one chunk)
+    for (int i = tid; i < W * c8n; i += kSppfThreads) {
+      const size_t off = (size_t)i * 16;     // (x, chunk) inside a row
+      auto row_at = [&](int r) -> uint4 {    // r in [-2, rows + 2)
+        if (r < 0) return *reinterpret_cast<const uint4*>(HALO + (size_t)(r + 2) * row_bytes + off);
+        if (r >= rows) return *reinterpret_cast<const uint4*>(HALO + (size_t)(r - rows + 2) * row_bytes + off);
+        return *reinterpret_cast<const uint4*>(X + (size_t)r * row_bytes + off);
+      };
+      uint4 a = row_at(-2), b = row_at(-1), c = row_at(0), d = row_at(1);
+      for (int r = 0; r < rows; ++r) {
+        const uint4 e = row_at(r + 2);
+        *reinterpret_cast<uint4*>(X + (size_t)r * row_bytes + off) = bf16x8_max(bf16x8_max(bf16x8_max(a, b), bf16x8_max(c, d)), e);
+        a = b; b = c; c = d; d = e;
+      }
+    }
+    __syncthreads();
+    SPPF_TS();   // pool V
+  }
+#ifdef DCFA_SPPF_TIMING
+  if (tid == 0 && blockIdx.x == 0) {
+    for (int i = 1; i < nts; ++i) printf("%d:%lld ", i, ts[i] - ts[i - 1]);
+    printf("total %lld\n", ts[nts - 1] - ts[0]);
+  }
+#endif
+}
+
 inline bool view_aligned(const void* ptr, int ld, int64_t img_stride, int64_t gstride) {
   return ((uintptr_t)ptr % 16) == 0 && ld % 8 == 0 && img_stride % 8 == 0 && gstride % 8 == 0;
 }
@@ -731,6 +1084,94 @@ int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& st
   }
   cudaError_t le = launch_k(cbam_fused_kernel, dim3((unsigned)(a.n_img * CS)), dim3(kFusedThreads), smem, st, CS, true, a);
   if (le != cudaSuccess) return fail(DCFA_E_CUDA, "cbam_fused: launch (cluster %d, smem %zu): %s", CS, smem, cudaGetErrorString(le));
+  count_launch();
+  return 1;
+}
+
+// The 19 records of SPPF_CBAM's attention / pooling sequence (CBAM x4 with a MAXPOOL5 between consecutive ones, each pool
+// reading the previous CBAM's output): 1 = the resident cluster kernel was launched, 0 = left to the separate units.
+int launch_sppf_fused(const dcfa_op* ops, void* const* bufs, cudaStream_t st) {
+  bool force = false;
+  {
+    const char* e = getenv("DCFA_SPPF_FUSED");   // debug / tests: 0 keeps the seven separate launches, 2 fuses even tiny batches
+    if (e && atoi(e) == 0) return 0;
+    force = e && atoi(e) == 2;
+  }
+  SppfArgs a;
+  a.stages = kSppfStages;
+  const dcfa_op& ap0 = ops[3];
+  a.n_img = ap0.n_img;
+  a.group_imgs = ap0.group_imgs > 0 ? ap0.group_imgs : ap0.n_img;
+  a.H = ap0.Hi; a.W = ap0.Wi; a.C = ap0.Cin; a.hidden = ops[1].hidden;
+  a.x = resolve<const __nv_bfloat16>(ap0.x, bufs);
+  for (int s = 0; s < kSppfStages; ++s) {
+    const dcfa_op* q = ops + 5 * s;   // POOL, MLP, STATS, APPLY of stage s
+    const dcfa_op &pool = q[0], &mlp = q[1], &stats = q[2], &apply = q[3];
+    const int gi = apply.group_imgs > 0 ? apply.group_imgs : apply.n_img;
+    if (pool.n_img != a.n_img || mlp.n_img != a.n_img || stats.n_img != a.n_img || apply.n_img != a.n_img || gi != a.group_imgs ||
+        pool.Cin != a.C || mlp.Cin != a.C || stats.Cin != a.C || apply.Cin != a.C || apply.Hi != a.H || apply.Wi != a.W ||
+        mlp.hidden != a.hidden)
+      return 0;
+    const View<const __nv_bfloat16> xa = resolve<const __nv_bfloat16>(apply.x, bufs), xp = resolve<const __nv_bfloat16>(pool.x, bufs),
+                                    xs = resolve<const __nv_bfloat16>(stats.x, bufs);
+    if (!xa.p || xp.p != xa.p || xs.p != xa.p) return 0;
+    a.y[s] = resolve<__nv_bfloat16>(apply.y, bufs);
+    a.fc1[s] = resolve_ptr<const float>(mlp.w, bufs);
+    a.fc2[s] = resolve_ptr<const float>(mlp.scale, bufs);
+    a.w7[s] = resolve_ptr<const float>(apply.w, bufs);
+    if (!(a.y[s].p && a.fc1[s] && a.fc2[s] && a.w7[s])) return 0;
+    if (!view_aligned(a.y[s].p, a.y[s].ld, a.y[s].img_stride, a.y[s].gstride)) return 0;
+    if (s > 0) {   // the pool between stage s-1 and s: reads stage s-1's output, feeds stage s
+      const dcfa_op& mp = ops[5 * s - 1];
+      const View<const __nv_bfloat16> mx = resolve<const __nv_bfloat16>(mp.x, bufs);
+      const View<__nv_bfloat16> my = resolve<__nv_bfloat16>(mp.y, bufs);
+      if (mp.n_img != a.n_img || mp.Cin != a.C || mp.Hi != a.H || mp.Wi != a.W || mx.p != a.y[s - 1].p || mx.ld != a.y[s - 1].ld ||
+          mx.img_stride != a.y[s - 1].img_stride || my.p != xa.p || my.ld != xa.ld)
+        return 0;
+    }
+  }
+  if (!view_aligned(a.x.p, a.x.ld, a.x.img_stride, a.x.gstride)) return 0;
+  const int c8n = a.C >> 3;
+  if (a.C % 8 != 0 || !(c8n == 8 || c8n == 16 || c8n == 32) || a.hidden < 1 || a.n_img > 65535) return 0;
+  // cluster size: the smallest power of two (<= 8) whose band + pooling halo fit in shared memory, bands of >= 3 rows
+  const size_t row_bytes = (size_t)a.W * a.C * 2;
+  auto smem_for = [&](int cs) {
+    const int rows = a.H / cs;
+    const size_t floats = (size_t)5 * a.C + ((a.hidden + 3) & ~3) + 100 * kSppfStages + (size_t)(rows + 6) * (a.W + 6) * 2 +
+                          ((rows * a.W + 3) & ~3);
+    return (size_t)(rows + 4) * row_bytes + floats * sizeof(float);
+  };
+  int CS = 1;
+  size_t smem = 0;
+  for (;; CS <<= 1) {
+    if (CS > 8 || a.H % CS != 0 || a.H / CS < 3) return 0;
+    smem = smem_for(CS);
+    if (smem <= 200 * 1024 && (force || (int64_t)a.n_img * CS >= sm_count() / 4)) break;
+  }
+  int nt = 1024;
+  {
+    const int cs2 = CS * 2;
+    // experiment (DCFA_SPPF_NT=512): measured 65 us either way at s/B=32 -- the phases are latency chains, not occupancy
+    const char* e = getenv("DCFA_SPPF_NT");
+    const bool allow = e && atoi(e) == 512;
+    if (allow && cs2 <= 8 && a.H % cs2 == 0 && a.H / cs2 >= 3 && smem_for(cs2) <= 100 * 1024 && (int64_t)a.n_img * cs2 <= 2 * sm_count()) {
+      CS = cs2;
+      smem = smem_for(CS);
+      nt = 512;
+    }
+  }
+  a.rows_per = a.H / CS;
+  if ((int64_t)a.n_img * CS > 2 * sm_count()) return 0;
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(sppf_cbam_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sppf_cbam_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return fail(DCFA_E_CUDA, "sppf_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set.mark();
+  }
+  cudaError_t le = nt == 512 ? launch_k(sppf_cbam_kernel<512>, dim3((unsigned)(a.n_img * CS)), dim3(512), smem, st, CS, true, a)
+                             : launch_k(sppf_cbam_kernel<1024>, dim3((unsigned)(a.n_img * CS)), dim3(1024), smem, st, CS, true, a);
+  if (le != cudaSuccess) return fail(DCFA_E_CUDA, "sppf_fused: launch (cluster %d, smem %zu): %s", CS, smem, cudaGetErrorString(le));
   count_launch();
   return 1;
 }

@@ -847,11 +847,14 @@ int launch_chain_impl(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op* pw2p
   const cuuint64_t gstr[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)a.W * x.ld * 2, (cuuint64_t)x.img_stride * 2};
   const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
 
-  // ---- second-generation kernel (depthwise stage on the tensor pipe); DCFA_CHAIN_MMA=0 keeps the first generation
-  bool use_mma = true;
+  // ---- second-generation kernel (depthwise stage on the tensor pipe): opt-in with DCFA_CHAIN_MMA=1.  Measured (s, B=32):
+  //      an M128 x N x K16 MMA costs ~47 cycles for every N <= 64 (tools/umma_nsweep_test.cu), so the 9 (x2 with split
+  //      taps) diagonal MMAs per 16-channel block make the tensor pipe the bottleneck: 0.187 / 0.165 ms against
+  //      0.161 / 0.078 ms for the first generation at C = 32 / 64 (0.133 / 0.083 ms with single-bf16 taps).
+  bool use_mma = false;
   {
     const char* e = getenv("DCFA_CHAIN_MMA");
-    if (e && atoi(e) == 0) use_mma = false;
+    if (e && atoi(e) == 1) use_mma = true;
   }
   if (use_mma) {
     ChainMmaArgs m;

@@ -236,6 +236,7 @@ int launch_cbam_apply(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_cbam_fused(const dcfa_op& pool, const dcfa_op& mlp, const dcfa_op& stats, const dcfa_op& apply, void* const* bufs,
                       cudaStream_t st);
 int launch_maxpool5(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_sppf_fused(const dcfa_op* ops, void* const* bufs, cudaStream_t st);   // 19 records, see cbam.cu
 int launch_upsample(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_dfl(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 

@@ -15,6 +15,11 @@ def _run(ops, bufs):
     torch.cuda.synchronize()
 
 
+def _launches():
+    from dcfa_b200 import _lib
+    return int(_lib.lib.dcfa_launch_count())
+
+
 def _act(v, act):
     from dcfa_b200 import abi
     if act == abi.ACT_RELU:
@@ -301,7 +306,8 @@ def test_dwconv(cuda, n, h, w, c, act, groups, use_res):
 
 @pytest.mark.parametrize("n,h,w,c,groups", [(2, 16, 32, 32, 1), (4, 21, 37, 64, 2), (2, 40, 40, 128, 2), (2, 160, 160, 32, 2),
                                             (1, 8, 16, 64, 1)])
-def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w, c, groups):
+@pytest.mark.parametrize("gen", ["0", "1"])
+def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w, c, groups, gen):
     """1x1 conv + BN + ReLU -> depthwise 3x3 + BN -> 1x1 conv + BN + ReLU (ShuffleNetV2 branch 2, nets/yolo_mul.py:
     138-162): the fused tcgen05 kernel must reproduce the three-kernel path (same bf16 rounding points) and both must
     match torch; the input is a channel sub-view, the output a channel slot of a wider tensor."""
@@ -329,6 +335,7 @@ def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w,
     outs = []
     for fused in ("2", "0"):   # "2": fused even for the shapes the launch heuristic leaves to the three kernels
         monkeypatch.setenv("DCFA_CHAIN", fused)
+        monkeypatch.setenv("DCFA_CHAIN_MMA", gen)   # "1": the second-generation kernel (depthwise stage on the tensor pipe)
         t1 = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
         t2 = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
         y = torch.full((n, h, w, 2 * c), 3.0, dtype=torch.bfloat16, device=cuda)   # output slot: channels [c, 2c)
@@ -350,12 +357,15 @@ def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w,
             assert float(t1.float().abs().max()) == 0.0 and float(t2.float().abs().max()) == 0.0, "fused path not taken"
         assert (y[..., :c] == 3.0).all(), "chain wrote outside its channel slot"
         outs.append(y[..., c:].float().cpu())
-    # The fused kernel runs the depthwise stage on the tensor pipe with each fp32 tap split into two bf16 parts (16 mantissa
-    # bits): its pre-rounding sums differ from the FMA path in the last bits, so a few results land on the other side of a
-    # bf16 rounding boundary.  Everything else is rounded at the same points.
-    _bf16_close(outs[0], outs[1], "fused chain vs three kernels")
-    differing = (outs[0] != outs[1]).float().mean().item()
-    assert differing < 0.02, "fused chain differs from the three-kernel path in %.2f %% of the outputs" % (100 * differing)
+    if gen == "0":   # same bf16 rounding points, same fp32 FMA order: bit-identical
+        assert torch.equal(outs[0], outs[1]), "fused chain differs from the three-kernel path: max %g" % (outs[0] - outs[1]).abs().max()
+    else:
+        # The second-generation kernel runs the depthwise stage on the tensor pipe with each fp32 tap split into two bf16 parts
+        # (16 mantissa bits): its pre-rounding sums differ from the FMA path in the last bits, so a few results land on the
+        # other side of a bf16 rounding boundary.
+        _bf16_close(outs[0], outs[1], "fused chain vs three kernels")
+        differing = (outs[0] != outs[1]).float().mean().item()
+        assert differing < 0.02, "fused chain differs from the three-kernel path in %.2f %% of the outputs" % (100 * differing)
     x = xfull[..., 16:16 + c].permute(0, 3, 1, 2)
     refs = []
     for gg in range(groups):
@@ -368,7 +378,8 @@ def test_shuffle_branch_chain_fused_vs_three_kernels(cuda, monkeypatch, n, h, w,
 
 @pytest.mark.parametrize("n,h,w,c,act,use_res", [(2, 16, 32, 64, 2, False), (3, 21, 37, 64, 0, True), (2, 40, 40, 128, 2, False),
                                                  (2, 40, 40, 128, 0, True), (1, 8, 16, 32, 2, True), (2, 80, 80, 64, 0, True)])
-def test_repghost_module_fused_vs_two_kernels(cuda, monkeypatch, n, h, w, c, act, use_res):
+@pytest.mark.parametrize("gen", ["0", "1"])
+def test_repghost_module_fused_vs_two_kernels(cuda, monkeypatch, n, h, w, c, act, use_res, gen):
     """RepGhostModule in deploy algebra (nets/repghost.py:98-123, :263-279): 1x1 conv + BN (+SiLU) -> depthwise 3x3 (+SiLU)
     (+ residual).  The fused kernel (DCFA_CONV_FLAG_GHOST_HEAD) against the two-kernel path and against torch; input,
     output and residual are channel slots of wider tensors, as in C2f_repghost's concat buffer."""
@@ -386,6 +397,7 @@ def test_repghost_module_fused_vs_two_kernels(cuda, monkeypatch, n, h, w, c, act
     outs = []
     for fused in ("2", "0"):
         monkeypatch.setenv("DCFA_GHOST", fused)
+        monkeypatch.setenv("DCFA_CHAIN_MMA", gen)
         xg = cat.to(torch.bfloat16).to(cuda)
         t1 = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda)
         bufs = [xg, W1, S1, B1, t1, WD, BD]
@@ -465,6 +477,67 @@ def test_cbam_chain(cuda, monkeypatch, b, h, w, c, hidden, groups, fused):
         ref = _cbam_ref(x[gg * b:(gg + 1) * b], fc1[gg], fc2[gg], w7[gg]).permute(0, 2, 3, 1)
         _bf16_close(y[..., slot0 + gg * c: slot0 + (gg + 1) * c].cpu(), ref, "cbam group %d" % gg)
     assert (y[..., :slot0] == 5.0).all()
+
+
+@pytest.mark.parametrize("b,h,w,c,hidden,groups", [(2, 20, 20, 256, 16, 2), (1, 12, 12, 64, 4, 1), (1, 40, 40, 256, 16, 2),
+                                                   (3, 20, 28, 128, 1, 1)])
+def test_sppf_cbam_sequence_fused_vs_separate(cuda, monkeypatch, b, h, w, c, hidden, groups):
+    """SPPF_CBAM after cv1 (nets/yolo_mul.py:18-31): x1 = cbam1(t), x_{k+1} = cbam_{k+1}(maxpool5(x_k)), the four results in the
+    slots of one concat buffer.  The 19 records run (a) as ONE cluster kernel that keeps each image resident in shared memory
+    ("2": forced for these small batches; cluster sizes 2, 1, 8 and 4 occur) and (b) unit by unit ("0"); both against torch."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(77 + c)
+    n = b * groups
+    t = bf16_round(torch.randn(n, c, h, w, generator=g))
+    fc1 = [[torch.randn(hidden, c, 1, 1, generator=g) * 0.2 for _ in range(groups)] for _ in range(4)]
+    fc2 = [[torch.randn(c, hidden, 1, 1, generator=g) * 0.5 for _ in range(groups)] for _ in range(4)]
+    w7 = [[torch.randn(1, 2, 7, 7, generator=g) * 0.2 for _ in range(groups)] for _ in range(4)]
+    tg = t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    parts = 2
+    outs = []
+    for fused in ("2", "0"):
+        monkeypatch.setenv("DCFA_SPPF_FUSED", fused)
+        cat = torch.full((n, h, w, 4 * c + 8), 7.0, dtype=torch.bfloat16, device=cuda)     # slots start at channel 8
+        pooled = [torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=cuda) for _ in range(3)]
+        psum, pmax = torch.zeros(n, parts, c, device=cuda), torch.zeros(n, parts, c, device=cuda)
+        gate, stats = torch.zeros(n, c, device=cuda), torch.zeros(n, h, w, 2, device=cuda)
+        bufs = [tg, cat, psum, pmax, gate, stats] + pooled
+        ops = []
+        common = dict(n_img=n, group_imgs=b, Hi=h, Wi=w, Cin=c, hidden=hidden, parts=parts)
+        for s in range(4):
+            f1 = torch.stack([q.reshape(hidden, c) for q in fc1[s]]).to(cuda)
+            f2 = torch.stack([q.reshape(c, hidden) for q in fc2[s]]).to(cuda)
+            k7 = torch.stack([q.reshape(98) for q in w7[s]]).to(cuda)
+            i0 = len(bufs)
+            bufs += [f1, f2, k7]
+            if s > 0:
+                ops.append(abi.new_op(abi.OP_MAXPOOL5, x=nhwc_view(cat, 1, 8 + (s - 1) * c), y=nhwc_view(pooled[s - 1], 5 + s),
+                                      n_img=n, Hi=h, Wi=w, Cin=c, Ho=h, Wo=w, Cout=c))
+            xin = nhwc_view(tg, 0) if s == 0 else nhwc_view(pooled[s - 1], 5 + s)
+            ops += [
+                abi.new_op(abi.OP_CBAM_POOL, x=xin, a0=flat_view(2), a1=flat_view(3), **common),
+                abi.new_op(abi.OP_CBAM_MLP, a0=flat_view(2), a1=flat_view(3), a2=flat_view(4), w=flat_view(i0), scale=flat_view(i0 + 1),
+                           w_gstride=hidden * c, sb_gstride=hidden * c, **common),
+                abi.new_op(abi.OP_CBAM_STATS, x=xin, a2=flat_view(4), a0=flat_view(5), **common),
+                abi.new_op(abi.OP_CBAM_APPLY, x=xin, a2=flat_view(4), a0=flat_view(5), w=flat_view(i0 + 2),
+                           y=nhwc_view(cat, 1, 8 + s * c), **common),
+            ]
+        assert len(ops) == 19
+        n0 = _launches()
+        _run(ops, bufs)
+        launched = _launches() - n0
+        assert fused == "0" or launched == 1, "fused SPPF_CBAM took %d launches" % launched
+        if fused == "2":
+            assert all(float(q.float().abs().max()) == 0.0 for q in pooled), "fused path not taken"
+        assert (cat[..., :8] == 7.0).all()
+        outs.append(cat[..., 8:].float().cpu())
+    _bf16_close(outs[0], outs[1], "fused SPPF_CBAM vs separate units")
+    x = t
+    for s in range(4):
+        if s > 0:
+            x = F.max_pool2d(x, 5, 1, 2)
+        x = bf16_round(torch.cat([_cbam_ref(x[gg * b:(gg + 1) * b], fc1[s][gg], fc2[s][gg], w7[s][gg]) for gg in range(groups)]))
+        _bf16_close(outs[0][..., s * c:(s + 1) * c], x.permute(0, 2, 3, 1), "SPPF_CBAM stage %d" % s)
 
 
 def test_maxpool5_and_upsample(cuda):
