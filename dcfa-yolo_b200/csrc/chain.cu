@@ -380,362 +380,16 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
 }
 
 
-// =====================================================================================================================
-// Second generation of the same unit: the depthwise 3x3 runs on the TENSOR pipe as well.
-//
-// The first-generation kernel above spends ~60 % of its instructions on the depthwise stage (shared-memory loads, bf16
-// unpacking, 9 taps x C FMAs per pixel) and sits at ~45 % issue utilisation.  Here the CUDA cores only run the
-// epilogues (TMEM -> BN/activation -> bf16), one accumulator row per thread:
-//   * one CTA owns a 12 x 16 pixel tile; its 14 x 18 halo = 252 pixels are the M rows (2 x 128) of GEMM 1;
-//   * epilogue 1 stores the result as CHANNEL PLANES: plane j holds channels 8j..8j+7 of every halo pixel, 16 bytes per
-//     pixel, pixels in halo-linear order.  In the no-swizzle K-major UMMA layout (LBO = plane pitch, SBO = 128 B) this
-//     is an A operand whose row m is pixel (start + m): a spatial tap (dy, dx) is the SAME buffer with the start
-//     address moved by (18 dy + dx) * 16 bytes -- no im2col, no shared-memory traffic from the CUDA cores;
-//   * the depthwise conv = for every 16-channel block, nine accumulating M128 x N16 x K16 MMAs against diagonal
-//     16 x 16 weight tiles (tap weights rounded to bf16 and, DW_HILO, their bf16 residuals in a second MMA, so the
-//     taps carry 16 mantissa bits); output row m' is the pixel whose halo-linear index is m' + 19, two of every
-//     18 rows are halo columns and are discarded;
-//   * ShuffleNet branch: epilogue D (+ bias) writes the planes of GEMM 2's A operand over the dead T1 planes, GEMM 2,
-//     epilogue 2 (BN + ReLU) stores to global memory.  RepGhost module: epilogue D (+ bias, SiLU, + residual) stores
-//     to global memory.
-// One control thread issues every TMA and MMA; the eight epilogue warps and the control thread hand each other the
-// accumulators and the planes through mbarriers; 2-3 CTAs per SM overlap each other's phases.
-// =====================================================================================================================
-constexpr int M_TH = 12, M_TW = 16;              // output tile
-constexpr int M_HH = M_TH + 2, M_HW = M_TW + 2;  // halo 14 x 18
-constexpr int M_NHALO = M_HH * M_HW;             // 252 halo pixels = rows of GEMM 1 (2 x 128)
-constexpr int M_PIX = 296;                       // pixels per plane: 256 rows + the largest tap shift (2 * 18 + 2), rounded up
-constexpr int M_PLANE = M_PIX * 16;              // bytes per 8-channel plane
-constexpr int kMmaEpiWarps = 8;
-constexpr int kMmaThreads = (kMmaEpiWarps + 1) * 32;   // + the control warp
-
-struct ChainMmaArgs {
-  ChainArgs c;
-  uint32_t off_wd, off_t1m;   // diagonal depthwise tiles, channel planes (T1, later the A operand of GEMM 2)
-};
-
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
-}
-
-__device__ __forceinline__ void tmem_ld_x32m(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// v[e] = act(acc[e] + bias[e]) for 16 channels (the depthwise stage: its BN scale is folded into the taps)
-__device__ __forceinline__ void bias_act16(const uint32_t* acc, const float* bi, int act, float* v) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bi + 4 * q);
-    v[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) + b4.x;
-    v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
-    v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z;
-    v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
-  }
-  if (act == DCFA_ACT_RELU) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
-  } else if (act == DCFA_ACT_SILU) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = silu_fast(v[e]);
-  }
-}
-
-// DW_PARTS = diagonal tiles per (16-channel block, tap): bf16(w) [, bf16(w - bf16(w))]
-template <int CT, int DW_PARTS>
-__global__ void __launch_bounds__(kMmaThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 1))
-    chain_mma_kernel(const __grid_constant__ CUtensorMap map_x, const ChainMmaArgs pa) {
-  const ChainArgs& p = pa.c;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gb = smem_raw + (base - ptx::smem_u32(smem_raw));
-  constexpr int C = CT;
-  constexpr int NB16 = C / 16;
-  const uint32_t s_xa = base, s_w1 = base + p.off_w1, s_w2 = base + p.off_w2, s_wd = base + pa.off_wd, s_t1 = base + pa.off_t1m;
-  float* bd_s = reinterpret_cast<float*>(gb + p.off_par);
-  float* s1_s = bd_s + C;
-  float* b1_s = s1_s + C;
-  float* s2_s = b1_s + C;
-  float* b2_s = s2_s + C;
-  const uint32_t bar_x = base + p.off_bar, bar_acc1 = bar_x + 8u, bar_t1 = bar_x + 16u, bar_accd = bar_x + 24u, bar_a2 = bar_x + 32u,
-                 bar_acc2 = bar_x + 40u, tmem_slot = bar_x + 48u;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gb + p.off_bar + 48u);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool ctl = warp == kMmaEpiWarps;
-  if (ctl) {
-    if (lane == 0) {
-      ptx::mbar_init(bar_x, 1);
-      ptx::mbar_init(bar_acc1, 1);
-      ptx::mbar_init(bar_t1, kMmaEpiWarps);
-      ptx::mbar_init(bar_accd, 1);
-      ptx::mbar_init(bar_a2, kMmaEpiWarps);
-      ptx::mbar_init(bar_acc2, 1);
-      ptx::fence_mbar_init();
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
-    }
-    __syncwarp();
-    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-    ptx::tmem_relinquish();
-  }
-  ptx::pdl_launch_dependents();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tm_acc1 = tmem_base, tm_accd = tmem_base + 2u * C;   // [mb * C + channel]; GEMM 2 reuses the accD columns
-  ptx::pdl_wait();
-
-  const uint32_t idesc_c = ptx::make_idesc_bf16_f32(128, C), idesc_16 = ptx::make_idesc_bf16_f32(128, 16);
-  const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(p.sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)p.layout_type << 61);
-  const int tiles_img = p.tiles_x * p.tiles_y;
-  const int total = p.n_img * tiles_img;
-  const int ksteps = p.bk >> 4;
-  const uint32_t xa_atom = 256u * p.row_bytes, w_atom = (uint32_t)C * p.row_bytes;
-
-  auto issue_x = [&](int tile) {   // control thread: the halo box(es) of `tile`
-    const int n = tile / tiles_img;
-    const int r = tile - n * tiles_img;
-    const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-    ptx::mbar_arrive_expect_tx(bar_x, (uint32_t)p.katoms * M_NHALO * p.row_bytes);
-    for (int ka = 0; ka < p.katoms; ++ka)
-      chain_tma_load(s_xa + (uint32_t)ka * xa_atom, &map_x, ka * p.bk, tx * M_TW - 1, ty * M_TH - 1, n, bar_x);
-  };
-
-  // per-thread constants of the epilogue roles: thread <-> accumulator row (TMEM lane quarter = warp % 4)
-  const int mb = (warp >> 2) & 1, q4 = warp & 3;
-  const int row = mb * 128 + q4 * 32 + lane;                 // GEMM-1 row = halo-linear pixel; GEMM-dw / GEMM-2 row m'
-  const int hy = row / M_HW, hx = row - hy * M_HW;           // as a halo pixel
-  const int oy_t = row / M_HW, ox_t = row - oy_t * M_HW;     // as an output row: pixel (oy_t, ox_t) of the tile if ox_t < 16
-  const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-
-  int tile = blockIdx.x;
-  if (ctl && lane == 0 && tile < total) issue_x(tile);
-  int cur_g = -1;
-  uint32_t ph = 0;
-  for (; tile < total; tile += gridDim.x, ph ^= 1u) {
-    const int n = tile / tiles_img;
-    const int trem = tile - n * tiles_img;
-    const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-    int g = 0;
-    for (int nn = n; nn >= p.group_imgs; nn -= p.group_imgs) ++g;
-    if (g != cur_g) {   // this modality's weights (every MMA of the previous tile has completed: its epilogues waited for them)
-      __syncthreads();
-      const uint4* src1 = reinterpret_cast<const uint4*>(p.w1 + (int64_t)g * p.w1_gstride);
-      const uint4* src2 = reinterpret_cast<const uint4*>(p.w2 + (int64_t)g * p.w2_gstride);
-      uint4* d1 = reinterpret_cast<uint4*>(gb + p.off_w1);
-      uint4* d2 = reinterpret_cast<uint4*>(gb + p.off_w2);
-      uint4* dd = reinterpret_cast<uint4*>(gb + pa.off_wd);
-      const int n16 = C * C * 2 / 16;
-      for (int i = tid; i < n16; i += kMmaThreads) d1[i] = __ldg(src1 + i);
-      if (!p.ghost)
-        for (int i = tid; i < n16; i += kMmaThreads) d2[i] = __ldg(src2 + i);
-      for (int i = tid; i < NB16 * 9 * DW_PARTS * 32; i += kMmaThreads) dd[i] = make_uint4(0u, 0u, 0u, 0u);
-      for (int i = tid; i < C; i += kMmaThreads) {
-        bd_s[i] = __ldg(p.bd + (int64_t)g * C + i);
-        s1_s[i] = __ldg(p.s1 + (int64_t)g * p.sb1_gstride + i);
-        b1_s[i] = __ldg(p.b1 + (int64_t)g * p.sb1_gstride + i);
-        if (!p.ghost) {
-          s2_s[i] = __ldg(p.s2 + (int64_t)g * p.sb2_gstride + i);
-          b2_s[i] = __ldg(p.b2 + (int64_t)g * p.sb2_gstride + i);
-        }
-      }
-      __syncthreads();
-      // diagonal tiles: element (n, k) of a canonical no-swizzle 16 x 16 tile at (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
-      for (int i = tid; i < 9 * C; i += kMmaThreads) {
-        const int t = i / C, c = i - t * C;
-        const float w = __ldg(p.wd + (int64_t)g * 9 * C + i);
-        const __nv_bfloat16 hi = __float2bfloat16(w);
-        const int d = c & 15;
-        uint8_t* tp = gb + pa.off_wd + (size_t)(((c >> 4) * 9 + t) * DW_PARTS) * 512 + (d >> 3) * 384 + (d & 7) * 18;
-        *reinterpret_cast<__nv_bfloat16*>(tp) = hi;
-        if (DW_PARTS == 2) *reinterpret_cast<__nv_bfloat16*>(tp + 512) = __float2bfloat16(w - __bfloat162float(hi));
-      }
-      ptx::fence_proxy_async_smem();
-      cur_g = g;
-      __syncthreads();
-    }
-
-    if (ctl) {
-      if (lane == 0) {
-        // ---- GEMM 1: [256 halo rows, C] x W1^T -> acc1
-        ptx::mbar_wait(bar_x, ph);
-        ptx::tc_fence_after();
-        for (int m2 = 0; m2 < 2; ++m2)
-          for (int ka = 0; ka < p.katoms; ++ka)
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t a_addr = s_xa + (uint32_t)ka * xa_atom + (uint32_t)m2 * 128u * p.row_bytes + (uint32_t)k * 32u;
-              const uint32_t b_addr = s_w1 + (uint32_t)ka * w_atom + (uint32_t)k * 32u;
-              ptx::umma_bf16(tm_acc1 + (uint32_t)(m2 * C), desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4),
-                             desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4), idesc_c, (ka | k) ? 1u : 0u);
-            }
-        ptx::umma_commit(bar_acc1);
-        ptx::mbar_wait(bar_acc1, ph);          // the halo tile has been consumed: request the next one
-        const int nxt = tile + (int)gridDim.x;
-        if (nxt < total) issue_x(nxt);
-        // ---- depthwise 3x3: per 16-channel block, 9 (x DW_PARTS) diagonal MMAs over shifted views of the T1 planes
-        ptx::mbar_wait(bar_t1, ph);
-        ptx::tc_fence_after();
-        for (int m2 = 0; m2 < 2; ++m2)
-          for (int j = 0; j < NB16; ++j)
-            for (int t = 0; t < 9; ++t) {
-              const int shift = (t / 3) * M_HW + (t % 3);
-              const uint64_t ad = desc_nosw(s_t1 + (uint32_t)(2 * j) * M_PLANE + (uint32_t)(m2 * 128 + shift) * 16u, M_PLANE, 128u);
-              for (int h = 0; h < DW_PARTS; ++h)
-                ptx::umma_bf16(tm_accd + (uint32_t)(m2 * C + 16 * j), ad,
-                               desc_nosw(s_wd + (uint32_t)(((j * 9 + t) * DW_PARTS + h) * 512), 128u, 256u), idesc_16, (t | h) ? 1u : 0u);
-            }
-        ptx::umma_commit(bar_accd);
-        if (!p.ghost) {
-          // ---- GEMM 2: [256 rows, C] (planes written by epilogue D) x W2^T -> the accD columns
-          ptx::mbar_wait(bar_a2, ph);
-          ptx::tc_fence_after();
-          for (int m2 = 0; m2 < 2; ++m2)
-            for (int ka = 0; ka < p.katoms; ++ka)
-              for (int k = 0; k < ksteps; ++k) {
-                const int k16 = ka * ksteps + k;
-                const uint64_t ad = desc_nosw(s_t1 + (uint32_t)(2 * k16) * M_PLANE + (uint32_t)(m2 * 128) * 16u, M_PLANE, 128u);
-                const uint32_t b_addr = s_w2 + (uint32_t)ka * w_atom + (uint32_t)k * 32u;
-                ptx::umma_bf16(tm_accd + (uint32_t)(m2 * C), ad, desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4), idesc_c,
-                               (ka | k) ? 1u : 0u);
-              }
-          ptx::umma_commit(bar_acc2);
-        }
-      }
-      __syncwarp();
-      continue;
-    }
-
-    // ---- epilogue 1: BN + act, zero outside the image (the depthwise conv pads its INPUT with zeros) -> T1 planes
-    ptx::mbar_wait(bar_acc1, ph);
-    ptx::tc_fence_after();
-    {
-      const int iy = ty * M_TH - 1 + hy, ix = tx * M_TW - 1 + hx;
-      const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      const uint32_t dst = s_t1 + (uint32_t)row * 16u;
-#pragma unroll
-      for (int j = 0; j < C / 32; ++j) {
-        uint32_t acc[32];
-        tmem_ld_x32m(tm_acc1 + (uint32_t)(mb * C + 32 * j) + lane_sel, acc);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float v[16];
-          bn_act16(*reinterpret_cast<const uint32_t(*)[16]>(acc + 16 * hh), s1_s + 32 * j + 16 * hh, b1_s + 32 * j + 16 * hh, p.act1, v);
-          if (row < M_NHALO) {
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            sts128(dst + (uint32_t)(4 * j + 2 * hh) * M_PLANE, inside ? pack8(v) : z);
-            sts128(dst + (uint32_t)(4 * j + 2 * hh + 1) * M_PLANE, inside ? pack8(v + 8) : z);
-          }
-        }
-      }
-    }
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(bar_t1);
-
-    // ---- epilogue D: + bias, act;  ghost: + residual -> global memory;  chain: -> planes of GEMM 2's A operand
-    const int oy = ty * M_TH + oy_t, ox = tx * M_TW + ox_t;
-    const bool valid = ox_t < M_TW && oy_t < M_TH && oy < p.H && ox < p.W;
-    ptx::mbar_wait(bar_accd, ph);
-    ptx::tc_fence_after();
-    if (p.ghost) {
-      __nv_bfloat16* yrow = p.y.p + p.y.img_off(n) + (int64_t)(oy * p.W + ox) * p.y.ld;
-      const __nv_bfloat16* rrow = p.res.p ? p.res.p + p.res.img_off(n) + (int64_t)(oy * p.W + ox) * p.res.ld : nullptr;
-#pragma unroll
-      for (int j = 0; j < C / 32; ++j) {
-        uint32_t acc[32];
-        tmem_ld_x32m(tm_accd + (uint32_t)(mb * C + 32 * j) + lane_sel, acc);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float v[16];
-          bias_act16(acc + 16 * hh, bd_s + 32 * j + 16 * hh, p.actd, v);
-          if (valid) {
-            if (rrow) {
-              float r0[8], r1[8];
-              unpack8(ldg128(rrow + 32 * j + 16 * hh), r0);
-              unpack8(ldg128(rrow + 32 * j + 16 * hh + 8), r1);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { v[e] += r0[e]; v[8 + e] += r1[e]; }
-            }
-            const uint4 lo = pack8(v), hi = pack8(v + 8);
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + 32 * j + 16 * hh), "r"(lo.x),
-                         "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
-                         : "memory");
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      continue;
-    }
-    {
-      const uint32_t dst = s_t1 + (uint32_t)row * 16u;
-#pragma unroll
-      for (int j = 0; j < C / 32; ++j) {
-        uint32_t acc[32];
-        tmem_ld_x32m(tm_accd + (uint32_t)(mb * C + 32 * j) + lane_sel, acc);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float v[16];
-          bias_act16(acc + 16 * hh, bd_s + 32 * j + 16 * hh, p.actd, v);
-          sts128(dst + (uint32_t)(4 * j + 2 * hh) * M_PLANE, pack8(v));
-          sts128(dst + (uint32_t)(4 * j + 2 * hh + 1) * M_PLANE, pack8(v + 8));
-        }
-      }
-    }
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(bar_a2);
-
-    // ---- epilogue 2: BN + act -> one 256-bit store per 16 channels
-    ptx::mbar_wait(bar_acc2, ph);
-    ptx::tc_fence_after();
-    {
-      __nv_bfloat16* yrow = p.y.p + p.y.img_off(n) + (int64_t)(oy * p.W + ox) * p.y.ld;
-#pragma unroll
-      for (int j = 0; j < C / 32; ++j) {
-        uint32_t acc[32];
-        tmem_ld_x32m(tm_accd + (uint32_t)(mb * C + 32 * j) + lane_sel, acc);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float v[16];
-          bn_act16(*reinterpret_cast<const uint32_t(*)[16]>(acc + 16 * hh), s2_s + 32 * j + 16 * hh, b2_s + 32 * j + 16 * hh, p.act2, v);
-          if (valid) {
-            const uint4 lo = pack8(v), hi = pack8(v + 8);
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + 32 * j + 16 * hh), "r"(lo.x),
-                         "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
-                         : "memory");
-          }
-        }
-      }
-    }
-    ptx::tc_fence_before();
-  }
-
-  __syncthreads();
-  if (ctl) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
+// Two second-generation designs of this unit were built on top of it in round 2, passed every parity test, were measured
+// on B200 (s, B=32) and removed again (profiles/README.md, round 2, items 2 and 8):
+//   * the depthwise stage on the TENSOR pipe (T1 as channel planes, nine diagonal M128 x N16 x K16 MMAs per 16-channel block
+//     over shifted no-swizzle views): an MMA costs ~47 cycles for every N <= 64 (tools/umma_nsweep_test.cu), so the tensor
+//     pipe became the bottleneck -- 0.187 / 0.165 ms against 0.161 / 0.078 ms here at C = 32 / 64;
+//   * a warp-specialised PIPELINE (producer, control, 4 epilogue-1 warps, 8 depthwise warps, 4 epilogue-2 warps, every
+//     hand-over double buffered, 12 x 16 tiles): bit-identical, 0.170 / 0.096 ms.  ncu: every role waits on its input
+//     barrier 11-15 % of the samples; one tile takes ~11 000 cycles end to end in both designs, this kernel keeps three
+//     tiles in flight per SM (three CTAs), the pipeline two.  The unit is bound by its instruction count (7 400 warp
+//     instructions per 128-pixel tile, 2.0 IPC per SM), not by phase serialisation.
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -847,75 +501,6 @@ int launch_chain_impl(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op* pw2p
   const cuuint64_t gstr[3] = {(cuuint64_t)x.ld * 2, (cuuint64_t)a.W * x.ld * 2, (cuuint64_t)x.img_stride * 2};
   const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
 
-  // ---- second-generation kernel (depthwise stage on the tensor pipe): opt-in with DCFA_CHAIN_MMA=1.  Measured (s, B=32):
-  //      an M128 x N x K16 MMA costs ~47 cycles for every N <= 64 (tools/umma_nsweep_test.cu), so the 9 (x2 with split
-  //      taps) diagonal MMAs per 16-channel block make the tensor pipe the bottleneck: 0.187 / 0.165 ms against
-  //      0.161 / 0.078 ms for the first generation at C = 32 / 64 (0.133 / 0.083 ms with single-bf16 taps).
-  bool use_mma = false;
-  {
-    const char* e = getenv("DCFA_CHAIN_MMA");
-    if (e && atoi(e) == 1) use_mma = true;
-  }
-  if (use_mma) {
-    ChainMmaArgs m;
-    m.c = a;
-    m.c.tiles_x = ceil_div(a.W, M_TW);
-    m.c.tiles_y = ceil_div(a.H, M_TH);
-    const int64_t total = (int64_t)a.n_img * m.c.tiles_x * m.c.tiles_y;
-    m.c.tmem_cols = (uint32_t)(4 * C);
-    auto layout = [&](int parts) {
-      uint32_t off = (uint32_t)a.katoms * 256u * a.row_bytes;
-      m.c.off_w1 = off; off += (uint32_t)C * C * 2u;
-      m.c.off_w2 = off; off += ghost ? 0u : (uint32_t)C * C * 2u;
-      m.off_wd = off; off += (uint32_t)(C / 16) * 9u * (uint32_t)parts * 512u;
-      m.off_t1m = off; off += (uint32_t)(C / 8) * (uint32_t)M_PLANE;
-      m.c.off_par = off; off += (uint32_t)(5 * C) * 4u;
-      m.c.off_bar = (off + 15u) & ~15u;
-      return (size_t)1024 + m.c.off_bar + 64;
-    };
-    int parts = 2;
-    {
-      const char* e = getenv("DCFA_DW_PARTS");   // debug: 1 = depthwise taps as single bf16 values
-      if (e && atoi(e) == 1) parts = 1;
-    }
-    size_t smem = layout(parts);
-    if (smem > 227 * 1024 && parts == 2) smem = layout(parts = 1);
-    if (total < (1ll << 31) && smem <= 227 * 1024 && m.c.tmem_cols <= 512) {
-      alignas(64) CUtensorMap map;
-      const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)M_HW, (cuuint32_t)M_HH, 1u};
-      CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x.p), gdim, gstr, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, promo,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "chain: cuTensorMapEncodeTiled failed with %d", (int)cr);
-      static DeviceOnce attr_set_m;
-      if (attr_set_m.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(chain_mma_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_mma_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_mma_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_mma_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_mma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chain_mma_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail(DCFA_E_CUDA, "chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set_m.mark();
-      }
-      int ctas = C == 32 ? 3 : (C == 64 ? 2 : 1);
-      while (ctas > 1 && (size_t)ctas * (smem + 1024) > 228 * 1024) --ctas;
-      int64_t grid = (int64_t)sm_count() * ctas;
-      if (grid > total) grid = total;
-      const dim3 g3((unsigned)grid), b3(kMmaThreads);
-      cudaError_t le;
-      if (C == 32) le = parts == 2 ? launch_pdl(chain_mma_kernel<32, 2>, g3, b3, smem, st, map, m) : launch_pdl(chain_mma_kernel<32, 1>, g3, b3, smem, st, map, m);
-      else if (C == 64) le = parts == 2 ? launch_pdl(chain_mma_kernel<64, 2>, g3, b3, smem, st, map, m) : launch_pdl(chain_mma_kernel<64, 1>, g3, b3, smem, st, map, m);
-      else le = parts == 2 ? launch_pdl(chain_mma_kernel<128, 2>, g3, b3, smem, st, map, m) : launch_pdl(chain_mma_kernel<128, 1>, g3, b3, smem, st, map, m);
-      if (le != cudaSuccess) return fail(DCFA_E_CUDA, "chain: launch: %s", cudaGetErrorString(le));
-      le = cudaGetLastError();
-      if (le != cudaSuccess) return fail(DCFA_E_CUDA, "chain_mma_kernel launch failed: %s", cudaGetErrorString(le));
-      count_launch();
-      return 1;
-    }
-  }
-
-  // ---- first-generation kernel
   if (C == 128 && !force) return 0;
   a.tiles_x = ceil_div(a.W, TW);
   a.tiles_y = ceil_div(a.H, TH);
