@@ -101,10 +101,16 @@ template <int R, int CT>
 __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, uint32_t s_a2, const float* wd_s, const float* bd_s,
                                          int c8_base, int tid, const GhostTile& gt) {
   constexpr int C8N = 2 * R;                 // chunks handled per pass: 4 (R = 2) or 8 (R = 4)
-  const int c8 = c8_base + tid % C8N;
-  const int col = (tid / C8N) % TW;
-  const int oy0 = (tid / (C8N * TW)) * R;
+  constexpr int RG = TH / R;                 // row groups
+  // Thread mapping.  Chain: columns fastest, so a warp works on ONE chunk -- its tap loads are broadcasts (1 shared-memory
+  // wavefront instead of 4-8: the taps were the largest consumer of shared-memory bandwidth) and its T1 reads / A-tile
+  // stores walk neighbouring pixels, conflict-free in both layouts.  Ghost: chunks fastest, so that the lanes of a quarter
+  // warp store the contiguous channels of one pixel to global memory (taps padded to 48 bytes per chunk: no bank conflict).
+  const int c8 = c8_base + (p.ghost ? tid % C8N : tid / (TW * RG));
+  const int col = p.ghost ? (tid / C8N) % TW : tid % TW;
+  const int oy0 = (p.ghost ? tid / (C8N * TW) : (tid / TW) % RG) * R;
   constexpr int C = CT;
+  constexpr int WTAP = (C / 8) * 12;         // floats per tap: 8 weights + 4 floats of padding per chunk
   F2 acc[R][4];
   {
     const float4 b0 = *reinterpret_cast<const float4*>(bd_s + c8 * 8);
@@ -120,15 +126,19 @@ __device__ __forceinline__ void chain_dw(const ChainArgs& p, const uint8_t* t1, 
     F2 w[3][4];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wd_s + (r * 3 + q) * C + c8 * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(wd_s + (r * 3 + q) * C + c8 * 8 + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(wd_s + (r * 3 + q) * WTAP + c8 * 12);
+      const float4 w1 = *reinterpret_cast<const float4*>(wd_s + (r * 3 + q) * WTAP + c8 * 12 + 4);
       w[r][0] = f2_make(w0.x, w0.y); w[r][1] = f2_make(w0.z, w0.w);
       w[r][2] = f2_make(w1.x, w1.y); w[r][3] = f2_make(w1.z, w1.w);
     }
 #pragma unroll
     for (int ri = 0; ri < R + 2; ++ri) {
       F2 v[4];
-      unpack8_f2(*reinterpret_cast<const uint4*>(t1 + (size_t)((oy0 + ri) * HW + col + q) * p.t1_pitch + c8 * 16), v);
+      const int hp = (oy0 + ri) * HW + col + q;   // halo pixel
+      // C = 32: unpadded 64-byte rows with the chunk index XOR-swizzled by the row pair (conflict-free for the row-wise
+      // writes of epilogue 1 AND for these reads, where a quarter warp covers 4 chunks of 2 neighbouring pixels)
+      const uint32_t t1_off = C == 32 ? (uint32_t)hp * 64u + (uint32_t)((c8 ^ (hp >> 1)) & 3) * 16u : (uint32_t)hp * p.t1_pitch + (uint32_t)c8 * 16u;
+      unpack8_f2(*reinterpret_cast<const uint4*>(t1 + t1_off), v);
 #pragma unroll
       for (int o = 0; o < R; ++o) {
         const int r = ri - o;
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
   uint8_t* t1 = gb + p.off_t1;
   constexpr int C = CT;
   float* wd_s = reinterpret_cast<float*>(gb + p.off_par);   // [9][C]
-  float* bd_s = wd_s + 9 * C;
+  float* bd_s = wd_s + 9 * (C / 8) * 12;   // taps padded to 48 bytes per chunk
   float* s1_s = bd_s + C;
   float* b1_s = s1_s + C;
   float* s2_s = b1_s + C;
@@ -243,7 +253,8 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
       for (int i = tid; i < n16; i += kChainThreads) d1[i] = __ldg(src1 + i);
       if (!p.ghost)
         for (int i = tid; i < n16; i += kChainThreads) d2[i] = __ldg(src2 + i);
-      for (int i = tid; i < 9 * C; i += kChainThreads) wd_s[i] = __ldg(p.wd + (int64_t)g * 9 * C + i);
+      for (int i = tid; i < 9 * C; i += kChainThreads)   // [tap][chunk][8 + 4 pad]
+        wd_s[(i / C) * (C / 8) * 12 + ((i % C) >> 3) * 12 + (i & 7)] = __ldg(p.wd + (int64_t)g * 9 * C + i);
       for (int i = tid; i < C; i += kChainThreads) {
         bd_s[i] = __ldg(p.bd + (int64_t)g * C + i);
         s1_s[i] = __ldg(p.s1 + (int64_t)g * p.sb1_gstride + i);
@@ -299,8 +310,9 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
         bn_act16(acc, s1_s + j * 16, b1_s + j * 16, p.act1, v);
         if (row_ok) {   // pixels outside the image are the depthwise conv's zero padding
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(dst + j * 32) = inside ? pack8(v) : z;
-          *reinterpret_cast<uint4*>(dst + j * 32 + 16) = inside ? pack8(v + 8) : z;
+          const uint32_t sw = C == 32 ? (uint32_t)(r >> 1) & 3u : 0u;
+          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = inside ? pack8(v) : z;
+          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = inside ? pack8(v + 8) : z;
         }
       }
     }
@@ -515,9 +527,9 @@ int launch_chain_impl(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op* pw2p
   a.off_a2 = off; off += ghost ? 0u : (uint32_t)a.katoms * 128u * a.row_bytes;
   a.off_w1 = off; off += (uint32_t)C * C * 2u;
   a.off_w2 = off; off += ghost ? 0u : (uint32_t)C * C * 2u;
-  a.t1_pitch = (uint32_t)C * 2u + 16u;
+  a.t1_pitch = C == 32 ? 64u : (uint32_t)C * 2u + 16u;   // C = 32: swizzled instead of padded (see chain_dw)
   a.off_t1 = off; off += ((uint32_t)NHALO * a.t1_pitch + 127u) & ~127u;
-  a.off_par = off; off += (uint32_t)(9 * C + 5 * C) * 4u;
+  a.off_par = off; off += (uint32_t)(9 * (C / 8) * 12 + 5 * C) * 4u;
   a.off_bar = (off + 15u) & ~15u;
   const size_t smem = 1024 + a.off_bar + 64;
   if (smem > 227 * 1024) return 0;

@@ -27,6 +27,8 @@ namespace {
 constexpr int TH = 8, TW = 16;                 // output tile (pixels)
 constexpr int HH = TH + 2, HW = TW + 2;        // halo window
 constexpr int CB = 64;                         // channels per tile (128-byte rows)
+constexpr int WTAP = (CB / 8) * 12;            // floats per tap in shared memory: 8 taps + 4 floats of padding per 8-channel chunk, so that
+                                               // the eight chunks a quarter warp reads (48 bytes apart) hit eight different bank groups
 constexpr int kDwThreads = 256;
 constexpr int IN_BYTES = HH * HW * CB * 2;     // 23040
 constexpr int IN_BUF = (IN_BYTES + 1023) / 1024 * 1024;
@@ -123,8 +125,8 @@ __device__ __forceinline__ void dw_tile_compute(const DwTmaArgs& p, const uint8_
     F2 w[3][4];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const float4 w0 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * CB + c8 * 8 + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * WTAP + c8 * 12);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + (r * 3 + q) * WTAP + c8 * 12 + 4);
       w[r][0] = f2_make(w0.x, w0.y); w[r][1] = f2_make(w0.z, w0.w);
       w[r][2] = f2_make(w1.x, w1.y); w[r][3] = f2_make(w1.z, w1.w);
     }
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(kDwThreads, R == 4 ? 2 : (R == 2 ? 3 : 4)) dwc
   const uint32_t s_res = s_in + NIN * IN_BUF;
   const uint32_t s_out = s_res + res_total;
   float* w_s = reinterpret_cast<float*>(gbase + NIN * IN_BUF + res_total + 2 * OUT_BUF);
-  float* b_s = w_s + 9 * CB;
-  const uint32_t bars = s_out + 2 * OUT_BUF + (9 * CB + CB) * 4;
+  float* b_s = w_s + 9 * WTAP;
+  const uint32_t bars = s_out + 2 * OUT_BUF + (9 * WTAP + CB) * 4;
   const uint32_t bar_in = bars;               // nin barriers (input box [+ residual box] landed)
 
   const int tid = threadIdx.x;
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(kDwThreads, R == 4 ? 2 : (R == 2 ? 3 : 4)) dwc
       __syncthreads();
       for (int i = tid; i < 9 * p.cb; i += kDwThreads) {
         const int tap = i / p.cb, c = i - tap * p.cb;
-        w_s[tap * CB + c] = __ldg(p.w + ((int64_t)g * 9 + tap) * p.C + t.cbi * p.cb + c);
+        w_s[tap * WTAP + (c >> 3) * 12 + (c & 7)] = __ldg(p.w + ((int64_t)g * 9 + tap) * p.C + t.cbi * p.cb + c);
       }
       for (int i = tid; i < p.cb; i += kDwThreads) b_s[i] = __ldg(p.bias + (int64_t)g * p.C + t.cbi * p.cb + i);
       cur_key = key;
@@ -445,7 +447,7 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     t.in_buf = (HH * HW * t.cb * 2 + 1023) / 1024 * 1024;
     t.out_buf = (TH * TW * t.cb * 2 + 1023) / 1024 * 1024;
     const int budget = (227 * 1024) / ctas - 1536;
-    const int fixed = 1024 + 2 * t.out_buf + (9 * CB + CB) * 4 + 64;
+    const int fixed = 1024 + 2 * t.out_buf + (9 * WTAP + CB) * 4 + 64;
     const int per_slot = t.in_buf + (t.has_res ? t.out_buf : 0);
     t.nin = std::min(kMaxNin, (budget - fixed) / per_slot);
     t.res_slots = t.has_res ? t.nin : 0;
@@ -456,7 +458,7 @@ int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     const size_t smem = (size_t)fixed + (size_t)t.nin * t.in_buf + (size_t)t.res_slots * t.out_buf;
     static DeviceOnce attr_set;
     if (attr_set.needed()) {
-      const int mx_smem = 1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * CB + CB) * 4 + 64;
+      const int mx_smem = 1024 + kMaxNin * (IN_BUF + OUT_BYTES) + 2 * OUT_BYTES + (9 * WTAP + CB) * 4 + 64;
       cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx_smem);
