@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) cbam_apply_kernel(const ApplyArgs p) {
 //      the 3 halo rows on each side are read from the neighbouring CTAs' tiles through DSMEM;
 //   D  7x7 conv + sigmoid for the band's pixels;   E  y = x * gate * s  (x read a third time: L2).
 // The launch count of a forward drops by 21, and the per-launch fill/drain of three kernels per CBAM disappears.
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 1024;
 
 struct FusedArgs {
   View<const __nv_bfloat16> x;
