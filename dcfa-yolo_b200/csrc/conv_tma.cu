@@ -132,10 +132,15 @@ __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// FAST: the configuration of most layers (SiLU, bf16 NHWC through 256-bit stores, no residual / split / post-scale) with
+// those choices compiled in: the generic epilogue spends ~30 % of its samples on constant loads, compares and branches
+// that re-derive them for every 16-channel chunk (ncu source page of dark2.0)
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                const __grid_constant__ CUtensorMap tmap_y,
                                                                const TmaConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) TL(7, 0);   // kernel entry (debug timeline)
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
   const uint32_t smem_a = smem_base;
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (threadIdx.x == 0) TL(7, 1);   // dependency wait passed
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -320,11 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       // two register buffers with STATIC indexing (a dynamically indexed array would live in local memory,
       // and with the whole L1 carved out as shared memory every local access is an L2 round trip)
       uint32_t accA[16], accB[16];
-      auto process = [&](const uint32_t (&a)[16], const int j) {
+      // A chunk = 16 channels of the thread's row.  compute(): accumulators -> BN -> activation -> post-scale, pure
+      // register arithmetic, so the two chunks in flight interleave (one chunk alone is a ~700-cycle dependent chain:
+      // LDS -> FFMA2 -> MUFU -> FFMA2; measured with tools/timeline.py); emit(): residual, pack, stores.
+      auto compute = [&](const uint32_t (&a)[16], const int j, float (&v)[16]) {
         const int c0 = j * 16;
         // packed fp32x2 arithmetic (fma.rn.f32x2 / mul.rn.f32x2 are single instructions on sm_100): BN and the FMA
         // halves of SiLU take half the issue slots; the results are the same IEEE operations as the scalar forms
-        float v[16];
         F2 v2[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           f2_fma(v2[2 * q], f2_make(__uint_as_float(a[4 * q + 0]), __uint_as_float(a[4 * q + 1])), f2_make(s4.x, s4.y));
           f2_fma(v2[2 * q + 1], f2_make(__uint_as_float(a[4 * q + 2]), __uint_as_float(a[4 * q + 3])), f2_make(s4.z, s4.w));
         }
-        if (p.act == DCFA_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
+        if (FAST || p.act == DCFA_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
           const F2 half2 = f2_make(0.5f, 0.5f), zero2 = f2_make(0.0f, 0.0f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -356,14 +364,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
           }
         }
-        if (p.post_scale != 1.0f) {
+        if (!FAST && p.post_scale != 1.0f) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] *= p.post_scale;
         }
-        if (p.st256) {
+      };
+      auto emit = [&](float (&v)[16], const int j) {
+        const int c0 = j * 16;
+        if (FAST || p.st256) {
           if (rvalid && c0 < cvalid) {
             uint4 lo, hi;
-            if (rb) {
+            if (!FAST && rb) {
               uint32_t q[8];
               asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             }
             lo = pack8(v);
             hi = pack8(v + 8);
-            __nv_bfloat16* dst = (p.split > 0 && nt * p.BN + c0 >= p.split) ? yb2 + c0 : yb + c0;
+            __nv_bfloat16* dst = (!FAST && p.split > 0 && nt * p.BN + c0 >= p.split) ? yb2 + c0 : yb + c0;
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y),
                          "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                          : "memory");
@@ -462,15 +473,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       // this group's chunks: all of them, or (split) every other one starting at `group`
       const int jstep = p.epi_split ? 2 : 1, j0 = p.epi_split ? group : 0;
       ptx::tmem_ld_x16(taddr0 + (uint32_t)(j0 * 16), accA);
+      if (j0 + jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j0 + jstep) * 16), accB);
       for (int j = j0; j < nchunks; j += 2 * jstep) {
+        const bool two = j + jstep < nchunks;
+        float vA[16], vB[16];
         ptx::tmem_ld_wait();
-        if (j + jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + jstep) * 16), accB);  // prefetch the next chunk
-        process(accA, j);
+        compute(accA, j, vA);
+        if (two) compute(accB, j + jstep, vB);
+        // both register buffers are consumed: the next pair of chunks loads while this pair is stored
+        if (j + 2 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2 * jstep) * 16), accA);
+        if (j + 3 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 3 * jstep) * 16), accB);
+        emit(vA, j);
         __syncwarp();
-        if (j + jstep < nchunks) {
-          ptx::tmem_ld_wait();
-          if (j + 2 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2 * jstep) * 16), accA);
-          process(accB, j + jstep);
+        if (two) {
+          emit(vB, j + jstep);
           __syncwarp();
         }
       }
@@ -690,10 +706,14 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
 
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "conv(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set.mark();
   }
+  bool fast = a.act == DCFA_ACT_SILU && a.st256 && !a.res.p && a.split == 0 && a.post_scale == 1.0f &&
+              a.out_mode == DCFA_OUT_BF16_NHWC && !a.dfl_dbox;
+  { const char* e = getenv("DCFA_CONV_FAST"); if (e && atoi(e) == 0) fast = false; }   // debug / tests: the generic instance
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
   alignas(64) CUtensorMap tmap_y;
   memset(&tmap_y, 0, sizeof(tmap_y));
@@ -708,7 +728,8 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
   }
-  launch_pdl(conv_tma_kernel, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
+  if (fast) launch_pdl(conv_tma_kernel<true>, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
+  else launch_pdl(conv_tma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
   DCFA_CHECK_LAUNCH("conv_tma_kernel");
   return DCFA_OK;
 }
@@ -718,5 +739,9 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
 #ifdef DCFA_TIMELINE
 extern "C" int dcfa_debug_read_timeline(void* dst, int bytes) {
   return cudaMemcpyFromSymbol(dst, dcfa::g_tl, bytes) == cudaSuccess ? 0 : -2;
+}
+extern "C" int dcfa_debug_clear_timeline() {
+  static long long zeros[8][2048];
+  return cudaMemcpyToSymbol(dcfa::g_tl, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -2;
 }
 #endif

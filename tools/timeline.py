@@ -21,11 +21,24 @@ for name in sys.argv[1:]:
         _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng.last_bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
     torch.cuda.synchronize()
     buf = np.zeros((8, 2048), np.int64)
+    _lib.lib.dcfa_debug_clear_timeline()
+    _lib.check(_lib.lib.dcfa_run_ops(op1, 1, eng.last_bufs, P.NUM_BUFS, C.c_void_p(st.cuda_stream)))
+    torch.cuda.synchronize()
     _lib.lib.dcfa_debug_read_timeline(buf.ctypes.data, buf.nbytes)
     kb = eng.plan.ops[i].k_blocks
     t0 = buf[0, 0]
     b = buf - t0
     print("== %s: k_blocks/tile %d" % (name, kb))
+    print(" entry %d  pdl_wait passed %d  first producer issue %d  (cycles after kernel entry of CTA 0)" % (0, buf[7, 1] - buf[7, 0], buf[0, 0] - buf[7, 0]))
+    for t in range(0, 4):   # the first tiles of CTA 0: launch latency, pipeline fill, epilogue drain
+        k0 = t * kb
+        if buf[0, k0] == 0 and t > 0:
+            break
+        g, lt = t & 1, t >> 1
+        e = buf[4 + g, 4 * lt: 4 * lt + 4] - buf[7, 0]
+        print(" first tiles: tile %d prod_issue[first,last] %d %d | full_ok[first,last] %d %d | mma issued[last] %d | epi start %d tfull %d done %d end %d" % (
+            t, buf[0, k0] - buf[7, 0], buf[0, k0 + kb - 1] - buf[7, 0], buf[1, k0] - buf[7, 0], buf[1, k0 + kb - 1] - buf[7, 0],
+            buf[2, k0 + kb - 1] - buf[7, 0], e[0], e[1], e[2], e[3]))
     T = 40  # look at tiles around T
     for t in range(T, T + 4):
         k0 = t * kb
