@@ -138,7 +138,7 @@ def test_golden_pairs_inside_the_bench_batch(cuda, name, batch, positions):
 
 
 @pytest.mark.parametrize("var,val", [("DCFA_CBAM_FUSED", "0"), ("DCFA_CBAM_FUSED", "2"), ("DCFA_CHAIN", "0"), ("DCFA_CHAIN", "2"),
-                                     ("DCFA_GHOST", "0"), ("DCFA_GHOST", "2"), ("DCFA_PDL", "1"), ("DCFA_SPPF_FUSED", "0")])
+                                     ("DCFA_GHOST", "0"), ("DCFA_GHOST", "2"), ("DCFA_PDL", "1"), ("DCFA_SPPF_FUSED", "0"), ("DCFA_CONV_FAST", "0")])
 def test_kernel_path_switches_end_to_end_at_640(cuda, monkeypatch, var, val):
     """Every alternative kernel path (four-kernel / always-fused CBAM, three-kernel / always-fused ShuffleNet branch)
     against the s@640x640 golden of the real reference, end to end."""
