@@ -75,6 +75,7 @@ constexpr int kStemThreads = (kMmaWarp + 1) * 32;   // 704
 constexpr uint32_t kTmemCols = 512;
 static_assert(NCVT == kCvtWarps && NRAW % kCvtWarps == 0 && (NRAW & (NRAW - 1)) == 0,
               "converter warp w owns converted slot w and the raw slots w, w + 4, ...");
+static_assert(XOFF == 2 && PWB == 32, "the converter reads 16 float pairs per raw row, pair 0 = the alignment padding");
 static_assert(2 * PP * 8 + (NCOL - 1) * 16 + 32 <= CVT_SLOT, "MMA over-read must stay inside the slot");
 static_assert((CH - 1) * HP + TPW + 1 <= NCOL, "tile does not fit the accumulator");
 
@@ -361,23 +362,28 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
       if (tma_in) wait_bar(b_raw_full, rph);
       if (MODE == MODE_F32 && p.use_tma) {
         // three 64-bit loads (one per channel plane) and one 128-bit store per item; all loads of the lane's items are
-        // issued before the first convert (independent chains)
-        float2 c[NI_F][3];
+        // issued before the first convert (independent chains).  item = (patch row, one of the row's 16 float pairs):
+        // a half warp reads the 128 contiguous bytes of ONE raw row (conflict-free; with 14 pairs per row the half warps
+        // straddled rows and every LDS.64 cost 4 wavefronts instead of 2); pairs 0 and 15 are the box's alignment padding.
+        constexpr int NI_T = (PH * 16 + 31) / 32;   // 6
+        float2 c[NI_T][3];
 #pragma unroll
-        for (int k = 0; k < NI_F; ++k) {
-          if (k < NI_F - 1 || lane + 32 * k < PH * HP) {
-            const float* src = reinterpret_cast<const float*>(raw) + rr[k] * PWB + XOFF + 2 * qq[k];
+        for (int k = 0; k < NI_T; ++k) {
+          const int item = lane + 32 * k, r16 = item >> 4, p16 = item & 15;
+          if (k < NI_T - 1 || r16 < PH) {
+            const float* src = reinterpret_cast<const float*>(raw) + r16 * PWB + 2 * p16;
             c[k][0] = *reinterpret_cast<const float2*>(src);
             c[k][1] = *reinterpret_cast<const float2*>(src + PH * PWB);
             c[k][2] = *reinterpret_cast<const float2*>(src + 2 * PH * PWB);
           }
         }
 #pragma unroll
-        for (int k = 0; k < NI_F; ++k) {
-          if (k < NI_F - 1 || lane + 32 * k < PH * HP) {
+        for (int k = 0; k < NI_T; ++k) {
+          const int item = lane + 32 * k, r16 = item >> 4, p16 = item & 15;
+          if ((k < NI_T - 1 || r16 < PH) && p16 >= XOFF / 2 && p16 < XOFF / 2 + HP) {
             const uint4 o4 = make_uint4(pack_bf16x2(c[k][0].x, c[k][1].x), pack_bf16x2(c[k][2].x, 0.f),
                                         pack_bf16x2(c[k][0].y, c[k][1].y), pack_bf16x2(c[k][2].y, 0.f));
-            *reinterpret_cast<uint4*>(cvt + (rr[k] * PP + 2 * qq[k]) * 8) = o4;
+            *reinterpret_cast<uint4*>(cvt + (r16 * PP + 2 * (p16 - XOFF / 2)) * 8) = o4;
           }
         }
       } else {
