@@ -63,7 +63,7 @@ def compare_x_maps(z, x, atol, rtol):
 
 def test_golden_set_is_complete():
     assert set(GOLDEN_CASES) >= {"n640_default", "n640_stress", "s128_stress", "m64x96_stress_nc3", "l64_stress",
-                                 "n96_default_b3"}
+                                 "n96_default_b3", "s640_stress", "l1280_stress", "x64_stress"}
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
