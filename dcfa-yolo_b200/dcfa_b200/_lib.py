@@ -13,7 +13,7 @@ SYMBOLS = ("dcfa_abi_version", "dcfa_sizeof_view", "dcfa_sizeof_op", "dcfa_last_
            "dcfa_launch_count", "dcfa_run_ops", "dcfa_decode_box", "dcfa_nms_workspace_bytes", "dcfa_nms",
            "dcfa_letterbox_workspace_bytes", "dcfa_letterbox_u8", "dcfa_pack_detections",
            "dcfa_plan_create", "dcfa_plan_run", "dcfa_plan_num_launches", "dcfa_plan_destroy", "dcfa_plan_load",
-           "dcfa_plan_get_info", "dcfa_plan_forward")
+           "dcfa_plan_get_info", "dcfa_plan_forward", "dcfa_loss_workspace_bytes", "dcfa_yolo_loss")
 
 
 class DcfaError(RuntimeError):
@@ -52,6 +52,10 @@ def _load():
     lib.dcfa_plan_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     lib.dcfa_plan_get_info.argtypes = [C.c_void_p, C.POINTER(abi.PlanInfo)]
     lib.dcfa_plan_forward.argtypes = [C.c_void_p] * 9
+    lib.dcfa_loss_workspace_bytes.restype = C.c_int64
+    lib.dcfa_loss_workspace_bytes.argtypes = [C.c_int] * 4
+    lib.dcfa_yolo_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     if lib.dcfa_abi_version() != abi.ABI_VERSION:
         raise ImportError("dcfa_b200: ABI version %d != %d" % (lib.dcfa_abi_version(), abi.ABI_VERSION))
     if lib.dcfa_sizeof_view() != C.sizeof(abi.View) or lib.dcfa_sizeof_op() != C.sizeof(abi.Op):

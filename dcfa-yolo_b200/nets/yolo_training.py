@@ -1,6 +1,13 @@
-"""Only the piece of the reference's nets/yolo_training.py that the inference path imports: weights_init
-(reference nets/yolo_training.py:480-498, called from YoloBody.__init__ at nets/yolo_mul.py:393-394).
-The loss, assigner, EMA and LR schedules are training-only and out of scope."""
+"""The pieces of the reference's nets/yolo_training.py that sit on or next to the inference path:
+
+* weights_init (reference nets/yolo_training.py:480-498, called from YoloBody.__init__ at nets/yolo_mul.py:393-394);
+* Loss (reference :323-430), FORWARD ONLY: the criterion the reference's validation loop applies under no_grad to the
+  eval-mode outputs of YoloBody.forward (utils/utils_fit_mul.py:78-92) -- decode, task-aligned assigner, BCE / CIoU /
+  DFL terms -- as four CUDA launches behind `dcfa_yolo_loss` (csrc/loss.cu).  The returned tensor
+  carries no autograd graph: backward, EMA and LR schedules are training (N3) and out of scope."""
+import ctypes as C
+
+import torch
 import torch.nn as nn
 
 _INITS = {
@@ -25,3 +32,83 @@ def weights_init(net, init_type='normal', init_gain=0.02):
             nn.init.normal_(m.weight.data, 1.0, 0.02)
             nn.init.constant_(m.bias.data, 0.0)
     print('initialize network with %s type' % init_type)
+
+
+class Loss:
+    """Drop-in for the reference criterion's forward value: `Loss(model)(outputs, batch)` returns the 0-dim tensor
+    box * 7.5 + cls * 0.5 + dfl * 1.5 on the device of the head maps (reference :371-430).  `outputs` is what
+    YoloBody.forward returns (or just its list of three head maps); `batch` holds one row per ground-truth box,
+    (image index, class, cx, cy, w, h) with the box normalised to [0, 1], on the host or on the device.
+    `last` keeps the device vector (box, cls, dfl, sum, target_scores_sum, foreground anchors, 0, 0) of the latest call."""
+
+    def __init__(self, model):
+        from dcfa_b200 import _lib   # raises if the CUDA library is missing: there is no CPU path
+        self._lib = _lib
+        self.stride = [float(s) for s in model.stride]
+        self.nc = int(model.num_classes)
+        self.no = int(model.no)
+        self.reg_max = int(model.reg_max)
+        if self.reg_max != 16 or self.no != self.nc + 64 or len(self.stride) != 3:
+            raise ValueError("Loss: the device criterion is built for reg_max = 16 and three levels (got reg_max %d, no %d, "
+                             "%d strides)" % (self.reg_max, self.no, len(self.stride)))
+        self.last = None
+        self._ws = {}
+
+    def preprocess(self, targets, batch_size, scale_tensor):
+        """Reference :342-360 on the host (index bookkeeping over a few rows): (n, 6) -> (B, G, 5) rows
+        (class, x1, y1, x2, y2) in input pixels, zero padded to the largest per-image count, order of appearance kept."""
+        targets = targets.detach().to("cpu", torch.float32).reshape(-1, 6)
+        if targets.shape[0] == 0:
+            return torch.zeros(batch_size, 0, 5)
+        img = targets[:, 0]
+        _, counts = img.unique(return_counts=True)
+        out = torch.zeros(batch_size, int(counts.max()), 5)
+        for j in range(batch_size):
+            rows = targets[img == j, 1:]
+            if rows.shape[0]:
+                out[j, :rows.shape[0]] = rows
+        xywh = out[..., 1:5].mul_(scale_tensor)
+        half_w, half_h = xywh[..., 2] / 2, xywh[..., 3] / 2
+        out[..., 1:5] = torch.stack((xywh[..., 0] - half_w, xywh[..., 1] - half_h, xywh[..., 0] + half_w, xywh[..., 1] + half_h), -1)
+        return out
+
+    def __call__(self, preds, batch):
+        feats = preds[2] if isinstance(preds, tuple) else preds
+        if len(feats) != 3:
+            raise ValueError("Loss: expected three head maps, got %d" % len(feats))
+        dev = feats[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("Loss: the head maps must be CUDA tensors (there is no CPU path)")
+        B = int(feats[0].shape[0])
+        maps = []
+        for f in feats:
+            if f.dtype != torch.float32 or f.dim() != 4 or f.shape[0] != B or f.shape[1] != self.no:
+                raise ValueError("Loss: head maps must be fp32 [B, %d, H, W]; got %s %s" % (self.no, f.dtype, tuple(f.shape)))
+            maps.append(f.detach().contiguous())
+        hw = [int(v) for f in maps for v in f.shape[2:]]
+        A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
+        # imgsz = feats[0].shape[2:] * stride[0] (:390); targets scaled by (w, h, w, h)
+        imgsz = torch.tensor(hw[:2], dtype=torch.float32) * self.stride[0]
+        gt = self.preprocess(torch.as_tensor(batch), B, imgsz[[1, 0, 1, 0]])
+        G = int(gt.shape[1])
+        if G and (int(gt[..., 0].min()) < 0 or int(gt[..., 0].max()) >= self.nc):
+            raise ValueError("Loss: class labels must lie in [0, %d)" % self.nc)
+        lib = self._lib.lib
+        need = int(lib.dcfa_loss_workspace_bytes(B, A, self.nc, G))
+        key = (dev.index, need)
+        ws = self._ws.get(key)
+        if ws is None:
+            self._ws.clear()
+            ws = self._ws[key] = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            gt_dev = gt.pin_memory().to(dev, non_blocking=True) if G else None
+            st = torch.cuda.current_stream(dev).cuda_stream
+            self._lib.check(lib.dcfa_yolo_loss(
+                maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), B, self.nc, (C.c_int32 * 6)(*hw),
+                (C.c_float * 3)(*self.stride), gt_dev.data_ptr() if G else None, G, out.data_ptr(), ws.data_ptr(),
+                ws.numel(), C.c_void_p(st)))
+            if gt_dev is not None:
+                gt_dev.record_stream(torch.cuda.current_stream(dev))
+        self.last = out
+        return out[3]

@@ -318,6 +318,26 @@ int dcfa_letterbox_u8(const uint8_t* src, int src_h, int src_w, int channels, ui
 int dcfa_pack_detections(const float* det, const int32_t* cnt, int B, int A, int K, const int32_t* image_hw, int in_h, int in_w,
                          int letterbox, float* out, void* stream);
 
+/*
+ * The criterion of the reference's validation loop, forward only: Loss.__call__ (nets/yolo_training.py:371-430) with the
+ * task-aligned assigner (:75-225), CIoU (:227-262) and BboxLoss (:272-303), applied to what YoloBody.forward returns
+ * (utils/utils_fit_mul.py:78-92 calls it under no_grad on the eval-mode outputs).  SURVEY 8(f) N4.
+ *   x0..x2       the three head maps [B, 64 + nc, H_l, W_l] fp32 NCHW contiguous (forward's `x` list)
+ *   level_hw     HOST int32[6] = (H_0, W_0, H_1, W_1, H_2, W_2);  level_stride: HOST float[3] (model.stride)
+ *   gt           DEVICE [B, G, 5] fp32 rows (class, x1, y1, x2, y2) in input pixels, zero padded to G rows per image --
+ *                the output of Loss.preprocess (:342-360); G = 0 (gt may be NULL): no targets in the batch
+ *   out          DEVICE float[8]: box * 7.5, cls * 0.5, dfl * 1.5, their sum (= the value the reference returns),
+ *                target_scores_sum, number of foreground anchors, 0, 0
+ *   workspace    dcfa_loss_workspace_bytes(B, A, nc, G) bytes of device scratch, A = sum of H_l * W_l
+ * Four launches on `stream`, no host synchronisation, deterministic (fixed-order sums).  Among anchors whose alignment
+ * metric is EQUAL at the top-10 boundary the lowest anchor index is taken (torch.topk leaves that order unspecified).
+ * Limits: reg_max = 16, A * 4 bytes and G * 128 bytes of shared memory (A <= 56 320, G <= 1 760), labels in [0, nc).
+ */
+int64_t dcfa_loss_workspace_bytes(int B, int A, int nc, int G);
+int dcfa_yolo_loss(const float* x0, const float* x1, const float* x2, int B, int nc, const int32_t* level_hw,
+                   const float* level_stride, const float* gt, int G, float* out, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
