@@ -139,13 +139,13 @@ def cpu_model():
     return "unknown"
 
 
-def run_ref_runner(phi, size, batch, steps, warmup, seconds=0.0):
+def run_ref_runner(phi, size, batch, steps, warmup, seconds=0.0, extra=()):
     """The REAL reference modules on the host cores, in their own process (their `nets`/`utils` packages clash with the
     drop-in's): oracle/ref_runner.py over oracle/_ref (staged by `make -C oracle ref`, git-ignored, shipped to the GPU
     box) or /root/reference.  None when neither exists or the run fails."""
     runner = os.path.join(ROOT, "oracle", "ref_runner.py")
     cmd = [sys.executable, runner, "--phi", phi, "--size", str(size), "--batch", str(batch), "--steps", str(steps),
-           "--warmup", str(warmup), "--seconds", str(seconds)]
+           "--warmup", str(warmup), "--seconds", str(seconds)] + list(extra)
     env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
@@ -210,6 +210,48 @@ def cpu_baseline(phi, size, batch, seconds):
     t = cpu_timing(phi, size, batch, 200, 2, seconds)
     return {"value": round(t["pairs_per_s"], 3), "unit": UNIT, "cores": t["threads"], "kind": t["kind"], "sample": describe(t),
             "cpu_model": t["cpu_model"], "configs0": configs0_baseline(min(seconds, 10.0))}
+
+
+def library_baseline(phi, size, batch):
+    """The reference's own modules run eagerly by torch / cuDNN on THIS GPU (the 'library' bar beside the CPU
+    baseline): fp32 as the reference runs them, and under bf16 autocast.  Same step as `value`: fwd + decode + NMS."""
+    out = {}
+    for name, extra in (("fp32", ["--device", "cuda"]), ("bf16_autocast", ["--device", "cuda", "--autocast", "bf16"])):
+        t = run_ref_runner(phi, size, batch, 30, 5, 8.0, extra)
+        if t is None:
+            return None
+        out[name] = {"value": round(t["pairs_per_s"], 1), "unit": UNIT, "ms_per_step": round(t["ms_median"], 3), "steps": t["steps"]}
+        out["what"] = "oracle/_ref (the reference's modules%s) on %s, torch %s eager, batch %d, host-timed with synchronize" % (
+            "" if t.get("shipped_unmodified") else " + the five-constant generalisation", t.get("gpu"), t["torch"], batch)
+    return out
+
+
+def val_loss_step(net, phi, batch, size, device, targets_per_image=10, iters=50):
+    """The validation-loss criterion (nets.yolo_training.Loss -> dcfa_yolo_loss) at the bench batch, through
+    the public API (the targets travel host -> device every call), CUDA events; beside it the reference criterion run
+    eagerly on the same GPU."""
+    from nets.yolo_training import Loss
+    from oracle import loss as OL   # synthetic head maps / targets only (the checker's generator)
+    feats, targets = OL.synth_case(seed=105, B=batch, nc=1, hw0=(size // 8, size // 8), n_targets=targets_per_image)
+    maps = [torch.from_numpy(f).to(device) for f in feats]
+    tgt = torch.from_numpy(targets)
+    crit = Loss(net)
+    for _ in range(5):
+        crit(maps, tgt)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        v = crit(maps, tgt)
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"ms_per_call": round(e0.elapsed_time(e1) / iters, 4), "batch": batch, "anchors": int(sum(f.shape[2] * f.shape[3] for f in feats)),
+           "targets_per_image": targets_per_image, "launches_per_call": 4, "loss": round(float(v), 4)}
+    t = run_ref_runner(phi, size, batch, 20, 3, 5.0, ["--device", "cuda", "--loss", str(targets_per_image)])
+    if t is not None:
+        out["reference_on_gpu_ms_per_call"] = round(t["ms_median"], 3)
+        out["reference_loss"] = round(float(t["kept"][0]), 4)
+    return out
 
 
 def run_reference(args):
@@ -626,6 +668,10 @@ def run_ours(args):
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
+        out["val_loss_step"] = val_loss_step(net, args.phi, B, S, device)
+        del pipe, pipe8
+        torch.cuda.empty_cache()
+        out["library_baseline"] = library_baseline(args.phi, S, B)
         out["cpu_baseline"] = cpu_baseline(args.phi, S, args.ref_batch, args.cpu_baseline_seconds)
     print(json.dumps(out))
     if world > 1:

@@ -7,6 +7,7 @@
   carries no autograd graph: backward, EMA and LR schedules are training (N3) and out of scope."""
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -53,24 +54,47 @@ class Loss:
                              "%d strides)" % (self.reg_max, self.no, len(self.stride)))
         self.last = None
         self._ws = {}
+        self._ring = None
+        self._slot = 0
 
     def preprocess(self, targets, batch_size, scale_tensor):
-        """Reference :342-360 on the host (index bookkeeping over a few rows): (n, 6) -> (B, G, 5) rows
-        (class, x1, y1, x2, y2) in input pixels, zero padded to the largest per-image count, order of appearance kept."""
-        targets = targets.detach().to("cpu", torch.float32).reshape(-1, 6)
-        if targets.shape[0] == 0:
-            return torch.zeros(batch_size, 0, 5)
-        img = targets[:, 0]
-        _, counts = img.unique(return_counts=True)
-        out = torch.zeros(batch_size, int(counts.max()), 5)
-        for j in range(batch_size):
-            rows = targets[img == j, 1:]
-            if rows.shape[0]:
-                out[j, :rows.shape[0]] = rows
-        xywh = out[..., 1:5].mul_(scale_tensor)
-        half_w, half_h = xywh[..., 2] / 2, xywh[..., 3] / 2
-        out[..., 1:5] = torch.stack((xywh[..., 0] - half_w, xywh[..., 1] - half_h, xywh[..., 0] + half_w, xywh[..., 1] + half_h), -1)
+        """Reference :342-360 on the host (index bookkeeping over a few rows, numpy float32 -- the same IEEE operations):
+        (n, 6) -> (B, G, 5) rows (class, x1, y1, x2, y2) in input pixels, zero padded to the largest per-image count,
+        order of appearance kept.  Returns a numpy array (a view of `out` when given)."""
+        t = targets.detach().to("cpu", torch.float32).numpy().reshape(-1, 6) if isinstance(targets, torch.Tensor) else \
+            np.asarray(targets, np.float32).reshape(-1, 6)
+        if t.shape[0] == 0:
+            return np.zeros((batch_size, 0, 5), np.float32)
+        img = t[:, 0]
+        _, counts = np.unique(img, return_counts=True)
+        G = int(counts.max())
+        out = np.zeros((batch_size, G, 5), np.float32)
+        order = np.argsort(img, kind="stable")
+        key = img[order]
+        first = np.searchsorted(key, key, side="left")            # position of the first row of the same image
+        rank = np.arange(len(key)) - first
+        ok = (key >= 0) & (key < batch_size) & (key == np.floor(key))   # `i == j` for j in range(batch_size)
+        out[key[ok].astype(np.int64), rank[ok]] = t[order[ok], 1:]
+        xywh = out[..., 1:5] * np.asarray(scale_tensor, np.float32)
+        half_w, half_h = xywh[..., 2] / np.float32(2), xywh[..., 3] / np.float32(2)
+        out[..., 1:5] = np.stack((xywh[..., 0] - half_w, xywh[..., 1] - half_h, xywh[..., 0] + half_w, xywh[..., 1] + half_h), -1)
         return out
+
+    def _stage(self, gt, dev):
+        """Pinned staging ring for the padded targets: slot i is reused only after the copy that last read it has finished."""
+        n = gt.size
+        if self._ring is None or self._ring[0][0].numel() < n or self._ring[0][1].device != dev:
+            cap = max(2 * n, 4096)
+            self._ring = [(torch.empty(cap, dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.float32, device=dev),
+                           torch.cuda.Event()) for _ in range(4)]
+            self._slot = 0
+        host, devbuf, ev = self._ring[self._slot]
+        self._slot = (self._slot + 1) % len(self._ring)
+        ev.synchronize()
+        host[:n].numpy()[:] = gt.reshape(-1)
+        devbuf[:n].copy_(host[:n], non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
+        return devbuf
 
     def __call__(self, preds, batch):
         feats = preds[2] if isinstance(preds, tuple) else preds
@@ -88,11 +112,25 @@ class Loss:
         hw = [int(v) for f in maps for v in f.shape[2:]]
         A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
         # imgsz = feats[0].shape[2:] * stride[0] (:390); targets scaled by (w, h, w, h)
-        imgsz = torch.tensor(hw[:2], dtype=torch.float32) * self.stride[0]
-        gt = self.preprocess(torch.as_tensor(batch), B, imgsz[[1, 0, 1, 0]])
+        imgsz = np.array(hw[:2], np.float32) * np.float32(self.stride[0])
+        gt = self.preprocess(batch, B, imgsz[[1, 0, 1, 0]])
         G = int(gt.shape[1])
-        if G and (int(gt[..., 0].min()) < 0 or int(gt[..., 0].max()) >= self.nc):
+        if G and (gt[..., 0].min() < 0 or gt[..., 0].max() >= self.nc):
             raise ValueError("Loss: class labels must lie in [0, %d)" % self.nc)
+        with torch.cuda.device(dev):
+            gt_dev = self._stage(gt, dev) if G else None
+            out = self.launch(maps, gt_dev, G)
+        self.last = out
+        return out[3]
+
+    def launch(self, maps, gt_dev, G, out=None):
+        """The four launches of dcfa_yolo_loss on the current stream (no host work beyond argument packing; CUDA-graph
+        capturable when `out` and the workspace already exist).  maps: three contiguous fp32 head maps; gt_dev: device
+        buffer holding (B, G, 5) padded targets.  Returns the device vector described in the class docstring."""
+        dev = maps[0].device
+        B = int(maps[0].shape[0])
+        hw = [int(v) for f in maps for v in f.shape[2:]]
+        A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
         lib = self._lib.lib
         need = int(lib.dcfa_loss_workspace_bytes(B, A, self.nc, G))
         key = (dev.index, need)
@@ -100,15 +138,11 @@ class Loss:
         if ws is None:
             self._ws.clear()
             ws = self._ws[key] = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-        out = torch.empty(8, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            gt_dev = gt.pin_memory().to(dev, non_blocking=True) if G else None
-            st = torch.cuda.current_stream(dev).cuda_stream
-            self._lib.check(lib.dcfa_yolo_loss(
-                maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), B, self.nc, (C.c_int32 * 6)(*hw),
-                (C.c_float * 3)(*self.stride), gt_dev.data_ptr() if G else None, G, out.data_ptr(), ws.data_ptr(),
-                ws.numel(), C.c_void_p(st)))
-            if gt_dev is not None:
-                gt_dev.record_stream(torch.cuda.current_stream(dev))
-        self.last = out
-        return out[3]
+        if out is None:
+            out = torch.empty(8, dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._lib.check(lib.dcfa_yolo_loss(
+            maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), B, self.nc, (C.c_int32 * 6)(*hw),
+            (C.c_float * 3)(*self.stride), gt_dev.data_ptr() if G else None, G, out.data_ptr(), ws.data_ptr(),
+            ws.numel(), C.c_void_p(st)))
+        return out

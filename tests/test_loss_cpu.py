@@ -62,8 +62,8 @@ def test_dropin_preprocess_matches_oracle():
     _, targets = OL.synth_case(seed=5, B=4, nc=3, hw0=(40, 56), n_targets=3, tiny=2, empty_image=2)
     targets = targets[np.random.RandomState(0).permutation(len(targets))]   # rows of one image need not be adjacent
     scale = np.array([448., 320., 448., 320.], np.float32)
-    mine = crit.preprocess(torch.from_numpy(targets), 4, torch.from_numpy(scale)).numpy()
+    mine = crit.preprocess(torch.from_numpy(targets), 4, scale)
     assert np.array_equal(mine, OL.preprocess(targets, 4, scale))
-    assert crit.preprocess(torch.zeros(0, 6), 4, torch.from_numpy(scale)).shape == (4, 0, 5)
+    assert crit.preprocess(torch.zeros(0, 6), 4, scale).shape == (4, 0, 5)
     with pytest.raises(RuntimeError, match="no CPU path"):
         crit([torch.zeros(1, 67, 8, 8), torch.zeros(1, 67, 4, 4), torch.zeros(1, 67, 2, 2)], torch.zeros(0, 6))

@@ -137,3 +137,27 @@ def test_validation_step_behind_forward(cuda):
         value = Loss(net)(outputs, torch.from_numpy(targets))
     ref = OL.loss_forward([t.cpu().numpy() for t in outputs[2]], targets, nc=2)
     assert abs(float(value) - float(ref[3])) <= RTOL * abs(float(ref[3])) + ATOL
+
+
+def test_validate_one_epoch(cuda):
+    """The reference's validation loop (utils/utils_fit_mul.py:78-94) over three batches, one of them without targets:
+    the running mean equals the mean of the oracle criterion over the same forward outputs."""
+    from nets.yolo_mul import YoloBody
+    from nets.yolo_training import Loss
+    from utils.utils_fit_mul import fit_one_epoch, validate_one_epoch
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = YoloBody([96, 96], 1, 'n').eval().to(cuda)
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for i in range(3):
+        _, t = OL.synth_case(seed=120 + i, B=2, nc=1, hw0=(12, 12), n_targets=0 if i == 1 else 2)
+        batches.append((torch.rand(2, 3, 96, 96, generator=g), torch.rand(2, 3, 96, 96, generator=g), torch.from_numpy(t)))
+    got = validate_one_epoch(net, Loss(net), batches, 3, True, 0)
+    want = 0.0
+    with torch.no_grad():
+        for rgb, nir, t in batches:
+            maps = net(rgb.to(cuda), nir.to(cuda))[2]
+            want += float(OL.loss_forward([m.cpu().numpy() for m in maps], t.numpy(), nc=1)[3])
+    assert abs(got - want / 3) <= RTOL * abs(want / 3) + ATOL
+    with pytest.raises(NotImplementedError):
+        fit_one_epoch()
