@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=1, help="pairs per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="development: time only `value` (graph replay) and the per-kind table")
     ap.add_argument("--profile-ops", default="", help="write per-op CUDA-event timings (JSON) to this path")
     return ap.parse_args()
 
@@ -514,6 +515,18 @@ def run_ours(args):
     value = total_pairs * K / (ms_total / 1e3)
     cand = pipe.ws.cand.cpu().numpy()
     kept = pipe.ws.cnt.cpu().numpy()
+    if args.value_only:
+        clk.__exit__(None, None, None)
+        rows, _ = profile_ops(net, B, S, device)
+        by_kind = {}
+        for r in rows:
+            by_kind[r["kind"]] = round(by_kind.get(r["kind"], 0.0) + r["ms"], 4)
+        if rank == 0:
+            print(json.dumps({"value": round(value, 1), "ms_per_step": round(ms_step, 4), "ms_by_kind": by_kind,
+                              "launches_per_step": pipe.launches_per_step}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: public API, pinned host inputs in, detections out, every step
     from utils.utils_bbox import DecodeBox

@@ -28,7 +28,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int kTmaWarp = 4;
 constexpr int kMmaWarp = 5;
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;       // generic instance: two epilogue groups
+#ifndef DCFA_FAST_GROUPS
+#define DCFA_FAST_GROUPS 2   // four groups (96 registers per thread) measured 0.8 % slower per step than two (130)
+#endif
+constexpr int kFastGroups = DCFA_FAST_GROUPS;             // FAST instance: epilogue groups (warps 0-3, 6-9, 10-13, 14-17)
+constexpr int kThreadsFast = 64 + 128 * kFastGroups;
 constexpr int kMaxStages = 24;
 
 struct FastDiv {
@@ -85,6 +90,7 @@ struct TmaConvArgs {
   float* dfl_dbox;       // [n_img, 4, A] (nullptr: off)
   float* dfl_cls;        // [n_img, nc, A]
   int dfl_A, dfl_aoff, dfl_nc;   // total anchors, first anchor of this level, classes
+  int ngroups;           // epilogue groups of four warps: 2 (generic instance) or 4 (FAST instance)
   int epi_split;         // 1: BOTH epilogue groups work on every tile, each on every other 16-channel chunk (wide
                          // tiles: halves the epilogue latency of a tile, which is exposed at the tail of every launch
                          // and is all there is when a CTA gets one tile); 0: the groups alternate tiles
@@ -136,7 +142,7 @@ __device__ __forceinline__ void bulk_wait() {
 // those choices compiled in: the generic epilogue spends ~30 % of its samples on constant loads, compares and branches
 // that re-derive them for every 16-channel chunk (ncu source page of dark2.0)
 template <bool FAST>
-__global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                const __grid_constant__ CUtensorMap tmap_y,
                                                                const TmaConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -151,8 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t bar_tfull = bars + 16u * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 32u;
   const uint32_t tmem_slot = bar_tempty + 32u;
-  const uint32_t sb_base = (tmem_slot + 4u + 15u) & ~15u;  // 2 groups x (256 scale + 256 bias) floats
-  const uint32_t stage_out = (sb_base + 4096u + 1023u) & ~1023u;  // [group][2] output staging tiles (TMA store)
+  const uint32_t sb_base = (tmem_slot + 4u + 15u) & ~15u;  // up to 4 groups x (256 scale + 256 bias) floats
+  const uint32_t stage_out = (sb_base + 8192u + 1023u) & ~1023u;  // [group][2] output staging tiles (TMA store)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       }
       for (int a = 0; a < (int)p.acc_stages; ++a) {
         ptx::mbar_init(bar_tfull + 8u * a, 1);
-        ptx::mbar_init(bar_tempty + 8u * a, p.epi_split ? 8 : 4);  // the warps of the epilogue group(s) reading the stage
+        ptx::mbar_init(bar_tempty + 8u * a, p.epi_split ? 4 * p.ngroups : 4);  // the warps of the epilogue group(s) reading the stage
       }
       ptx::fence_mbar_init();
     }
@@ -267,7 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue: group 0 = warps 0-3, group 1 = warps 6-9
-    const int group = warp < 4 ? 0 : 1;
+    const int group = warp < 4 ? 0 : 1 + ((warp - 6) >> 2);
+    const uint32_t gmask = (uint32_t)p.ngroups - 1u;   // 2 or 4 groups
     const int q4 = warp & 3;           // TMEM lane quarter this warp may access
     const int r = q4 * 32 + lane;      // accumulator row
     const int gtid = q4 * 32 + lane;   // thread index inside the group
@@ -280,9 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     int sb_key = -1;
     const uint32_t acc_shift = p.acc_stages == 4u ? 2u : 1u;
     uint32_t slab = 0;   // store slabs issued by this group (selects the staging buffer)
+    [[maybe_unused]] uint32_t tl_fine = 0;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      if (!p.epi_split && (int)(tcount & 1u) != group) continue;
+      if (!p.epi_split && (int)(tcount & gmask) != group) continue;
       const uint32_t as = tcount & (p.acc_stages - 1u);   // accumulator stage; its parity is the group's
       const uint32_t aph = (tcount >> acc_shift) & 1u;     // the stage's use count, mod 2
       const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
@@ -295,13 +303,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       const int oy = ty * p.th + iy, ox = tx * p.tw + ix;
       const bool rvalid = iy < p.th && oy < p.Ho && ox < p.Wo;
       const int pix = oy * p.Wo + ox;
-      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1));
+      if (q4 == 0 && lane == 0 && group < 2) TL(4 + group, 4 * (tcount >> 1));
       if (g * p.n_tiles + nt != sb_key) {   // uniform across the group's 128 threads
         sb_key = g * p.n_tiles + nt;
         ptx::named_bar_sync(1 + group, 128);  // previous tile's readers are done
         const float* sc = p.scale + (int64_t)g * p.sb_gstride + nt * p.BN;
         const float* bi = p.bias + (int64_t)g * p.sb_gstride + nt * p.BN;
-        for (int c = gtid; c < p.BN; c += 128) { sb[c] = __ldg(sc + c); sb[256 + c] = __ldg(bi + c); }
+        // FAST (SiLU): the epilogue needs h = (acc * s + b) / 2 -- halve the vectors here (exact: a power of two)
+        const float pre = FAST ? 0.5f : 1.0f;
+        for (int c = gtid; c < p.BN; c += 128) { sb[c] = pre * __ldg(sc + c); sb[256 + c] = pre * __ldg(bi + c); }
         ptx::named_bar_sync(1 + group, 128);
       }
       __nv_bfloat16* yb = nullptr;
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       const int cvalid = min(p.BN, p.Cout - nt * p.BN);  // valid channels of this n-tile
       ptx::mbar_wait(bar_tfull + 8u * as, aph);
       ptx::tc_fence_after();
-      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 1);
+      if (q4 == 0 && lane == 0 && group < 2) TL(4 + group, 4 * (tcount >> 1) + 1);
       const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
       const int nchunks = p.BN >> 4;
       // two register buffers with STATIC indexing (a dynamically indexed array would live in local memory,
@@ -348,11 +358,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             F2 h = zero2;
-            f2_fma(h, v2[e], half2);
+            if (FAST) h = v2[e];   // scale and bias were halved when they were staged
+            else f2_fma(h, v2[e], half2);
             float h0, h1, t0, t1;
             f2_get(h, h0, h1);
+#ifdef DCFA_EXP_NOMUFU
+            t0 = h0 * 0.25f; t1 = h1 * 0.25f;
+#else
             asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
             asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+#endif
             f2_fma(h, h, f2_make(t0, t1));   // h * t + h
             f2_get(h, v[2 * e], v[2 * e + 1]);
           }
@@ -372,7 +387,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       auto emit = [&](float (&v)[16], const int j) {
         const int c0 = j * 16;
         if (FAST || p.st256) {
+#ifdef DCFA_EXP_NOSTORE
+          if (rvalid && c0 < cvalid && v[3] == 12345.678f) {
+#else
           if (rvalid && c0 < cvalid) {
+#endif
             uint4 lo, hi;
             if (!FAST && rb) {
               uint32_t q[8];
@@ -471,15 +490,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         }
       };
       // this group's chunks: all of them, or (split) every other one starting at `group`
-      const int jstep = p.epi_split ? 2 : 1, j0 = p.epi_split ? group : 0;
+      const int jstep = p.epi_split ? p.ngroups : 1, j0 = p.epi_split ? group : 0;
       ptx::tmem_ld_x16(taddr0 + (uint32_t)(j0 * 16), accA);
       if (j0 + jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j0 + jstep) * 16), accB);
       for (int j = j0; j < nchunks; j += 2 * jstep) {
         const bool two = j + jstep < nchunks;
         float vA[16], vB[16];
+#ifdef DCFA_TIMELINE
+        if (group == 0 && q4 == 0 && lane == 0) { TL(6, tl_fine); ++tl_fine; }
+#endif
         ptx::tmem_ld_wait();
+#ifdef DCFA_TIMELINE
+        if (group == 0 && q4 == 0 && lane == 0) { TL(6, tl_fine); ++tl_fine; }
+#endif
         compute(accA, j, vA);
         if (two) compute(accB, j + jstep, vB);
+#ifdef DCFA_TIMELINE
+        if (group == 0 && q4 == 0 && lane == 0) { asm volatile("" :: "f"(vA[0]), "f"(vA[15]), "f"(vB[0]), "f"(vB[15])); TL(6, tl_fine); ++tl_fine; }
+#endif
         // both register buffers are consumed: the next pair of chunks loads while this pair is stored
         if (j + 2 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 2 * jstep) * 16), accA);
         if (j + 3 * jstep < nchunks) ptx::tmem_ld_x16(taddr0 + (uint32_t)((j + 3 * jstep) * 16), accB);
@@ -489,12 +517,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           emit(vB, j + jstep);
           __syncwarp();
         }
+#ifdef DCFA_TIMELINE
+        if (group == 0 && q4 == 0 && lane == 0) { TL(6, tl_fine); ++tl_fine; }
+#endif
       }
-      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 2);
+      if (q4 == 0 && lane == 0 && group < 2) TL(4 + group, 4 * (tcount >> 1) + 2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8u * as);
-      if (q4 == 0 && lane == 0) TL(4 + group, 4 * (tcount >> 1) + 3);
+      if (q4 == 0 && lane == 0 && group < 2) TL(4 + group, 4 * (tcount >> 1) + 3);
     }
     if (p.tma_store && gtid == 0) bulk_wait<0>();   // staging smem must outlive the last TMA store
   }
@@ -563,7 +594,8 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.sb_gstride = op.sb_gstride;
   a.n_img = op.n_img;
   a.group_imgs = op.group_imgs > 0 ? op.group_imgs : op.n_img;
-  const int Hi = op.Hi, Wi = op.Wi, Cin = op.Cin;
+  int Hi = op.Hi, Wi = op.Wi;
+  const int Cin = op.Cin;
   a.Ho = op.Ho; a.Wo = op.Wo; a.Cout = op.Cout;
   a.ksize = op.ksize; a.stride = op.stride; a.pad = op.ksize / 2;
   a.BN = op.BN; a.n_tiles = op.n_tiles; a.k_blocks = op.k_blocks;
@@ -618,6 +650,40 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     DCFA_REQUIRE(a.y.img_stride == (int64_t)a.out_ctot * a.Ho * a.Wo, "conv(tma): NCHW img_stride mismatch");
   }
 
+  // ---- 1x1 stride-1 convolutions over dense tensors are plain GEMMs over pixels: describe each weight group as ONE
+  // image of height 1 and width group_imgs * H * W, so that an M tile is 128 consecutive pixels whatever the map size.
+  // At 40 x 40 a spatial tile holds 3 x 40 = 120 pixels: 448 tiles for 32 images, i.e. FOUR waves on 148 SMs for
+  // 3.03 tiles per CTA; flattened it is 400 tiles and three waves (dn1.cv1: 23 -> 18 us).
+  {
+    const char* e = getenv("DCFA_CONV_FLAT");   // debug / tests: DCFA_CONV_FLAT=0 keeps the spatial tiling
+    const int hw = a.Ho * a.Wo;
+    auto uniform = [&](int64_t ld, int64_t img_stride, int gi) {   // pixels of a whole weight group are equidistant
+      return img_stride == (int64_t)hw * ld && (gi <= 0 || gi == a.group_imgs);
+    };
+    bool flat = !(e && atoi(e) == 0) && a.ksize == 1 && a.stride == 1 && !a.pair && a.out_mode == DCFA_OUT_BF16_NHWC &&
+                !a.dfl_dbox && (int64_t)a.group_imgs * hw < (1ll << 30) && uniform(x.ld, x.img_stride, x.gi) &&
+                uniform(a.y.ld, a.y.img_stride, a.y.gi) && (!a.res.p || uniform(a.res.ld, a.res.img_stride, a.res.gi)) &&
+                (a.split == 0 || uniform(a.y2.ld, a.y2.img_stride, a.y2.gi));
+    if (flat) {
+      int tw0, th0;
+      pick_tile(a.Ho, a.Wo, &tw0, &th0);
+      const int64_t spatial = (int64_t)a.n_img * ((a.Ho + th0 - 1) / th0) * ((a.Wo + tw0 - 1) / tw0);
+      const int64_t P = (int64_t)a.group_imgs * hw;
+      const int groups = a.n_img / a.group_imgs;
+      if (groups * ((P + 127) / 128) < spatial) {
+        auto regroup = [&](auto& v) {   // one "image" per weight group
+          v.img_stride = v.gi > 0 ? v.gstride : (int64_t)a.group_imgs * v.img_stride;
+          v.gi = 0; v.gstride = 0;
+        };
+        regroup(x); regroup(a.y);
+        if (a.res.p) regroup(a.res);
+        if (a.split > 0) regroup(a.y2);
+        a.n_img = groups; a.group_imgs = 1;
+        Hi = 1; Wi = (int)P; a.Ho = 1; a.Wo = (int)P;
+      }
+    }
+  }
+
   pick_tile(a.Ho, a.Wo, &a.tw, &a.th);
   a.tiles_x = (a.Wo + a.tw - 1) / a.tw;
   const int tiles_y = (a.Ho + a.th - 1) / a.th;
@@ -660,7 +726,7 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
   a.cbox = a.BN >= 64 ? 64 : a.BN;   // BN is 16, 32, 48 or a multiple of 64 below
   if (a.tma_store && (a.BN % a.cbox != 0 || (a.cbox != 64 && a.cbox != 32 && a.cbox != 16))) a.tma_store = 0;
   a.out_stage_bytes = 128u * (uint32_t)a.cbox * 2u;
-  const int fixed = 1024 + 512 + 4096 + 1024 + (a.tma_store ? 4 * (int)a.out_stage_bytes : 0);
+  const int fixed = 1024 + 512 + 8192 + 1024 + (a.tma_store ? 4 * (int)a.out_stage_bytes : 0);
   int stages = (max_smem - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   { const char* e = getenv("DCFA_STAGES"); if (e && atoi(e) > 1 && atoi(e) < stages) stages = atoi(e); }
@@ -728,7 +794,12 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(tma): cuTensorMapEncodeTiled(output) failed with %d", (int)cr);
   }
-  if (fast) launch_pdl(conv_tma_kernel<true>, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
+  a.ngroups = 2;
+  if (fast) {   // latency-bound epilogue (ncu: 16 % of its samples issue): four groups instead of two
+    const char* e = getenv("DCFA_EPI_GROUPS");   // debug: DCFA_EPI_GROUPS=2 launches the FAST instance with two groups
+    a.ngroups = (e && atoi(e) == 2) ? 2 : kFastGroups;
+  }
+  if (fast) launch_pdl(conv_tma_kernel<true>, dim3(grid), dim3(64 + 128 * a.ngroups), smem, st, tmap, tmap_y, a);
   else launch_pdl(conv_tma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
   DCFA_CHECK_LAUNCH("conv_tma_kernel");
   return DCFA_OK;

@@ -27,9 +27,10 @@ import json
 import os
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-# model goldens (oracle/make_golden.py); facade_*.npz hold the host-helper goldens of oracle/make_golden_facade.py
+# model goldens (oracle/make_golden.py); facade_*.npz hold the host-helper goldens of oracle/make_golden_facade.py,
+# loss_*.npz those of the validation-loss criterion (oracle/make_golden_loss.py, tests/test_loss_*.py)
 GOLDEN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz"))
-                      if not os.path.basename(p).startswith("facade_"))
+                      if not os.path.basename(p).startswith(("facade_", "loss_")))
 
 
 def load_golden(name):
