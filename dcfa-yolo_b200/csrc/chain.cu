@@ -57,26 +57,51 @@ struct ChainArgs {
   View<const __nv_bfloat16> res;   // ghost mode: optional residual, added after the depthwise activation
 };
 
-// v[e] = act(acc[e] * scale[e] + bias[e]) for 16 consecutive channels: 128-bit shared-memory loads of the BN vectors,
-// the (uniform) activation branch taken once per chunk, not per element
-__device__ __forceinline__ void bn_act16(const uint32_t (&acc)[16], const float* sc, const float* bi, int act, float* v) {
+// 16 consecutive channels of one row: act(acc * scale + bias) -> two 128-bit words of bf16.  128-bit shared-memory loads
+// of the BN vectors, packed fp32x2 FMAs (same IEEE results, half the issue slots), the (uniform) activation branch taken
+// once per chunk.  ReLU is folded into the conversion (cvt.rn.relu.bf16x2: the same values as max(x, 0) then round);
+// for SiLU the caller stages scale and bias HALVED (exact), so the FMA yields h = x / 2 and x * sigmoid(x) = h + h * tanh(h).
+__device__ __forceinline__ void bn_act16(const uint32_t (&acc)[16], const float* sc, const float* bi, int act, uint4& lo, uint4& hi) {
+  F2 v2[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {   // packed fp32x2 FMAs: same IEEE results, half the issue slots
+  for (int q = 0; q < 4; ++q) {
     const float4 s4 = *reinterpret_cast<const float4*>(sc + 4 * q);
     const float4 b4 = *reinterpret_cast<const float4*>(bi + 4 * q);
-    F2 lo = f2_make(b4.x, b4.y), hi = f2_make(b4.z, b4.w);
-    f2_fma(lo, f2_make(__uint_as_float(acc[4 * q + 0]), __uint_as_float(acc[4 * q + 1])), f2_make(s4.x, s4.y));
-    f2_fma(hi, f2_make(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), f2_make(s4.z, s4.w));
-    f2_get(lo, v[4 * q + 0], v[4 * q + 1]);
-    f2_get(hi, v[4 * q + 2], v[4 * q + 3]);
+    v2[2 * q] = f2_make(b4.x, b4.y);
+    v2[2 * q + 1] = f2_make(b4.z, b4.w);
+    f2_fma(v2[2 * q], f2_make(__uint_as_float(acc[4 * q + 0]), __uint_as_float(acc[4 * q + 1])), f2_make(s4.x, s4.y));
+    f2_fma(v2[2 * q + 1], f2_make(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), f2_make(s4.z, s4.w));
   }
+  uint32_t w[8];
   if (act == DCFA_ACT_RELU) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+    for (int e = 0; e < 8; ++e) {
+      float a, b;
+      f2_get(v2[e], a, b);
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(b), "f"(a));
+    }
   } else if (act == DCFA_ACT_SILU) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = silu_fast(v[e]);
+    for (int e = 0; e < 8; ++e) {
+      float h0, h1, t0, t1;
+      f2_get(v2[e], h0, h1);
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+      F2 h = v2[e];
+      f2_fma(h, h, f2_make(t0, t1));   // h * t + h
+      f2_get(h, h0, h1);
+      w[e] = pack_bf16x2(h0, h1);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a, b;
+      f2_get(v2[e], a, b);
+      w[e] = pack_bf16x2(a, b);
+    }
   }
+  lo = make_uint4(w[0], w[1], w[2], w[3]);
+  hi = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 __device__ __forceinline__ void chain_tma_load(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
@@ -257,11 +282,12 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
         wd_s[(i / C) * (C / 8) * 12 + ((i % C) >> 3) * 12 + (i & 7)] = __ldg(p.wd + (int64_t)g * 9 * C + i);
       for (int i = tid; i < C; i += kChainThreads) {
         bd_s[i] = __ldg(p.bd + (int64_t)g * C + i);
-        s1_s[i] = __ldg(p.s1 + (int64_t)g * p.sb1_gstride + i);
-        b1_s[i] = __ldg(p.b1 + (int64_t)g * p.sb1_gstride + i);
+        const float pre1 = p.act1 == DCFA_ACT_SILU ? 0.5f : 1.0f, pre2 = p.act2 == DCFA_ACT_SILU ? 0.5f : 1.0f;   // see bn_act16
+        s1_s[i] = pre1 * __ldg(p.s1 + (int64_t)g * p.sb1_gstride + i);
+        b1_s[i] = pre1 * __ldg(p.b1 + (int64_t)g * p.sb1_gstride + i);
         if (!p.ghost) {
-          s2_s[i] = __ldg(p.s2 + (int64_t)g * p.sb2_gstride + i);
-          b2_s[i] = __ldg(p.b2 + (int64_t)g * p.sb2_gstride + i);
+          s2_s[i] = pre2 * __ldg(p.s2 + (int64_t)g * p.sb2_gstride + i);
+          b2_s[i] = pre2 * __ldg(p.b2 + (int64_t)g * p.sb2_gstride + i);
         }
       }
       cur_g = g;
@@ -306,13 +332,13 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
         uint32_t acc[16];
         ptx::tmem_ld_x16(taddr + (uint32_t)(j * 16), acc);
         ptx::tmem_ld_wait();
-        float v[16];
-        bn_act16(acc, s1_s + j * 16, b1_s + j * 16, p.act1, v);
+        uint4 lo, hi;
+        bn_act16(acc, s1_s + j * 16, b1_s + j * 16, p.act1, lo, hi);
         if (row_ok) {   // pixels outside the image are the depthwise conv's zero padding
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
           const uint32_t sw = C == 32 ? (uint32_t)(r >> 1) & 3u : 0u;
-          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = inside ? pack8(v) : z;
-          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = inside ? pack8(v + 8) : z;
+          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = inside ? lo : z;
+          *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = inside ? hi : z;
         }
       }
     }
@@ -371,10 +397,9 @@ __global__ void __launch_bounds__(kChainThreads, CT == 32 ? 3 : (CT == 64 ? 2 : 
         uint32_t acc[16];
         ptx::tmem_ld_x16(taddr + (uint32_t)(j * 16), acc);
         ptx::tmem_ld_wait();
-        float v[16];
-        bn_act16(acc, s2_s + j * 16, b2_s + j * 16, p.act2, v);
+        uint4 lo, hi;
+        bn_act16(acc, s2_s + j * 16, b2_s + j * 16, p.act2, lo, hi);
         if (valid) {
-          const uint4 lo = pack8(v), hi = pack8(v + 8);
           asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + j * 16), "r"(lo.x), "r"(lo.y),
                        "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                        : "memory");
