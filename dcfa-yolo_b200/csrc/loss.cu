@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) loss_assign_kernel(const LossArgs p) {
     if (threadIdx.x < kTopK) p.cand_a[cbase + threadIdx.x] = -1;
     return;
   }
-  const int label = (int)gt[0];
+  const int label = min(max((int)gt[0], 0), p.nc - 1);   // callers validate labels; the clamp only keeps a bad one inside the tensor
   const float* sig = p.sig + ((int64_t)b * p.nc + label) * p.A;
   for (int a = threadIdx.x; a < p.A; a += 256) {
     float ov, al;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kResolveThreads) loss_resolve_kernel(const Los
             const float* gj = gt + j * 5;
             float o, m;
             bool inside;
-            box_metric(p, b, a, p.sig[((int64_t)b * p.nc + (int)gj[0]) * p.A + a], gj + 1, o, m, inside);
+            box_metric(p, b, a, p.sig[((int64_t)b * p.nc + min(max((int)gj[0], 0), p.nc - 1)) * p.A + a], gj + 1, o, m, inside);
             if (o > best) { best = o; g = j; ov = o; al = m; }
           }
         }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kResolveThreads) loss_resolve_kernel(const Los
     const float* src = p.map[l] + (int64_t)b * p.no * hw + pos;
     // BCE (:411): the one element of this anchor whose target is not zero
     {
-      const float x = __ldg(src + (int64_t)(4 * kBins + (int)gj[0]) * hw);
+      const float x = __ldg(src + (int64_t)(4 * kBins + min(max((int)gj[0], 0), p.nc - 1)) * hw);
       const float ls = __fsub_rn(fminf(x, 0.0f), log1pf(expf(-fabsf(x))));
       const float with_t = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, norm), x), ls);
       s_bce += (double)with_t - (double)__fsub_rn(x, ls);

@@ -161,3 +161,30 @@ def test_validate_one_epoch(cuda):
     assert abs(got - want / 3) <= RTOL * abs(want / 3) + ATOL
     with pytest.raises(NotImplementedError):
         fit_one_epoch()
+
+
+def test_loss_through_the_c_abi(cuda):
+    """dcfa_yolo_loss called with raw pointers, as the header declares it (no Python wrapper in between)."""
+    import ctypes as C
+    from dcfa_b200 import _lib
+    kw = dict(seed=130, B=2, nc=3, hw0=(24, 32), n_targets=4, tiny=1)
+    feats, targets = OL.synth_case(**kw)
+    ref = OL.loss_forward(feats, targets, nc=3)
+    B, nc = 2, 3
+    x = [torch.from_numpy(f).to(cuda) for f in feats]
+    hw = [int(v) for f in feats for v in f.shape[2:]]
+    A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
+    gt = OL.preprocess(targets, B, np.array([hw[1] * 8, hw[0] * 8, hw[1] * 8, hw[0] * 8], np.float32))
+    G = gt.shape[1]
+    gt_dev = torch.from_numpy(gt).to(cuda)
+    need = _lib.lib.dcfa_loss_workspace_bytes(B, A, nc, G)
+    ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+    out = torch.zeros(8, device=cuda)
+    st = torch.cuda.current_stream(cuda).cuda_stream
+    args = (x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), B, nc, (C.c_int32 * 6)(*hw), (C.c_float * 3)(8., 16., 32.),
+            gt_dev.data_ptr(), G, out.data_ptr(), ws.data_ptr())
+    assert _lib.lib.dcfa_yolo_loss(*args, need, C.c_void_p(st)) == 0
+    np.testing.assert_allclose(out.cpu().numpy()[:4], ref, rtol=RTOL, atol=ATOL)
+    # a workspace that is too small is refused with a message, nothing is launched
+    assert _lib.lib.dcfa_yolo_loss(*args, need - 256, C.c_void_p(st)) == -1
+    assert b"workspace" in _lib.lib.dcfa_last_error()

@@ -54,6 +54,8 @@ CONV_CASES = [
     (2, 20, 20, 512, 256, 1, 1, 2, 1),  # 20x20 maps: partial spatial tiles
     (2, 40, 40, 128, 128, 3, 2, 2, 2),  # stride 2, two k-blocks per tap, two groups
     (1, 22, 38, 64, 32, 3, 2, 0, 1),    # stride 2, even width, partial tiles on the right / bottom edge
+    (4, 20, 20, 64, 64, 1, 1, 2, 2),    # 1x1, two weight groups: flattened pixel tiling, 7 tiles per group (partial last)
+    (6, 40, 40, 128, 256, 1, 1, 2, 2),  # 1x1 at 40x40 (the neck's shape): 38 flattened tiles per group instead of 3 x 14
 ]
 
 
@@ -88,6 +90,26 @@ def test_conv_bf16_nhwc(cuda, monkeypatch, n, h, w, cin, cout, k, s, act, groups
         refs.append(_act(r, act))
     ref = torch.cat(refs).permute(0, 2, 3, 1)
     _bf16_close(y, ref, "conv")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,groups", [(4, 20, 20, 64, 64, 2), (3, 40, 40, 128, 256, 1), (2, 10, 10, 256, 512, 1)])
+def test_conv_1x1_flattened_tiling_equals_spatial(cuda, monkeypatch, n, h, w, cin, cout, groups):
+    """1x1 stride-1 convs tile the flattened pixel axis of each weight group (launch_conv_tma); DCFA_CONV_FLAT=0 keeps the
+    spatial tiles.  Same MMAs on the same rows in a different tile order: the outputs must be bit-identical."""
+    from dcfa_b200 import abi
+    g = torch.Generator().manual_seed(77 + cin + cout)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g)).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(cuda)
+    ws = [bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5) for _ in range(groups)]
+    scs = [torch.rand(cout, generator=g) + 0.5 for _ in range(groups)]
+    bis = [torch.randn(cout, generator=g) * 0.1 for _ in range(groups)]
+    outs = []
+    for flat in ("1", "0"):
+        monkeypatch.setenv("DCFA_CONV_FLAT", flat)
+        y = torch.full((n, h, w, cout), 7.0, dtype=torch.bfloat16, device=cuda)
+        op, bufs = conv_op(x, ws, scs, bis, y, ksize=1, stride=1, act=abi.ACT_SILU, cin=cin, group_imgs=n // groups)
+        _run([op], bufs)
+        outs.append(y)
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
 
 
 def test_conv_views_residual_postscale(cuda):
