@@ -457,9 +457,19 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
               }
             }
           } else {
+            // fp32 NCHW: lanes are consecutive pixels, so every store instruction writes whole 32-byte sectors.  One
+            // running pointer (a 64-bit add per channel) instead of a 64-bit multiply per element; full chunks skip the
+            // per-channel predicate (the head map's 64 + nc channels end inside the last chunk only)
+            {
+              float* q = yf + (int64_t)c0 * HoWo;
+              if (c0 + 16 <= cvalid) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (c0 + e < cvalid) yf[(int64_t)(c0 + e) * HoWo] = v[e];
+                for (int e = 0; e < 16; ++e) { *q = v[e]; q += HoWo; }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { if (c0 + e < cvalid) *q = v[e]; q += HoWo; }
+              }
+            }
             if (p.dfl_dbox) {
               // DFL (nets/yolo_mul.py:312-322) straight from the fp32 accumulators: a 16-channel chunk of the box part is
               // one side's 16 bins -- softmax expectation in registers; the class logits are gathered into (B, nc, A)
@@ -467,22 +477,30 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
               const int cg0 = nt * p.BN + c0;
               const int64_t a = (int64_t)p.dfl_aoff + pix;
               if (cg0 < 64) {
-                float mx = v[0];
+                // max by a tree (four dependent steps instead of fifteen), exp(v - mx) as ex2(v * log2e - mx * log2e): one
+                // FFMA + one MUFU per bin, two independent accumulation chains each for the sum and the expectation
+                float m01 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), m23 = fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]));
+                float m45 = fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), m67 = fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]));
+                const float mx = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+                const float kLog2e = 1.4426950408889634f;
+                const float off = -mx * kLog2e;
+                float den0 = 0.0f, den1 = 0.0f, num0 = 0.0f, num1 = 0.0f;
 #pragma unroll
-                for (int e = 1; e < 16; ++e) mx = fmaxf(mx, v[e]);
-                float den = 0.0f, num = 0.0f;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float ex = __expf(v[e] - mx);
-                  den += ex;
-                  num = fmaf((float)e, ex, num);
+                for (int e = 0; e < 16; e += 2) {
+                  float e0, e1;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(v[e], kLog2e, off)));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(v[e + 1], kLog2e, off)));
+                  den0 += e0; den1 += e1;
+                  num0 = fmaf((float)e, e0, num0);
+                  num1 = fmaf((float)(e + 1), e1, num1);
                 }
-                p.dfl_dbox[((int64_t)n * 4 + (cg0 >> 4)) * p.dfl_A + a] = __fdividef(num, den);
+                p.dfl_dbox[((int64_t)n * 4 + (cg0 >> 4)) * p.dfl_A + a] = __fdividef(num0 + num1, den0 + den1);
               } else {
+                float* q = p.dfl_cls + ((int64_t)n * p.dfl_nc + (cg0 - 64)) * p.dfl_A + a;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                  const int c = cg0 + e - 64;
-                  if (c < p.dfl_nc) p.dfl_cls[((int64_t)n * p.dfl_nc + c) * p.dfl_A + a] = v[e];
+                  if (cg0 - 64 + e < p.dfl_nc) *q = v[e];
+                  q += p.dfl_A;
                 }
               }
             }
