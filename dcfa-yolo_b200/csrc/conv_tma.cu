@@ -90,6 +90,10 @@ struct TmaConvArgs {
   float* dfl_dbox;       // [n_img, 4, A] (nullptr: off)
   float* dfl_cls;        // [n_img, nc, A]
   int dfl_A, dfl_aoff, dfl_nc;   // total anchors, first anchor of this level, classes
+  int mc;                // 1: CTA PAIRS (cluster of 2) on two M tiles of the same weight tile: each CTA fetches half of
+                         // every W k-block and multicasts it into both CTAs' rings (W is 40-67 % of the bytes a k-block
+                         // pulls through L2 -> SM, the delivery limit of the N >= 128 layers)
+  int iters;             // loop range of the persistent roles: total_tiles, or the number of tile PAIRS with mc
   int ngroups;           // epilogue groups of four warps: 2 (generic instance) or 4 (FAST instance)
   int epi_split;         // 1: BOTH epilogue groups work on every tile, each on every other 16-channel chunk (wide
                          // tiles: halves the epilogue latency of a tile, which is exposed at the tail of every launch
@@ -163,12 +167,24 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // persistent schedule: unit u of `units` takes iterations u, u + units, ...  Without mc a unit is a CTA and an
+  // iteration a tile; with mc a unit is a CTA PAIR and iteration i covers the M tiles 2 * (i / n_tiles) + {0, 1} of
+  // n-tile i % n_tiles -- both CTAs walk the same (weight group, n-tile, k-block) sequence in lockstep.
+  uint32_t crank = 0;
+  if (p.mc) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int unit0 = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_of = [&](int it) -> int {
+    if (!p.mc) return it;
+    const int j = (int)p.div_ntiles.div((uint32_t)it);
+    return (2 * j + (int)crank) * p.n_tiles + (it - j * p.n_tiles);
+  };
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         ptx::mbar_init(bar_full + 8u * s, 1);   // one arrive.expect_tx; A and W complete through tx bytes
-        ptx::mbar_init(bar_empty + 8u * s, 1);  // one tcgen05.commit
+        ptx::mbar_init(bar_empty + 8u * s, p.mc ? 2 : 1);  // one tcgen05.commit (mc: of each CTA of the pair)
       }
       for (int a = 0; a < (int)p.acc_stages; ++a) {
         ptx::mbar_init(bar_tfull + 8u * a, 1);
@@ -186,6 +202,10 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
   ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.mc) {   // the peer's barriers must exist before anything is multicast into them
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here on
@@ -201,7 +221,9 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
       uint32_t a_dst = smem_a, b_dst = smem_b, full = bar_full, empty = bar_empty;
       const uint32_t tx_bytes = p.a_tx_bytes + p.b_tx_bytes;
       const int64_t wstep = (int64_t)p.BN * p.bk;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const uint32_t w_half = p.b_tx_bytes >> 1;   // mc: this CTA's half of every W tile
+      for (int it = unit0; it < p.iters; it += units) {
+        const int tile = tile_of(it);
         const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
         const int nt = tile - (int)rest * p.n_tiles;
         const int n = (int)p.div_tiles_img.div(rest);
@@ -221,7 +243,17 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
               ptx::mbar_wait(empty, ph ^ 1u);
               ptx::mbar_arrive_expect_tx(full, tx_bytes);
               tma_load_4d(a_dst, &tmap, c, p.pair ? tx * p.tw - 1 + dx : x0 + dx, y0 + dy, n, full);
-              ptx::bulk_g2s(b_dst, wp, p.b_tx_bytes, full);
+              if (p.mc) {
+                // half of the W tile, into the same ring slot of BOTH CTAs; each copy signals the full barrier of the
+                // CTA it lands in (a complete_tx that overtakes that CTA's expect_tx is fine: its arrival is still pending)
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                    ::"r"(b_dst + crank * w_half), "l"(reinterpret_cast<const char*>(wp) + crank * w_half), "r"(w_half), "r"(full),
+                    "h"((uint16_t)3)
+                    : "memory");
+              } else {
+                ptx::bulk_g2s(b_dst, wp, p.b_tx_bytes, full);
+              }
               TL(0, tl_it); ++tl_it;
               wp += wstep;
               a_dst += p.a_stage_bytes; b_dst += p.b_stage_bytes; full += 8u; empty += 8u;
@@ -246,7 +278,7 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
       uint32_t s = 0, ph = 0, a_lo = a_lo0, b_lo = b_lo0, full = bar_full, empty = bar_empty;
       uint32_t as = 0, aph = 0;
       [[maybe_unused]] uint32_t tl_it = 0, tl_tile = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int it = unit0; it < p.iters; it += units) {
         ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
         TL(3, tl_tile); ++tl_tile;
         ptx::tc_fence_after();
@@ -259,7 +291,12 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
           ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
           for (int k = 1; k < kk; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
             ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-          ptx::umma_commit(empty);
+          if (p.mc) {   // the ring slot is free once BOTH CTAs have consumed it: arrive on the pair's two empty barriers
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(empty), "h"((uint16_t)3) : "memory");
+          } else {
+            ptx::umma_commit(empty);
+          }
           TL(2, tl_it); ++tl_it;
           a_lo += a_step; b_lo += b_step; full += 8u; empty += 8u;
           if (++s == (uint32_t)S) {
@@ -289,8 +326,9 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
     uint32_t slab = 0;   // store slabs issued by this group (selects the staging buffer)
     [[maybe_unused]] uint32_t tl_fine = 0;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+    for (int it = unit0; it < p.iters; it += units, ++tcount) {
       if (!p.epi_split && (int)(tcount & gmask) != group) continue;
+      const int tile = tile_of(it);
       const uint32_t as = tcount & (p.acc_stages - 1u);   // accumulator stage; its parity is the group's
       const uint32_t aph = (tcount >> acc_shift) & 1u;     // the stage's use count, mod 2
       const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
@@ -550,6 +588,10 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.mc) {   // the peer may still arrive on this CTA's empty barriers: leave together
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -799,6 +841,25 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
               a.out_mode == DCFA_OUT_BF16_NHWC && !a.dfl_dbox;
   { const char* e = getenv("DCFA_CONV_FAST"); if (e && atoi(e) == 0) fast = false; }   // debug / tests: the generic instance
   int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  // ---- CTA pairs sharing every W tile by multicast.  Both CTAs of a pair must walk the same weight sequence: the M tiles
+  // 2j and 2j + 1 have to belong to the same weight group, so the tiles of a group must come in an even number.
+  a.mc = 0;
+  a.iters = a.total_tiles;
+  {
+    // OFF by default: parity-green, but measured on B200 (s, B=32) head0.0 0.079 / 0.080 ms, head0.cls1 0.070 / 0.068,
+    // dark4.0 0.067 / 0.066, head1.0 0.052 / 0.052 with / without -- halving the W bytes each SM pulls from L2 buys nothing,
+    // like the resident-weight experiments before it: the k-block rate is set by the A side (profiles/README.md, round 2).
+    const char* e = getenv("DCFA_CONV_MC");   // experiments / tests: n > 0 = CTA pairs for BN >= n
+    const int min_bn = e ? atoi(e) : 0;
+    const int64_t mtiles_group = (int64_t)a.group_imgs * a.tiles_img;
+    if (min_bn > 0 && a.BN >= min_bn && mtiles_group % 2 == 0 && a.total_tiles >= 2 && (a.b_tx_bytes >> 1) % 16 == 0 &&
+        sm_count() >= 2) {
+      a.mc = 1;
+      a.iters = a.total_tiles / 2;
+      const int pairs = a.iters < sm_count() / 2 ? a.iters : sm_count() / 2;
+      grid = 2 * pairs;
+    }
+  }
   alignas(64) CUtensorMap tmap_y;
   memset(&tmap_y, 0, sizeof(tmap_y));
   if (a.tma_store) {
@@ -817,8 +878,8 @@ int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
     const char* e = getenv("DCFA_EPI_GROUPS");   // debug: DCFA_EPI_GROUPS=2 launches the FAST instance with two groups
     a.ngroups = (e && atoi(e) == 2) ? 2 : kFastGroups;
   }
-  if (fast) launch_pdl(conv_tma_kernel<true>, dim3(grid), dim3(64 + 128 * a.ngroups), smem, st, tmap, tmap_y, a);
-  else launch_pdl(conv_tma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tmap, tmap_y, a);
+  if (fast) launch_k(conv_tma_kernel<true>, dim3(grid), dim3(64 + 128 * a.ngroups), smem, st, a.mc ? 2 : 0, true, tmap, tmap_y, a);
+  else launch_k(conv_tma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, a.mc ? 2 : 0, true, tmap, tmap_y, a);
   DCFA_CHECK_LAUNCH("conv_tma_kernel");
   return DCFA_OK;
 }

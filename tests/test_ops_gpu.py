@@ -59,15 +59,19 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("path", ["tma", "tma-staged", "gather"])
+@pytest.mark.parametrize("path", ["tma", "tma-staged", "gather", "tma-pairs"])
 @pytest.mark.parametrize("n,h,w,cin,cout,k,s,act,groups", CONV_CASES)
 def test_conv_bf16_nhwc(cuda, monkeypatch, n, h, w, cin, cout, k, s, act, groups, path):
     """both A-operand paths: TMA box loads (one k-block per tap x channel block) and the cp.async gather (flat K);
     and both store paths of the TMA kernel: 256-bit sector stores (default) and the staged tile + TMA store
-    ("tma-staged": DCFA_ST256=0, the path taken by outputs that are not 32-byte aligned)."""
+    ("tma-staged": DCFA_ST256=0, the path taken by outputs that are not 32-byte aligned); "tma-pairs": the opt-in
+    CTA-pair schedule with multicast weight tiles (DCFA_CONV_MC)."""
     from dcfa_b200 import abi
     if path == "tma-staged":
         monkeypatch.setenv("DCFA_ST256", "0")
+        path = "tma"
+    if path == "tma-pairs":   # CTA pairs (cluster of 2) multicasting each W k-block to both rings (opt-in, DCFA_CONV_MC)
+        monkeypatch.setenv("DCFA_CONV_MC", "16")
         path = "tma"
     g = torch.Generator().manual_seed(1234 + cin + cout + k + s)
     x = bf16_round(torch.randn(n, cin, h, w, generator=g))
