@@ -241,8 +241,17 @@ __global__ void __launch_bounds__(FAST ? kThreadsFast : kThreads, 1) conv_tma_ke
           for (int dx = 0; dx < nx; ++dx) {
             for (int c = 0; c < nc; c += p.bk) {
               ptx::mbar_wait(empty, ph ^ 1u);
+#ifdef DCFA_EXP_HALFW
+              ptx::mbar_arrive_expect_tx(full, p.mc ? p.a_tx_bytes + w_half : tx_bytes);
+#else
               ptx::mbar_arrive_expect_tx(full, tx_bytes);
+#endif
               tma_load_4d(a_dst, &tmap, c, p.pair ? tx * p.tw - 1 + dx : x0 + dx, y0 + dy, n, full);
+#ifdef DCFA_EXP_HALFW   // timing experiment (WRONG results): every CTA of a pair receives only ITS half of W -- what a 2-CTA MMA would pull
+              if (p.mc) {
+                ptx::bulk_g2s(b_dst + crank * w_half, reinterpret_cast<const char*>(wp) + crank * w_half, w_half, full);
+              } else
+#endif
               if (p.mc) {
                 // half of the W tile, into the same ring slot of BOTH CTAs; each copy signals the full barrier of the
                 // CTA it lands in (a complete_tx that overtakes that CTA's expect_tx is fine: its arrival is still pending)
