@@ -226,6 +226,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int launch_stem(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st);
+int launch_conv_strip(const dcfa_op& op, void* const* bufs, cudaStream_t st, bool* taken);   // 3x3 stride-1 halo-strip path
 int launch_dwconv(const dcfa_op& op, void* const* bufs, cudaStream_t st);
 int launch_chain(const dcfa_op& pw1, const dcfa_op& dw, const dcfa_op& pw2, void* const* bufs, cudaStream_t st);
 int launch_ghost(const dcfa_op& pw, const dcfa_op& dw, void* const* bufs, cudaStream_t st);

@@ -650,6 +650,11 @@ void pick_tile(int Ho, int Wo, int* tw_out, int* th_out) {
 
 // Returns DCFA_OK after launching, or a negative code.  Called by launch_conv when the op was packed for TMA.
 int launch_conv_tma(const dcfa_op& op, void* const* bufs, cudaStream_t st) {
+  {   // 3x3 stride-1 SiLU layers: nine taps from one shared-memory strip (conv_strip.cu) when the shape qualifies
+    bool taken = false;
+    const int rc = launch_conv_strip(op, bufs, st, &taken);
+    if (taken) return rc;
+  }
   TmaConvArgs a;
   View<const __nv_bfloat16> x = resolve<const __nv_bfloat16>(op.x, bufs);
   a.res = resolve<const __nv_bfloat16>(op.x2, bufs);

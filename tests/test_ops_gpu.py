@@ -56,19 +56,27 @@ CONV_CASES = [
     (1, 22, 38, 64, 32, 3, 2, 0, 1),    # stride 2, even width, partial tiles on the right / bottom edge
     (4, 20, 20, 64, 64, 1, 1, 2, 2),    # 1x1, two weight groups: flattened pixel tiling, 7 tiles per group (partial last)
     (6, 40, 40, 128, 256, 1, 1, 2, 2),  # 1x1 at 40x40 (the neck's shape): 38 flattened tiles per group instead of 3 x 14
+    (2, 80, 80, 128, 192, 3, 1, 2, 1),  # head0.0's shape: halo-strip path, 5-row strips, 4 weight stages
+    (2, 20, 20, 512, 192, 3, 1, 2, 1),  # head2.0's shape: 8 channel blocks per tile, 9-row strips
+    (3, 13, 27, 64, 64, 3, 1, 2, 1),    # strip path, odd sizes: tiles that start and end inside a row, N = 64 (groups alternate tiles)
+    (2, 40, 40, 256, 128, 3, 1, 2, 2),  # strip path, two weight groups, 4 channel blocks
 ]
 
 
-@pytest.mark.parametrize("path", ["tma", "tma-staged", "gather", "tma-pairs"])
+@pytest.mark.parametrize("path", ["tma", "tma-staged", "gather", "tma-pairs", "tma-nostrip"])
 @pytest.mark.parametrize("n,h,w,cin,cout,k,s,act,groups", CONV_CASES)
 def test_conv_bf16_nhwc(cuda, monkeypatch, n, h, w, cin, cout, k, s, act, groups, path):
     """both A-operand paths: TMA box loads (one k-block per tap x channel block) and the cp.async gather (flat K);
     and both store paths of the TMA kernel: 256-bit sector stores (default) and the staged tile + TMA store
     ("tma-staged": DCFA_ST256=0, the path taken by outputs that are not 32-byte aligned); "tma-pairs": the opt-in
-    CTA-pair schedule with multicast weight tiles (DCFA_CONV_MC)."""
+    CTA-pair schedule with multicast weight tiles (DCFA_CONV_MC); "tma-nostrip": DCFA_CONV_STRIP=0 (by default the 3x3 stride-1
+    SiLU cases with Cin % 64 == 0 run on the halo-strip kernel)."""
     from dcfa_b200 import abi
     if path == "tma-staged":
         monkeypatch.setenv("DCFA_ST256", "0")
+        path = "tma"
+    if path == "tma-nostrip":   # 3x3 stride-1 SiLU layers on the tap-box kernel instead of the halo-strip kernel (conv_strip.cu)
+        monkeypatch.setenv("DCFA_CONV_STRIP", "0")
         path = "tma"
     if path == "tma-pairs":   # CTA pairs (cluster of 2) multicasting each W k-block to both rings (opt-in, DCFA_CONV_MC)
         monkeypatch.setenv("DCFA_CONV_MC", "16")
