@@ -57,6 +57,7 @@ struct StripArgs {
   int H, W, P;            // P = W + 2: pitch of the flattened padded image
   int Cout, BN, n_tiles, cblocks;
   int NR;                 // padded rows per strip box
+  int MT;                 // M tiles (128 positions each) per pass: every weight k-block feeds MT accumulators
   int tiles_img, total_tiles;
   int wstages;
   uint32_t strip_bytes, strip_tx, w_stage_bytes, w_tx_bytes;   // strip_bytes: ring pitch (multiple of 1024); strip_tx: bytes one box delivers
@@ -75,6 +76,8 @@ __device__ __forceinline__ void strip_tma_load(uint32_t dst, const CUtensorMap* 
 // floor(a / b) for b > 0 and any a
 __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
+// MT = M tiles per pass, compile time: the MMA-issuing thread is a serial instruction stream, a runtime loop there costs more than the MMAs
+template <int MT>
 __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __grid_constant__ CUtensorMap tmap, const StripArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
     const uint32_t rest = p.div_ntiles.div((uint32_t)tile);
     nt = tile - (int)rest * p.n_tiles;
     n = (int)p.div_tiles_img.div(rest);
-    q0 = ((int)rest - n * p.tiles_img) * 128;
+    q0 = ((int)rest - n * p.tiles_img) * 128 * MT;
   };
 
   if (warp == kStripWarp) {
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
         const uint32_t row0 = (uint32_t)(q0 - 1 - r0 * p.P);   // strip row of tap (0, 0) of the tile's first position
         ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.BN;
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)(MT * p.BN);
         for (int cb = 0; cb < p.cblocks; ++cb) {
           ptx::mbar_wait(bar_sfull + 8u * u, uph);
           ptx::tc_fence_after();
@@ -182,8 +185,12 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
             const uint64_t adesc = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
             const uint64_t bdesc = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+            for (int m = 0; m < MT; ++m) {   // +128 strip rows = +1024 in the (address >> 4) field
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(1024 * m + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                               (cb | tap | k) ? 1u : 0u);
+            }
             ptx::umma_commit(bar_wempty + 8u * s);
             if (++s == (uint32_t)p.wstages) { s = 0; sph ^= 1u; }
           }
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
     const int gtid = r;
     float* sb = reinterpret_cast<float*>(smem_raw + (sb_base - ptx::smem_u32(smem_raw))) + group * 512;
     int sb_key = -1;
-    const uint32_t acc_shift = p.acc_stages == 4u ? 2u : 1u;
+    const uint32_t acc_shift = p.acc_stages == 4u ? 2u : (p.acc_stages == 2u ? 1u : 0u);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       if (!p.epi_split && (int)(tcount & 1u) != group) continue;
@@ -211,10 +218,6 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
       int nt, n, q0;
       decode(tile, nt, n, q0);
       const int g = n / p.group_imgs;
-      const int q = q0 + r;
-      const int yy = (int)p.div_P.div((uint32_t)q);
-      const int xp = q - yy * p.P;
-      const bool rvalid = xp >= 1 && xp <= p.W && yy < p.H;   // the two pad columns and the tail of the last tile are not outputs
       if (g * p.n_tiles + nt != sb_key) {
         sb_key = g * p.n_tiles + nt;
         ptx::named_bar_sync(1 + group, 128);
@@ -224,13 +227,19 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
         for (int c = gtid; c < p.BN; c += 128) { sb[c] = 0.5f * __ldg(sc + c); sb[256 + c] = 0.5f * __ldg(bi + c); }
         ptx::named_bar_sync(1 + group, 128);
       }
-      __nv_bfloat16* yb = nullptr;
-      if (rvalid) yb = p.y.p + p.y.img_off(n) + (int64_t)(yy * p.W + xp - 1) * p.y.ld + nt * p.BN;
       const int cvalid = min(p.BN, p.Cout - nt * p.BN);
       ptx::mbar_wait(bar_tfull + 8u * as, aph);
       ptx::tc_fence_after();
-      const uint32_t taddr0 = tmem_base + as * (uint32_t)p.BN + ((uint32_t)(q4 * 32) << 16);
       const int nchunks = p.BN >> 4;
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+      const int q = q0 + m * 128 + r;
+      const int yy = (int)p.div_P.div((uint32_t)q);
+      const int xp = q - yy * p.P;
+      const bool rvalid = xp >= 1 && xp <= p.W && yy < p.H;   // the two pad columns and the tail of the last tile are not outputs
+      __nv_bfloat16* yb = nullptr;
+      if (rvalid) yb = p.y.p + p.y.img_off(n) + (int64_t)(yy * p.W + xp - 1) * p.y.ld + nt * p.BN;
+      const uint32_t taddr0 = tmem_base + as * (uint32_t)(MT * p.BN) + (uint32_t)(m * p.BN) + ((uint32_t)(q4 * 32) << 16);
       uint32_t accA[16], accB[16];
       auto compute = [&](const uint32_t (&a)[16], const int j, float (&v)[16]) {
         const int c0 = j * 16;
@@ -282,6 +291,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
           __syncwarp();
         }
       }
+      }   // m
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8u * as);
@@ -348,26 +358,41 @@ int launch_conv_strip(const dcfa_op& op, void* const* bufs, cudaStream_t st, boo
   a.cblocks = op.Cin / 64;
   if (a.BN < 16 || a.BN > 256 || a.BN % 16 != 0 || op.k_blocks != 9 * a.cblocks || a.n_img % a.group_imgs != 0) return DCFA_OK;
   // rows of the padded image a strip must hold: positions q0 - 1 ... q0 + 128 + 2P, starting anywhere inside a row
-  a.NR = (a.P - 1 + 130 + 2 * a.P) / a.P + 1;
-  if (a.NR > 256) return DCFA_OK;
-  a.strip_tx = (uint32_t)a.NR * a.P * 128u;
-  a.strip_bytes = (a.strip_tx + 1023u) & ~1023u;
   a.w_tx_bytes = (uint32_t)a.BN * 128u;
   a.w_stage_bytes = (a.w_tx_bytes + 1023u) & ~1023u;
   const int max_smem = 227 * 1024;
   const int fixed = 1024 + 512 + 4096 + 1024;
-  int wst = (max_smem - fixed - kStripUnits * (int)a.strip_bytes) / (int)a.w_stage_bytes;
-  if (wst > kMaxWStages) wst = kMaxWStages;
-  if (wst < 3) return DCFA_OK;   // not enough shared memory for a useful weight ring: leave it to the tap-box kernel
-  a.wstages = wst;
-  a.tiles_img = (a.H * a.P + 127) / 128;
+  // Two M tiles per pass when their accumulators fit TMEM and the bigger strips still leave a weight ring: with the A side
+  // served from the strip, the weight tiles are what an SM pulls from L2 (9 * cblocks * BN * 128 bytes per pass), and
+  // every k-block then feeds twice the MMAs.
+  // Measured (B200, s, B=32): two tiles per pass pay for BN <= 128 (two accumulator stages remain: head0.cls1 0.080 -> 0.065 ms,
+  // head0.box1 0.044 -> 0.035) and lose for BN = 192 (one stage: the epilogue is exposed, head0.0 0.086 -> 0.094) and when
+  // the halved number of passes no longer fills the SMs (20 x 20 maps: head2.0 0.033 -> 0.047).
+  const int64_t passes2 = (int64_t)a.n_img * a.n_tiles * (((int64_t)a.H * a.P + 255) / 256);
+  int mt_max = (4 * a.BN <= 512 && passes2 >= sm_count()) ? 2 : 1;
+  { const char* e = getenv("DCFA_STRIP_MT"); if (e && (atoi(e) == 1 || atoi(e) == 2)) mt_max = 2 * a.BN <= 512 ? atoi(e) : 1; }   // debug
+  a.MT = 0;
+  for (int mt = mt_max; mt >= 1; --mt) {
+    const int nr = (a.P - 1 + 128 * mt + 2 + 2 * a.P) / a.P + 1;
+    const uint32_t tx = (uint32_t)nr * a.P * 128u;
+    const uint32_t pitch = (tx + 1023u) & ~1023u;
+    int wst = (max_smem - fixed - kStripUnits * (int)pitch) / (int)a.w_stage_bytes;
+    if (wst > kMaxWStages) wst = kMaxWStages;
+    if (nr <= 256 && wst >= 3) {
+      a.MT = mt; a.NR = nr; a.strip_tx = tx; a.strip_bytes = pitch; a.wstages = wst;
+      break;
+    }
+  }
+  if (a.MT == 0) return DCFA_OK;   // not enough shared memory for a useful weight ring: leave it to the tap-box kernel
+  a.tiles_img = (a.H * a.P + 128 * a.MT - 1) / (128 * a.MT);
   const int64_t total = (int64_t)a.n_img * a.tiles_img * a.n_tiles;
   if (total >= (1ll << 31)) return DCFA_OK;
   a.total_tiles = (int)total;
-  a.acc_stages = 4 * a.BN <= 512 ? 4u : 2u;
-  a.epi_split = a.BN >= 128 ? 1 : 0;
+  const int pass_cols = a.MT * a.BN;
+  a.acc_stages = 4 * pass_cols <= 512 ? 4u : (2 * pass_cols <= 512 ? 2u : 1u);
+  a.epi_split = pass_cols >= 128 ? 1 : 0;   // both groups share every pass (the alternate mode needs >= 2 accumulator stages)
   uint32_t cols = 32;
-  while (cols < a.acc_stages * (uint32_t)a.BN) cols <<= 1;
+  while (cols < a.acc_stages * (uint32_t)pass_cols) cols <<= 1;
   a.tmem_cols = cols;
   a.div_P = make_fastdiv_s((uint32_t)a.P);
   a.div_tiles_img = make_fastdiv_s((uint32_t)a.tiles_img);
@@ -389,13 +414,15 @@ int launch_conv_strip(const dcfa_op& op, void* const* bufs, cudaStream_t st, boo
   if (cr != CUDA_SUCCESS) return fail(DCFA_E_CUDA, "conv(strip): cuTensorMapEncodeTiled failed with %d", (int)cr);
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return fail(DCFA_E_CUDA, "conv(strip): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set.mark();
   }
   const int smem = fixed + kStripUnits * (int)a.strip_bytes + a.wstages * (int)a.w_stage_bytes;
   const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
-  launch_pdl(conv_strip_kernel, dim3(grid), dim3(kStripThreads), smem, st, tmap, a);
+  if (a.MT == 2) launch_pdl(conv_strip_kernel<2>, dim3(grid), dim3(kStripThreads), smem, st, tmap, a);
+  else launch_pdl(conv_strip_kernel<1>, dim3(grid), dim3(kStripThreads), smem, st, tmap, a);
   DCFA_CHECK_LAUNCH("conv_strip_kernel");
   return DCFA_OK;
 }
