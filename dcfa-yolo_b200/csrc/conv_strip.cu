@@ -176,11 +176,13 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
           ptx::mbar_wait(bar_sfull + 8u * u, uph);
           ptx::tc_fence_after();
           const uint32_t strip = s_strip + u * p.strip_bytes;
-          for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_row0 = strip + row0 * 128u;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {   // unrolled: dy, dx are constants, the tap offset is one add
             const int dy = tap / 3, dx = tap - dy * 3;
             ptx::mbar_wait(bar_wfull + 8u * s, sph);
             ptx::tc_fence_after();
-            const uint32_t a_addr = strip + (row0 + (uint32_t)(dy * p.P + dx)) * 128u;
+            const uint32_t a_addr = a_row0 + (uint32_t)(dy * p.P + dx) * 128u;
             const uint32_t b_addr = s_w + s * p.w_stage_bytes;
             const uint64_t adesc = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
             const uint64_t bdesc = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
