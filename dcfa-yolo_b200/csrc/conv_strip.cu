@@ -369,7 +369,8 @@ int launch_conv_strip(const dcfa_op& op, void* const* bufs, cudaStream_t st, boo
   // every k-block then feeds twice the MMAs.
   // Measured (B200, s, B=32): two tiles per pass pay for BN <= 128 (two accumulator stages remain: head0.cls1 0.080 -> 0.065 ms,
   // head0.box1 0.044 -> 0.035) and lose for BN = 192 (one stage: the epilogue is exposed, head0.0 0.086 -> 0.094) and when
-  // the halved number of passes no longer fills the SMs (20 x 20 maps: head2.0 0.033 -> 0.047).
+  // the halved number of passes no longer fills the SMs (20 x 20 maps: head2.0 0.033 -> 0.047).  Packing head*.0 as two
+  // n-tiles of 96 columns so that it could take two tiles per pass was measured too: head0.0 0.082 (unchanged), head1.0 0.049 -> 0.057.
   const int64_t passes2 = (int64_t)a.n_img * a.n_tiles * (((int64_t)a.H * a.P + 255) / 256);
   int mt_max = (4 * a.BN <= 512 && passes2 >= sm_count()) ? 2 : 1;
   { const char* e = getenv("DCFA_STRIP_MT"); if (e && (atoi(e) == 1 || atoi(e) == 2)) mt_max = 2 * a.BN <= 512 ? atoi(e) : 1; }   // debug

@@ -18,9 +18,9 @@ def fold_bn(bn):
     return scale, b - mean * scale
 
 
-def conv_tiling(cout):
-    """(BN, n_tiles) for a conv with `cout` output channels: UMMA N must be a multiple of 16 in [16, 256]."""
-    n_tiles = max(1, math.ceil(cout / 256))
+def conv_tiling(cout, max_bn=256):
+    """(BN, n_tiles) for a conv with `cout` output channels: UMMA N must be a multiple of 16 in [16, max_bn <= 256]."""
+    n_tiles = max(1, math.ceil(cout / max_bn))
     bn = 16 * math.ceil(math.ceil(cout / n_tiles) / 16)
     return bn, n_tiles
 
@@ -63,14 +63,14 @@ def pack_conv_weight_pair(w):
     return torch.cat(tiles), meta
 
 
-def pack_conv_weight(w, bk=None):
+def pack_conv_weight(w, bk=None, max_bn=256):
     """w: [Cout, Cin, k, k] fp32 (input channels already in PHYSICAL order) ->
     (packed bf16 [n_tiles*k_blocks*BN*bk], meta dict).  K index = (ky*k + kx)*Cin + ci.
     bk > 0: one k-block per (tap, channel block of bk) -- the TMA path; bk == 0: flat K padded to 64 (gather path)."""
     cout, cin, k, _ = w.shape
     if bk is None:
         bk = pick_bk(cin)
-    bn, n_tiles = conv_tiling(cout)
+    bn, n_tiles = conv_tiling(cout, max_bn)
     k_real = k * k * cin
     tile_k = bk if bk else BK
     k_blocks = math.ceil(k_real / tile_k)
