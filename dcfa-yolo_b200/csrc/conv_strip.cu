@@ -47,6 +47,15 @@ FastDivS make_fastdiv_s(uint32_t d) {
   return f;
 }
 
+#ifdef DCFA_TIMELINE
+// debug build only: clock64 timestamps of CTA 0 (rows: 0 strip issue, 1 strip landed (seen by MMA), 2 W issue, 3 W landed, 4 MMA
+// k-block issued, 5 tile start (MMA), 6 epilogue tfull / done pairs), read back by tools/tl_strip.py
+__device__ long long g_tls[8][4096];
+#define TLS(role, idx) do { if (blockIdx.x == 0 && (idx) < 4096) g_tls[role][idx] = clock64(); } while (0)
+#else
+#define TLS(role, idx) do { } while (0)
+#endif
+
 struct StripArgs {
   View<__nv_bfloat16> y;
   const __nv_bfloat16* w;
@@ -72,9 +81,6 @@ __device__ __forceinline__ void strip_tma_load(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(bar)
       : "memory");
 }
-
-// floor(a / b) for b > 0 and any a
-__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 // MT = M tiles per pass, compile time: the MMA-issuing thread is a serial instruction stream, a runtime loop there costs more than the MMAs
 template <int MT>
@@ -126,12 +132,14 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
     // ------------------------------------------------------------------ strip producer
     if (ptx::elect_one()) {
       uint32_t u = 0, ph = 0;
+      [[maybe_unused]] uint32_t tl = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, q0;
         decode(tile, nt, n, q0);
-        const int r0 = floor_div(q0 - 1, p.P);   // first padded row of the strip (padded row r = image row r - 1)
+        const int r0 = q0 == 0 ? -1 : (int)p.div_P.div((uint32_t)(q0 - 1));   // first padded row of the strip (padded row r = image row r - 1)
         for (int cb = 0; cb < p.cblocks; ++cb) {
           ptx::mbar_wait(bar_sempty + 8u * u, ph ^ 1u);
+          TLS(0, tl); ++tl;
           ptx::mbar_arrive_expect_tx(bar_sfull + 8u * u, p.strip_tx);
           strip_tma_load(s_strip + u * p.strip_bytes, &tmap, cb * 64, -1, r0 - 1, n, bar_sfull + 8u * u);
           if (++u == kStripUnits) { u = 0; ph ^= 1u; }
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
     // ------------------------------------------------------------------ weight producer
     if (ptx::elect_one()) {
       uint32_t s = 0, ph = 0;
+      [[maybe_unused]] uint32_t tl = 0;
       const int64_t wstep = (int64_t)p.BN * 64;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, q0;
@@ -151,6 +160,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(bar_wempty + 8u * s, ph ^ 1u);
+            TLS(2, tl); ++tl;
             ptx::mbar_arrive_expect_tx(bar_wfull + 8u * s, p.w_tx_bytes);
             ptx::bulk_g2s(s_w + s * p.w_stage_bytes, wt + (int64_t)(tap * p.cblocks + cb) * wstep, p.w_tx_bytes, bar_wfull + 8u * s);
             if (++s == (uint32_t)p.wstages) { s = 0; ph ^= 1u; }
@@ -164,16 +174,19 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
       // K-major SWIZZLE_128B descriptor: LBO field 1, SBO = 1024 bytes (8 rows), version bit 46, layout type 2
       const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       uint32_t u = 0, uph = 0, s = 0, sph = 0, as = 0, aph = 0;
+      [[maybe_unused]] uint32_t tl_u = 0, tl_w = 0, tl_t = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, q0;
         decode(tile, nt, n, q0);
-        const int r0 = floor_div(q0 - 1, p.P);
+        const int r0 = q0 == 0 ? -1 : (int)p.div_P.div((uint32_t)(q0 - 1));
         const uint32_t row0 = (uint32_t)(q0 - 1 - r0 * p.P);   // strip row of tap (0, 0) of the tile's first position
         ptx::mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
+        TLS(5, tl_t); ++tl_t;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * (uint32_t)(MT * p.BN);
         for (int cb = 0; cb < p.cblocks; ++cb) {
           ptx::mbar_wait(bar_sfull + 8u * u, uph);
+          TLS(1, tl_u); ++tl_u;
           ptx::tc_fence_after();
           const uint32_t strip = s_strip + u * p.strip_bytes;
           const uint32_t a_row0 = strip + row0 * 128u;
@@ -181,6 +194,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
           for (int tap = 0; tap < 9; ++tap) {   // unrolled: dy, dx are constants, the tap offset is one add
             const int dy = tap / 3, dx = tap - dy * 3;
             ptx::mbar_wait(bar_wfull + 8u * s, sph);
+            TLS(3, tl_w);
             ptx::tc_fence_after();
             const uint32_t a_addr = a_row0 + (uint32_t)(dy * p.P + dx) * 128u;
             const uint32_t b_addr = s_w + s * p.w_stage_bytes;
@@ -194,6 +208,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
                                (cb | tap | k) ? 1u : 0u);
             }
             ptx::umma_commit(bar_wempty + 8u * s);
+            TLS(4, tl_w); ++tl_w;
             if (++s == (uint32_t)p.wstages) { s = 0; sph ^= 1u; }
           }
           ptx::umma_commit(bar_sempty + 8u * u);
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
       }
       const int cvalid = min(p.BN, p.Cout - nt * p.BN);
       ptx::mbar_wait(bar_tfull + 8u * as, aph);
+      if (group == 0 && q4 == 0 && lane == 0) TLS(6, 2 * tcount);
       ptx::tc_fence_after();
       const int nchunks = p.BN >> 4;
 #pragma unroll 1
@@ -294,6 +310,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) conv_strip_kernel(const __gr
         }
       }
       }   // m
+      if (group == 0 && q4 == 0 && lane == 0) TLS(6, 2 * tcount + 1);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8u * as);
@@ -431,3 +448,13 @@ int launch_conv_strip(const dcfa_op& op, void* const* bufs, cudaStream_t st, boo
 }
 
 }  // namespace dcfa
+
+#ifdef DCFA_TIMELINE
+extern "C" int dcfa_debug_read_strip_timeline(void* dst, int bytes) {
+  return cudaMemcpyFromSymbol(dst, dcfa::g_tls, bytes) == cudaSuccess ? 0 : -2;
+}
+extern "C" int dcfa_debug_clear_strip_timeline() {
+  static long long zeros[8][4096];
+  return cudaMemcpyToSymbol(dcfa::g_tls, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -2;
+}
+#endif
