@@ -646,7 +646,7 @@ def run_ours(args):
             traffic = tj["dram_bytes_read_per_step"] + tj["dram_bytes_write_per_step"]
     except (OSError, KeyError, ValueError):
         pass
-    roofline = {"bound": "tensor", "kernel": "conv_tma_kernel", "achieved": round(achieved, 2), "peak": peaks["tflops"],
+    roofline = {"bound": "tensor", "kernel": "conv_tma_kernel (+ conv_strip_kernel for the head's 3x3 stride-1 layers)", "achieved": round(achieved, 2), "peak": peaks["tflops"],
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic,
                 "traffic_note": "DRAM read+write bytes summed over the step's conv launches (ncu, cold caches); achieved = "
                                 "algorithmic conv FLOPs of the step / summed conv launch time", "peak_source": peaks["src"],

@@ -70,7 +70,7 @@ for r in foreign:
     print("foreign kernel: %s  %.2f us" % (r[col["Kernel Name"]][:80], float(r[col["gpu__time_duration.sum"]])))
 print("total time_us %.1f over %d launches" % (sum(a[1] for a in tot.values()), len(body)))
 if len(sys.argv) > 4:
-    json.dump({"kernel": "conv_tma_kernel", "phi": units["phi"], "batch": units["batch"], "size": units["size"],
+    json.dump({"kernel": "conv_tma_kernel + conv_strip_kernel", "phi": units["phi"], "batch": units["batch"], "size": units["size"],
                "launches_per_step": conv_n, "dram_bytes_read_per_step": int(conv_rd), "dram_bytes_write_per_step": int(conv_wr),
                "source": "%s (ncu --set full --clock-control none over one step launched by tools/ncu_step.py, one launch per "
                          "layer, cold caches) summed over the %d records bench.py times as 'conv'" % (out, conv_n)},
